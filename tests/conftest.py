@@ -1,0 +1,40 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    has_gpu = torch.cuda.is_available()
+    has_ref = os.path.isfile("/root/reference/model.py")
+    for item in items:
+        if "gpu" in item.keywords and not has_gpu:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "reference" in item.keywords and not has_ref:
+            item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+
+
+def load_golden(name):
+    import numpy as np
+    import torch
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    W = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("W/")}
+    G = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("G/")}
+    return z, W, G
+
+
+@pytest.fixture(scope="session")
+def golden_loader():
+    return load_golden
