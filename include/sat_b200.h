@@ -1,0 +1,173 @@
+/* sat_b200.h -- C ABI of libsat_b200.so: the B200 (sm_100a) implementation of the
+ * Show-Attend-and-Tell per-timestep decoder hot path.
+ *
+ * The reference (Lukeasargen/Show-Attend-and-Tell-Pytorch-Lightning) is pure Python and has
+ * no FFI; the "interface" each entry point replaces is therefore a span of the reference's
+ * model.py / util.py, cited per function below.  The Python host (sat_b200/model.py) mirrors
+ * the reference's module/LightningModule API on top of these calls via ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer into caller-owned memory (torch tensors in practice);
+ *    nothing is allocated, freed or retained by the library;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync;
+ *  - return 0 on success, SAT_ERR_INVALID (<0) for a bad argument / unsupported shape,
+ *    >0 for a cudaError_t; sat_last_error() gives a thread-local message;
+ *  - results are deterministic (no floating-point atomics);
+ *  - dtype is the operand/storage type of activations and packed weights (SAT_F32 or
+ *    SAT_BF16); accumulation, cell state, softmax, losses are always fp32;
+ *  - shapes: B caption rows (= Bi images * ncap), L locations, D encoder_dim, A attention_dim,
+ *    E embed_dim, H decoder_dim, V vocab, T decoder steps.  D, A, E, H, V must be multiples of 8.
+ *  - "gate-interleaved": row 4*j+g of a packed LSTM weight is row g*H+j of the torch weight
+ *    (g = 0..3 for i,f,g,o), so the four gates of hidden unit j are adjacent output columns.
+ */
+#ifndef SAT_B200_H_
+#define SAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAT_F32 0
+#define SAT_BF16 1
+#define SAT_ERR_INVALID (-1)
+
+#define SAT_ABI_VERSION 1
+
+typedef struct SatDims {
+  int32_t B, Bi, ncap;
+  int32_t L, D, A, E, H, V, T;
+  int32_t dtype;      /* SAT_F32 | SAT_BF16 */
+  int32_t exact;      /* 1: libm-accurate tanh/exp (fp32 parity mode); 0: MUFU approximations */
+  int32_t use_tc;     /* 1: tcgen05 tensor-core GEMMs where the shape allows (bf16 only); 0: SIMT FFMA GEMMs */
+  int32_t reserved;
+} SatDims;
+
+/* Packed decoder weights (device).  "s" = storage dtype of SatDims.dtype. */
+typedef struct SatWeights {
+  const void* Wa;      /* [A,D] s      attention.encoder_att.weight               model.py:90  */
+  const void* Whcat;   /* [A+D+4H+E,H] s: attention.decoder_att.weight | beta.0.weight |
+                          lstm.weight_hh_l0 (gate-interleaved) | output.hidden.weight           */
+  const float* bhcat;  /* [A+D+4H+E]:   0 | beta.0.bias | 0 | 0                                 */
+  const void* Wihz;    /* [4H,D] s     lstm.weight_ih_l0[:, E:], gate-interleaved               */
+  const void* Wihe;    /* [4H,E] s     lstm.weight_ih_l0[:, :E], gate-interleaved               */
+  const float* bg;     /* [4H]         bias_ih_l0 + bias_hh_l0, gate-interleaved                */
+  const void* Whozo;   /* [E,H+D] s    output.hidden.weight | output.context.weight             */
+  const void* Wo;      /* [V,E] s      output.output.weight                                     */
+  const float* bo;     /* [V] or NULL  output.output.bias (NULL when weight-tied)               */
+  const float* wf;     /* [A]          attention.f_att.weight                                   */
+  const void* Emb;     /* [V,E] s      embedding.weight                                         */
+  const void* Wfact;   /* [E,D] s      init_lstm.factorize.weight                               */
+  const float* bfact;  /* [E]                                                                   */
+  const void* Winit;   /* [2H,E] s     init_lstm.init.weight                                    */
+  const float* binit;  /* [2H]                                                                  */
+  /* transposed copies, used by the backward pass only (may be NULL for inference) */
+  const void* WoT;     /* [E,V] s */
+  const void* WhozoT;  /* [H+D,E] s */
+  const void* WihzT;   /* [D,4H] s */
+  const void* WiheT;   /* [E,4H] s */
+  const void* WhcatT;  /* [H,A+D+4H] s  (first three row blocks of Whcat, transposed) */
+  const void* WaT;     /* [D,A] s */
+  const void* WinitT;  /* [E,2H] s */
+  const void* WfactT;  /* [D,E] s */
+} SatWeights;
+
+/* Buffers of one teacher-forced training step.  fwd = written by sat_train_forward and read by
+ * sat_train_backward; bwd = written by sat_train_backward. */
+typedef struct SatTrainBuffers {
+  /* inputs */
+  const void* ann;       /* [Bi,L,D] s   annotations: channels-last view of get_encoder's [Bi,D,h,w] (model.py:483) */
+  const int32_t* caps;   /* [B,T+1]      encoded captions, column 0 = <START>                     */
+  const int32_t* lens;   /* [B]          number of targets per caption (model.py:492)             */
+  /* fwd */
+  void* P;               /* [Bi,L,A] s   W_a * a, once per image (reference recomputes per step, model.py:100) */
+  void* meanv;           /* [Bi,D] s     mean over locations (model.py:78)                        */
+  void* f1;              /* [Bi,E] s     init_lstm.factorize output                               */
+  float* init_out;       /* [Bi,2H]      init_lstm.init output before the [2,B,H] reinterpretation */
+  /* per-step buffers are TIME-MAJOR (row m = t*B + b): each step's slice is a contiguous GEMM
+   * operand, and the whole-sequence projections are single GEMMs with M = T*B. */
+  void* Xe;              /* [T,B,E] s    embedded previous words                                  */
+  float* Gx;             /* [T,B,4H]     Xe * Wihe^T + bg                                          */
+  void* Hs;              /* [T+1,B,H] s  hidden state before step t at [t] (Hs[0] = h0)           */
+  float* Cs;             /* [T+1,B,H]    cell state                                               */
+  float* hp;             /* [B,A+D+4H]   per-step scratch: q | beta_pre | W_hh h                   */
+  float* Q;              /* [T,B,A]      q_t = W_h h_t (saved for backward)                        */
+  float* alphas;         /* [B,T,L]      attention weights (batch-major, the reference's return layout);
+                                         zeros where t >= lens[b] (model.py:534)                   */
+  void* Z;               /* [T,B,D] s    context z_t                                               */
+  void* GZ;              /* [T,B,D] s    beta_t * z_t  (LSTM input)                                */
+  void* Beta;            /* [T,B,D] s    beta_t                                                    */
+  void* Gates;           /* [T,B,4H] s   post-activation i,f,g,o (gate-interleaved)                */
+  void* Xo;              /* [T,B,E] s    tanh(Xe + W_ho h' + W_zo z)                               */
+  void* logits;          /* [T,B,V]      s, or fp32 when logits_f32 != 0; zeros where inactive     */
+  void* dlogits;         /* [T,B,V] s    (softmax - target dist)/N_tok; may alias `logits` when the
+                                         caller does not need the logits back; NULL = not wanted   */
+  float* row_loss;       /* [T,B]        per-token loss (0 where inactive)                         */
+  int32_t* row_argmax;   /* [T,B]        argmax_v logits (-1 where inactive)                       */
+  float* S;              /* [B,L]        sum_t alphas                                              */
+  float* out;            /* [8]          loss, cross-entropy part, doubly-stochastic part, accuracy, 1/N_tok, N_tok */
+  /* bwd */
+  const float* gscale;   /* [1]          upstream d(loss) (device scalar)                          */
+  void* dpre;            /* [T,B,E] s    grad wrt deep-output pre-activation                       */
+  float* dHZ;            /* [T,B,H+D]    dpre * [W_ho|W_zo]                                        */
+  void* DY;              /* [T,B,A+D+4H] s: dq | dbeta_pre | dG (gate-interleaved)                 */
+  float* dgz;            /* [B,D]        per-step scratch                                          */
+  float* dh;             /* [B,H]        running grad wrt h                                        */
+  float* dc;             /* [B,H]        running grad wrt c                                        */
+  void* dZ;              /* [T,B,D] s    total grad wrt z_t (for d_ann)                            */
+  float* dP;             /* [B,L,A]      accumulated grad wrt P                                    */
+  float* dwf_part;       /* [T,B,A]      per-(b,t) partial of d f_att.weight                       */
+  float* dXe;            /* [T,B,E]      grad wrt embedded words                                   */
+  float* d_init_out;     /* [Bi,2H]                                                               */
+  float* df1;            /* [Bi,E]                                                                */
+  float* dmean;          /* [Bi,D]                                                                */
+  void* d_ann;           /* [Bi,L,D] s   grad wrt annotations                                      */
+  /* scalars */
+  float label_smoothing;
+  float att_gamma;
+  int32_t logits_f32;    /* logits buffer is fp32 (API path: train_batch returns fp32 logits, model.py:504) */
+  int32_t reserved;
+} SatTrainBuffers;
+
+int sat_version(void);
+const char* sat_last_error(void);
+/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers */
+int sat_abi_sizeof(int which);
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
+unsigned long long sat_launch_count(void);
+
+/* C[M,N] (ldc) = A[M,K] (lda) * W[N,K]^T (ldw) + bias[N] (optional).  a/w dtype = dtype, C fp32 when
+ * c_f32 != 0 else dtype.  The GEMM core shared by every projection below; exported for unit tests.
+ * Replaces torch.nn.Linear call sites model.py:72-73,90-92,119-123,188. */
+int sat_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+               int32_t M, int32_t N, int32_t K, int32_t dtype, int32_t c_f32, int32_t use_tc, void* stream);
+
+/* Once per image: P = ann * Wa^T (model.py:100), mean over L (model.py:78), factorize/init Linear
+ * layers (model.py:79) and the [B,2H] -> [2,B,H] state reinterpretation (model.py:79-80) into
+ * h0 [B,H] (s) / c0 [B,H] (fp32). */
+int sat_prepare_images(const SatDims* d, const SatWeights* w, const void* ann, void* P, void* meanv, void* f1,
+                       float* init_out, void* h0, float* c0, void* stream);
+
+/* One decoder time step, attention part (SoftAttention.forward model.py:94-109 + beta gate
+ * model.py:187-192,538-541), rows with t < lens[b] only.
+ *   hp [B,ldhp] fp32 holds q (cols 0..A) and beta_pre (cols A..A+D) for this step.
+ *   Writes alpha[b,:] (row stride ld_alpha), z, beta*z, beta (row strides ld_z). */
+int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, const float* wf, const float* hp,
+                           int64_t ldhp, const int32_t* lens, int32_t t, float* alpha, int64_t ld_alpha, void* z,
+                           void* gz, void* beta, int64_t ld_z, void* stream);
+
+/* Whole teacher-forced forward + loss: SAT.train_batch (model.py:474-557) with epsilon = 1,
+ * LabelSmoothing (util.py:105-112), doubly-stochastic term and accuracy (model.py:592-597). */
+int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
+
+/* Hand-written BPTT of sat_train_forward (what autograd derives from model.py:510-548): fills
+ * dlogits-derived buffers, DY, dZ, dP, dwf_part, dXe, d_init_out, df1, dmean, d_ann.  The
+ * reductions over (b,t) that produce parameter gradients are plain GEMMs on these buffers and
+ * are done by the host (cuBLAS through torch). */
+int sat_train_backward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAT_B200_H_ */

@@ -1,0 +1,110 @@
+"""ctypes binding of libsat_b200.so (include/sat_b200.h).  No CPU fallback: every op raises if the
+library is missing or a call fails."""
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsat_b200.so")
+SAT_F32, SAT_BF16 = 0, 1
+
+vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # all device pointers travel as void*
+
+
+class SatDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("B", "Bi", "ncap", "L", "D", "A", "E", "H", "V", "T", "dtype", "exact", "use_tc", "reserved")]
+
+
+class SatWeights(C.Structure):
+    _fields_ = [(n, vp) for n in
+                ("Wa", "Whcat", "bhcat", "Wihz", "Wihe", "bg", "Whozo", "Wo", "bo", "wf", "Emb", "Wfact", "bfact",
+                 "Winit", "binit", "WoT", "WhozoT", "WihzT", "WiheT", "WhcatT", "WaT", "WinitT", "WfactT")]
+
+
+class SatTrainBuffers(C.Structure):
+    _fields_ = [(n, vp) for n in
+                ("ann", "caps", "lens", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
+                 "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
+                 "gscale", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dwf_part", "dXe", "d_init_out",
+                 "df1", "dmean", "d_ann")] + \
+               [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("logits_f32", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_linear", "sat_prepare_images",
+           "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward"]
+
+_lib = None
+
+
+class SatError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libsat_b200.so for sm_100a with nvcc (works without a GPU)."""
+    root = os.path.dirname(_HERE)
+    r = subprocess.run(["bash", os.path.join(root, "build.sh")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise SatError("building libsat_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SatError("libsat_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "or ./build.sh); there is no CPU fallback for the SAT decoder path")
+    L = C.CDLL(LIB_PATH)
+    L.sat_last_error.restype = C.c_char_p
+    L.sat_launch_count.restype = C.c_ulonglong
+    L.sat_abi_sizeof.argtypes = [C.c_int]
+    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers)):
+        if L.sat_abi_sizeof(i) != C.sizeof(st):
+            raise SatError("ABI mismatch for %s: lib %d vs ctypes %d" % (st.__name__, L.sat_abi_sizeof(i), C.sizeof(st)))
+    L.sat_linear.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                             C.c_int32, C.c_int32, C.c_int32, vp]
+    L.sat_prepare_images.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sat_attention_step_fwd.argtypes = [C.POINTER(SatDims), vp, vp, vp, vp, C.c_int64, vp, C.c_int32, vp, C.c_int64,
+                                         vp, vp, vp, C.c_int64, vp]
+    L.sat_train_forward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
+    L.sat_train_backward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().sat_last_error().decode("utf-8", "replace")
+        raise SatError("%s failed (rc=%d): %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "sat_b200 kernels take CUDA tensors only (no CPU fallback)"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return SAT_F32
+    if dt == torch.bfloat16:
+        return SAT_BF16
+    raise SatError("unsupported dtype %s" % dt)
+
+
+def launch_count():
+    return int(lib().sat_launch_count())

@@ -1,0 +1,160 @@
+// Common device/host helpers for the SAT decoder kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sat_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local message behind sat_last_error()) --------------------
+void sat_set_error(const char* fmt, ...);
+
+#define SAT_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      sat_set_error(__VA_ARGS__);                                \
+      return SAT_ERR_INVALID;                                    \
+    }                                                            \
+  } while (0)
+
+#define SAT_CUDA(call)                                                               \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      sat_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (int)e__;                                                               \
+    }                                                                                \
+  } while (0)
+
+#define SAT_LAUNCH_OK() SAT_CUDA(cudaGetLastError())
+
+#define SAT_TRY(call)            \
+  do {                           \
+    int r__ = (call);            \
+    if (r__ != 0) return r__;    \
+  } while (0)
+
+// launch counter (gpu_launches claim in bench.py)
+extern unsigned long long g_sat_launches;
+#define SAT_COUNT_LAUNCH() (++g_sat_launches)
+
+// ---- typed loads / stores ------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements -> float4 (pointer must be 16B (float) / 8B (bf16) aligned)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// 16-byte vector of T -> floats (float: 4 values, bf16: 8 values)
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ __forceinline__ static void load(const float* p, float* o) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  __device__ __forceinline__ static void store(float* p, const float* o) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  __device__ __forceinline__ static void load(const bf16* p, float* o) {
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ static void store(bf16* p, const float* o) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+// ---- math ------------------------------------------------------------------------------
+// kExact = true : IEEE-accurate libm paths (fp32 parity mode, 1e-5 vs the CPU oracle)
+// kExact = false: MUFU approximations (bf16 throughput mode)
+template <bool kExact> __device__ __forceinline__ float sat_tanh(float x) {
+  if (kExact) return tanhf(x);
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool kExact> __device__ __forceinline__ float sat_exp(float x) {
+  if (kExact) return expf(x);
+  return __expf(x);
+}
+template <bool kExact> __device__ __forceinline__ float sat_sigmoid(float x) {
+  if (kExact) return 1.0f / (1.0f + expf(-x));
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide reductions for blockDim.x <= 1024 (scratch: 33 floats of shared memory)
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float r = lane < nw ? scratch[lane] : 0.0f;
+    r = warp_sum(r);
+    if (lane == 0) scratch[32] = r;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float r = lane < nw ? scratch[lane] : -INFINITY;
+    r = warp_max(r);
+    if (lane == 0) scratch[32] = r;
+  }
+  __syncthreads();
+  return scratch[32];
+}

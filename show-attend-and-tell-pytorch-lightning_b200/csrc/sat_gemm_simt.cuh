@@ -1,0 +1,215 @@
+// FFMA (SIMT) GEMM core with fused epilogues:  C[M,N] = epi( sum_seg A_seg[M,K_seg] * W[N, Kbase_seg..]^T ).
+//
+// This is the fp32 parity path (Blackwell tensor cores have no fp32 MMA; TF32 is ~1e-3) and the
+// shape fallback of the bf16 path when a GEMM does not meet the tcgen05/TMA tile constraints.
+// Operands are K-major ("TN": nn.Linear weight layout), A may be split into up to three K
+// segments living in different buffers (e.g. [h' ; z] for the deep-output projection).
+// 64x64x16 CTA tile, 256 threads, 4x4 register micro-tile, register-prefetch double buffering.
+#pragma once
+#include "sat_common.cuh"
+
+struct GemmOperandA {
+  const void* p[3];
+  int64_t ld[3];
+  int k[3];
+  int nseg;
+};
+
+static inline GemmOperandA gemm_a1(const void* p, int64_t ld, int k) {
+  GemmOperandA a{};
+  a.p[0] = p; a.ld[0] = ld; a.k[0] = k; a.nseg = 1;
+  return a;
+}
+static inline GemmOperandA gemm_a2(const void* p0, int64_t ld0, int k0, const void* p1, int64_t ld1, int k1) {
+  GemmOperandA a{};
+  a.p[0] = p0; a.ld[0] = ld0; a.k[0] = k0;
+  a.p[1] = p1; a.ld[1] = ld1; a.k[1] = k1;
+  a.nseg = 2;
+  return a;
+}
+
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+
+// Epilogue concept:  __device__ void operator()(int m, int n, const float (&acc)[4]) const
+// called once per (row m, 4 consecutive columns n..n+3), n % 4 == 0, m < M, n < N (N % 4 == 0).
+
+template <typename TA, typename TW, typename Epi>
+__global__ void __launch_bounds__(SG_THREADS)
+gemm_tn_simt_kernel(GemmOperandA A, const TW* __restrict__ W, int64_t ldw, int M, int N, Epi epi) {
+  __shared__ __align__(16) float As[2][SG_BK][SG_BM + 4];
+  __shared__ __align__(16) float Ws[2][SG_BK][SG_BN + 4];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int lrow = tid >> 2;          // 0..63
+  const int lk = (tid & 3) * 4;       // 0,4,8,12
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  // total number of k tiles over all segments
+  int ntiles = 0;
+  for (int s = 0; s < A.nseg; ++s) ntiles += (A.k[s] + SG_BK - 1) / SG_BK;
+
+  int seg = 0, kt_in_seg = 0, kbase = 0;   // iterator state for the *next tile to load*
+  float4 ra, rw;
+
+  auto load_tile = [&]() {
+    const int k = kt_in_seg * SG_BK + lk;
+    const int am = m0 + lrow, wn = n0 + lrow;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < A.k[seg]) {
+      if (am < M) ra = ld4(reinterpret_cast<const TA*>(A.p[seg]) + (int64_t)am * A.ld[seg] + k);
+      if (wn < N) rw = ld4(W + (int64_t)wn * ldw + kbase + k);
+    }
+    // advance iterator
+    ++kt_in_seg;
+    if (kt_in_seg * SG_BK >= A.k[seg]) {
+      kbase += A.k[seg];
+      ++seg;
+      kt_in_seg = 0;
+    }
+  };
+  auto store_tile = [&](int buf) {
+    As[buf][lk + 0][lrow] = ra.x; As[buf][lk + 1][lrow] = ra.y; As[buf][lk + 2][lrow] = ra.z; As[buf][lk + 3][lrow] = ra.w;
+    Ws[buf][lk + 0][lrow] = rw.x; Ws[buf][lk + 1][lrow] = rw.y; Ws[buf][lk + 2][lrow] = rw.z; Ws[buf][lk + 3][lrow] = rw.w;
+  };
+
+  load_tile();
+  store_tile(0);
+  __syncthreads();
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) load_tile();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    if (it + 1 < ntiles) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  const int n = n0 + tx * 4;
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < M) epi(m, n, acc[i]);
+    }
+  }
+}
+
+template <typename TA, typename TW, typename Epi>
+static int launch_gemm_tn_simt(const GemmOperandA& A, const TW* W, int64_t ldw, int M, int N, const Epi& epi,
+                               cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  int ktot = 0;
+  for (int s = 0; s < A.nseg; ++s) {
+    SAT_REQUIRE(A.k[s] % 4 == 0 && A.ld[s] % 4 == 0, "gemm: K segment %d (k=%d ld=%lld) must be a multiple of 4", s, A.k[s],
+                (long long)A.ld[s]);
+    ktot += A.k[s];
+  }
+  SAT_REQUIRE(N % 4 == 0 && ldw % 4 == 0 && ktot > 0, "gemm: N=%d ldw=%lld must be multiples of 4", N, (long long)ldw);
+  dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
+  gemm_tn_simt_kernel<TA, TW, Epi><<<grid, SG_THREADS, 0, stream>>>(A, W, ldw, M, N, epi);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
+
+// ---- epilogues -----------------------------------------------------------------------------
+
+// C = acc + bias (+ residual)
+template <typename TO>
+struct EpiStore {
+  TO* C;
+  int64_t ldc;
+  const float* bias;        // [N] or nullptr
+  const float* res;         // fp32 residual [M, ldr] or nullptr
+  int64_t ldr;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+    float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (bias) { v.x += bias[n]; v.y += bias[n + 1]; v.z += bias[n + 2]; v.w += bias[n + 3]; }
+    if (res) {
+      const float4 r = ld4(res + (int64_t)m * ldr + n);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    st4(C + (int64_t)m * ldc + n, v);
+  }
+};
+
+// LSTM cell (torch.nn.LSTM, gate order i,f,g,o; model.py:544): the GEMM computes (beta*z) * Wihz^T over
+// gate-interleaved columns, so acc[0..3] are the i,f,g,o pre-activations of hidden unit j = n/4 once
+// Gx (embedding part + biases) and the W_hh*h part (from the h-projection GEMM) are added.
+// Rows with t >= lens[m] are frozen (model.py:512,544: only incomplete rows are updated).
+template <typename TS, bool kExact>
+struct EpiLstm {
+  const float* Gx;  int64_t ldgx;      // row m -> Gx + m*ldgx (already offset to step t)
+  const float* Gh;  int64_t ldgh;      // W_hh h part: hp + (A+D), row stride ldgh
+  const TS* h_prev;
+  const float* c_prev;                 // [.., H] row stride ldst_c
+  TS* h_next; float* c_next;           // row stride ldst
+  int64_t ldst_h, ldst_c;
+  TS* gates; int64_t ldgates;          // post-activation gates for backward (row m -> gates + m*ldgates)
+  const int32_t* lens; int t;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+    const int j = n >> 2;
+    const bool active = t < lens[m];
+    const float cp = c_prev[(int64_t)m * ldst_c + j];
+    if (!active) {
+      h_next[(int64_t)m * ldst_h + j] = h_prev[(int64_t)m * ldst_h + j];
+      c_next[(int64_t)m * ldst_c + j] = cp;
+      if (gates) st4(gates + (int64_t)m * ldgates + n, make_float4(0.f, 0.f, 0.f, 0.f));
+      return;
+    }
+    const float4 gx = ld4(Gx + (int64_t)m * ldgx + n);
+    const float4 gh = ld4(Gh + (int64_t)m * ldgh + n);
+    const float gi = sat_sigmoid<kExact>(acc[0] + gx.x + gh.x);
+    const float gf = sat_sigmoid<kExact>(acc[1] + gx.y + gh.y);
+    const float gg = sat_tanh<kExact>(acc[2] + gx.z + gh.z);
+    const float go = sat_sigmoid<kExact>(acc[3] + gx.w + gh.w);
+    const float cn = gf * cp + gi * gg;
+    const float hn = go * sat_tanh<kExact>(cn);
+    c_next[(int64_t)m * ldst_c + j] = cn;
+    h_next[(int64_t)m * ldst_h + j] = from_f<TS>(hn);
+    if (gates) st4(gates + (int64_t)m * ldgates + n, make_float4(gi, gf, gg, go));
+  }
+};
+
+// deep output pre-activation: Xo = tanh(acc + Xe)   (model.py:127)
+template <typename TS, bool kExact>
+struct EpiTanhAdd {
+  const TS* Xe; TS* Xo; int64_t ld;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+    const float4 x = ld4(Xe + (int64_t)m * ld + n);
+    st4(Xo + (int64_t)m * ld + n,
+        make_float4(sat_tanh<kExact>(acc[0] + x.x), sat_tanh<kExact>(acc[1] + x.y), sat_tanh<kExact>(acc[2] + x.z),
+                    sat_tanh<kExact>(acc[3] + x.w)));
+  }
+};
+
+// dpre = g * acc * (1 - Xo^2)
+template <typename TS>
+struct EpiDpre {
+  const TS* Xo; TS* dpre; int64_t ld; const float* gscale;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+    const float g = gscale ? *gscale : 1.0f;
+    const float4 x = ld4(Xo + (int64_t)m * ld + n);
+    st4(dpre + (int64_t)m * ld + n, make_float4(g * acc[0] * (1.f - x.x * x.x), g * acc[1] * (1.f - x.y * x.y),
+                                                 g * acc[2] * (1.f - x.z * x.z), g * acc[3] * (1.f - x.w * x.w)));
+  }
+};

@@ -1,0 +1,377 @@
+// Non-GEMM kernels of the SAT decoder hot path (sm_100a): fused attention step (forward/backward),
+// row-wise cross-entropy, state initialisation, gathers and the small deterministic reductions.
+#pragma once
+#include "sat_common.cuh"
+
+constexpr int ATT_THREADS = 256;
+
+// =============================================================================================
+// K1  fused attention step, forward.   One CTA per caption row b (rows with t >= lens[b] write zeros).
+//   e_l   = (sum_a wf[a] * tanh(P[img,l,a] + q[a])) * L^-0.5        model.py:104
+//   alpha = softmax_l(e)                                             model.py:106
+//   z     = sum_l alpha_l * ann[img,l,:]                             model.py:108
+//   beta  = sigmoid(beta_pre) ; gz = beta * z                        model.py:538-541
+// q and beta_pre (bias included) come from the h-projection GEMM (hp[b, 0:A], hp[b, A:A+D]).
+// Algorithmic traffic per active row: L*(A+D)*sizeof(T) read once + (A+2D) small vectors + L floats out.
+// =============================================================================================
+template <typename T, bool kExact>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_step_fwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, const float* __restrict__ wf,
+                          const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t,
+                          int ncap, int L, int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha,
+                          float* __restrict__ qsave, T* __restrict__ z, T* __restrict__ gz, T* __restrict__ beta,
+                          int64_t ld_z) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int VN = Vec16<T>::N;
+  const int NV = D / VN;
+  const int RG = NV >= ATT_THREADS ? 1 : ATT_THREADS / NV;
+  float* e = smem;                 // [L]
+  float* qs = e + ((L + 3) & ~3);  // [A]
+  float* ws = qs + A;              // [A]
+  float* red = ws + A;             // [RG*D]
+  float* scratch = red + RG * D;   // [33]
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool active = lens == nullptr || t < lens[b];
+  float* alpha_b = alpha + (int64_t)b * ld_alpha;
+  if (!active) {
+    for (int l = tid; l < L; l += ATT_THREADS) alpha_b[l] = 0.0f;
+    for (int d = tid; d < D; d += ATT_THREADS) {
+      z[(int64_t)b * ld_z + d] = from_f<T>(0.f);
+      gz[(int64_t)b * ld_z + d] = from_f<T>(0.f);
+      if (beta) beta[(int64_t)b * ld_z + d] = from_f<T>(0.f);
+    }
+    if (qsave) for (int a = tid; a < A; a += ATT_THREADS) qsave[(int64_t)b * A + a] = 0.0f;
+    return;
+  }
+  const int img = b / ncap;
+  const float* hp_b = hp + (int64_t)b * ldhp;
+  for (int a = tid; a < A; a += ATT_THREADS) {
+    const float q = hp_b[a];
+    qs[a] = q;
+    ws[a] = wf[a];
+    if (qsave) qsave[(int64_t)b * A + a] = q;
+  }
+  __syncthreads();
+
+  // ---- phase 1: scores (one warp per location, lanes over attention_dim) --------------------
+  const T* Pb = P + (int64_t)img * L * A;
+  for (int l = warp; l < L; l += ATT_THREADS / 32) {
+    float s = 0.0f;
+    for (int a = lane * 4; a < A; a += 128) {
+      const float4 p = ld4(Pb + (int64_t)l * A + a);
+      s = fmaf(ws[a + 0], sat_tanh<kExact>(p.x + qs[a + 0]), s);
+      s = fmaf(ws[a + 1], sat_tanh<kExact>(p.y + qs[a + 1]), s);
+      s = fmaf(ws[a + 2], sat_tanh<kExact>(p.z + qs[a + 2]), s);
+      s = fmaf(ws[a + 3], sat_tanh<kExact>(p.w + qs[a + 3]), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) e[l] = s * scale;
+  }
+  __syncthreads();
+
+  // ---- phase 2: softmax over L --------------------------------------------------------------
+  float mx = -INFINITY;
+  for (int l = tid; l < L; l += ATT_THREADS) mx = fmaxf(mx, e[l]);
+  mx = block_max(mx, scratch);
+  float sum = 0.0f;
+  for (int l = tid; l < L; l += ATT_THREADS) {
+    const float p = sat_exp<kExact>(e[l] - mx);
+    e[l] = p;
+    sum += p;
+  }
+  sum = block_sum(sum, scratch);
+  for (int l = tid; l < L; l += ATT_THREADS) {
+    const float al = e[l] / sum;
+    e[l] = al;
+    alpha_b[l] = al;
+  }
+  __syncthreads();
+
+  // ---- phase 3: context z = sum_l alpha_l * a_l (16-byte loads, RG row groups) ----------------
+  const T* ab = ann + (int64_t)img * L * D;
+  if (RG == 1) {
+    for (int cv = tid; cv < NV; cv += ATT_THREADS) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
+      int l = 0;
+      for (; l + 4 <= L; l += 4) {
+        float v[4][VN];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Vec16<T>::load(ab + (int64_t)(l + u) * D + cv * VN, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float al = e[l + u];
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] = fmaf(al, v[u][i], acc[i]);
+        }
+      }
+      for (; l < L; ++l) {
+        float v[VN];
+        Vec16<T>::load(ab + (int64_t)l * D + cv * VN, v);
+        const float al = e[l];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] = fmaf(al, v[i], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) red[cv * VN + i] = acc[i];
+    }
+  } else {
+    const int rg = tid / NV, cv = tid - rg * NV;
+    if (rg < RG) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
+      int l = rg;
+      for (; l + 3 * RG < L; l += 4 * RG) {
+        float v[4][VN];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Vec16<T>::load(ab + (int64_t)(l + u * RG) * D + cv * VN, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float al = e[l + u * RG];
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] = fmaf(al, v[u][i], acc[i]);
+        }
+      }
+      for (; l < L; l += RG) {
+        float v[VN];
+        Vec16<T>::load(ab + (int64_t)l * D + cv * VN, v);
+        const float al = e[l];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] = fmaf(al, v[i], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) red[rg * D + cv * VN + i] = acc[i];
+    }
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += ATT_THREADS) {
+    float zs = 0.0f;
+    for (int r = 0; r < RG; ++r) zs += red[r * D + d];
+    const float bt = sat_sigmoid<kExact>(hp_b[A + d]);
+    z[(int64_t)b * ld_z + d] = from_f<T>(zs);
+    gz[(int64_t)b * ld_z + d] = from_f<T>(bt * zs);
+    if (beta) beta[(int64_t)b * ld_z + d] = from_f<T>(bt);
+  }
+}
+
+static inline size_t attention_fwd_smem(int L, int D, int A, int vn) {
+  const int NV = D / vn;
+  const int RG = NV >= ATT_THREADS ? 1 : ATT_THREADS / NV;
+  return sizeof(float) * (size_t)(((L + 3) & ~3) + 2 * A + RG * D + 40);
+}
+
+// =============================================================================================
+// mean over locations: meanv[i,d] = (1/L) sum_l ann[i,l,d]                        model.py:78
+// =============================================================================================
+template <typename T>
+__global__ void mean_L_kernel(const T* __restrict__ ann, T* __restrict__ meanv, int L, int D) {
+  constexpr int VN = Vec16<T>::N;
+  const int NV = D / VN;
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (cv >= NV) return;
+  const T* a = ann + (int64_t)i * L * D + cv * VN;
+  float acc[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] = 0.0f;
+  for (int l = 0; l < L; ++l) {
+    float v[VN];
+    Vec16<T>::load(a + (int64_t)l * D, v);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) acc[k] += v[k];
+  }
+  const float inv = 1.0f / (float)L;
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] *= inv;
+  Vec16<T>::store(meanv + (int64_t)i * D + cv * VN, acc);
+}
+
+// =============================================================================================
+// InitLSTM state reinterpretation (model.py:79-80): the [B,2H] init output (row b = image b/ncap)
+// is read row-major as [2,B,H]:  h0[b,j] = flat[b*H+j],  c0[b,j] = flat[(B+b)*H+j].
+// =============================================================================================
+template <typename T>
+__global__ void init_state_kernel(const float* __restrict__ init_out, T* __restrict__ h0, float* __restrict__ c0,
+                                  int64_t ld_h, int64_t ld_c, int B, int H, int ncap) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t BH = (int64_t)B * H;
+  if (idx >= 2 * BH) return;
+  const int64_t r = idx / (2 * H);          // row of the (virtual) repeated [B,2H] matrix
+  const int col = (int)(idx - r * 2 * H);
+  const float v = init_out[(r / ncap) * 2 * H + col];
+  if (idx < BH) {
+    const int64_t b = idx / H;
+    const int j = (int)(idx - b * H);
+    h0[b * ld_h + j] = from_f<T>(v);
+  } else {
+    const int64_t k = idx - BH;
+    const int64_t b = k / H;
+    const int j = (int)(k - b * H);
+    c0[b * ld_c + j] = v;
+  }
+}
+
+// inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i
+__global__ void init_state_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ dc0,
+                                      float* __restrict__ d_init_out, int B, int H, int ncap) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, 2H]
+  const int Bi = B / ncap;
+  if (idx >= (int64_t)Bi * 2 * H) return;
+  const int64_t i = idx / (2 * H);
+  const int col = (int)(idx - i * 2 * H);
+  const int64_t BH = (int64_t)B * H;
+  float s = 0.0f;
+  for (int c = 0; c < ncap; ++c) {
+    const int64_t r = i * ncap + c;
+    const int64_t f = r * 2 * H + col;
+    s += f < BH ? dh0[f] : dc0[f - BH];
+  }
+  d_init_out[idx] = s;
+}
+
+// =============================================================================================
+// embedding gather, time-major:  Xe[t,b,:] = Emb[caps[b,t],:]                         model.py:526
+// =============================================================================================
+template <typename T>
+__global__ void embed_gather_kernel(const T* __restrict__ Emb, const int32_t* __restrict__ caps, T* __restrict__ Xe,
+                                    int B, int T_, int E, int caplen) {
+  const int m = blockIdx.x;            // m = t*B + b
+  const int t = m / B, b = m - t * B;
+  const int w = caps[(int64_t)b * caplen + t];
+  constexpr int VN = Vec16<T>::N;
+  for (int c = threadIdx.x; c < E / VN; c += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(Emb + (int64_t)w * E + c * VN);
+    *reinterpret_cast<uint4*>(Xe + (int64_t)m * E + c * VN) = v;
+  }
+}
+
+// =============================================================================================
+// row-wise cross entropy with label smoothing + argmax + dlogits (util.py:105-112, model.py:596)
+//   rows are time-major m = t*B + b;  inactive rows (t >= lens[b]) give zeros (model.py:504,548).
+//   loss_row = (1-s)*(lse - x_y) + s*(lse - mean_v x)
+//   dlogits  = (softmax - (1-s)*onehot(y) - s/V) * inv_ntok
+// =============================================================================================
+template <typename TL, typename TD, bool kExact>
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t* __restrict__ caps,
+               const int32_t* __restrict__ lens, const float* __restrict__ inv_ntok_p, float* __restrict__ row_loss,
+               int32_t* __restrict__ row_argmax, int B, int V, int caplen, float smoothing, int zero_inactive_logits) {
+  extern __shared__ __align__(16) float smem[];
+  float* x = smem;              // [V]
+  float* scratch = x + V;       // [33]
+  __shared__ int s_arg[8];
+  __shared__ float s_val[8];
+  const int m = blockIdx.x, t = m / B, b = m - t * B, tid = threadIdx.x;
+  TL* row = logits + (int64_t)m * V;
+  const bool active = t < lens[b];
+  if (!active) {
+    if (zero_inactive_logits) for (int v = tid; v < V; v += 256) row[v] = from_f<TL>(0.f);
+    if (dlogits && (void*)dlogits != (void*)logits)
+      for (int v = tid; v < V; v += 256) dlogits[(int64_t)m * V + v] = from_f<TD>(0.f);
+    else if (dlogits)
+      for (int v = tid; v < V; v += 256) dlogits[(int64_t)m * V + v] = from_f<TD>(0.f);
+    if (tid == 0) { row_loss[m] = 0.0f; row_argmax[m] = -1; }
+    return;
+  }
+  const int y = caps[(int64_t)b * caplen + t + 1];
+  float mx = -INFINITY, sx = 0.0f;
+  int arg = 0x7fffffff;
+  for (int v = tid; v < V; v += 256) {
+    const float xv = to_f(row[v]);
+    x[v] = xv;
+    sx += xv;
+    if (xv > mx) { mx = xv; arg = v; }
+  }
+  // block argmax with lowest-index tie break (torch.argmax returns the first maximal index)
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = mx; s_arg[tid >> 5] = arg; }
+  __syncthreads();
+  mx = s_val[0]; arg = s_arg[0];
+  for (int w = 1; w < 8; ++w)
+    if (s_val[w] > mx || (s_val[w] == mx && s_arg[w] < arg)) { mx = s_val[w]; arg = s_arg[w]; }
+  float se = 0.0f;
+  for (int v = tid; v < V; v += 256) se += sat_exp<kExact>(x[v] - mx);
+  se = block_sum(se, scratch);
+  sx = block_sum(sx, scratch);
+  const float lse = mx + (kExact ? logf(se) : __logf(se));
+  if (tid == 0) {
+    const float nll = lse - x[y];
+    const float smooth = lse - sx / (float)V;
+    row_loss[m] = (1.0f - smoothing) * nll + smoothing * smooth;
+    row_argmax[m] = arg;
+  }
+  if (dlogits) {
+    const float inv_ntok = *inv_ntok_p;
+    const float sv = smoothing / (float)V;
+    for (int v = tid; v < V; v += 256) {
+      float p = sat_exp<kExact>(x[v] - lse) - sv;
+      if (v == y) p -= (1.0f - smoothing);
+      dlogits[(int64_t)m * V + v] = from_f<TD>(p * inv_ntok);
+    }
+  }
+}
+
+// ntok = sum_b lens[b] ; out[4] = 1/ntok        (single CTA)
+__global__ void ntok_kernel(const int32_t* __restrict__ lens, int B, float* __restrict__ out) {
+  __shared__ int sh[32];
+  int s = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += lens[b];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+    out[4] = 1.0f / (float)tot;
+    out[5] = (float)tot;
+  }
+}
+
+// S[b,l] = sum_t alphas[b,t,l]                                                  model.py:594
+__global__ void alpha_sum_kernel(const float* __restrict__ alphas, float* __restrict__ S, int B, int T_, int L) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * L) return;
+  const int64_t b = idx / L;
+  const int l = (int)(idx - b * L);
+  float s = 0.0f;
+  for (int t = 0; t < T_; ++t) s += alphas[(b * T_ + t) * L + l];
+  S[idx] = s;
+}
+
+// loss = mean_tok(row_loss) + gamma * mean_{b,l} (1-S)^2 ; accuracy.  Single CTA, fixed summation order.
+__global__ void __launch_bounds__(1024)
+loss_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_argmax,
+                     const int32_t* __restrict__ caps, const int32_t* __restrict__ lens, const float* __restrict__ S,
+                     int B, int T_, int L, int caplen, float gamma, float* __restrict__ out) {
+  __shared__ float scratch[33];
+  float ce = 0.0f, hit = 0.0f, reg = 0.0f;
+  for (int m = threadIdx.x; m < B * T_; m += blockDim.x) {
+    const int t = m / B, b = m - t * B;
+    if (t < lens[b]) {
+      ce += row_loss[m];
+      hit += (row_argmax[m] == caps[(int64_t)b * caplen + t + 1]) ? 1.0f : 0.0f;
+    }
+  }
+  for (int i = threadIdx.x; i < B * L; i += blockDim.x) {
+    const float d = 1.0f - S[i];
+    reg = fmaf(d, d, reg);
+  }
+  ce = block_sum(ce, scratch);
+  hit = block_sum(hit, scratch);
+  reg = block_sum(reg, scratch);
+  if (threadIdx.x == 0) {
+    const float inv = out[4];
+    const float cem = ce * inv, regm = reg / ((float)B * (float)L);
+    out[0] = cem + gamma * regm;
+    out[1] = cem;
+    out[2] = regm;
+    out[3] = hit * inv;
+  }
+}

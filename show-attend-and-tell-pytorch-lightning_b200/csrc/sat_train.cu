@@ -1,0 +1,206 @@
+// Teacher-forced training step of the SAT decoder: forward + loss (sat_train_forward) and the
+// hand-written BPTT (sat_train_backward), built from the fused kernels in sat_kernels.cuh and the
+// GEMM cores (SIMT FFMA for fp32 parity, tcgen05 for bf16).
+//
+// Structure (B200-first, not a translation of model.py:510-548):
+//  * everything that does not sit on the h/c recurrence is hoisted out of the time loop and run
+//    as ONE GEMM over all T*B rows: W_a*a (once per image), the embedding half of the LSTM input
+//    projection, the deep-output projection and the vocabulary projection + cross-entropy;
+//  * the recurrent part of a step is three launches: h-projection GEMM (q | beta_pre | W_hh h),
+//    fused attention kernel, gate GEMM with the LSTM cell in its epilogue;
+//  * finished captions are predicated (t < lens[b]) instead of compacted, so there is no host
+//    sync, no gather/scatter of state and no per-step reallocation.
+#include "sat_gemm.cuh"
+#include "sat_kernels.cuh"
+
+namespace {
+
+template <typename TS>
+static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void* ann, void* P, void* meanv, void* f1,
+                               float* init_out, void* h0, float* c0, cudaStream_t st) {
+  const int B = d.B, Bi = d.Bi, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H;
+  const bool tc = d.use_tc != 0;
+  // P = ann * Wa^T  ([Bi*L, D] x [A, D]^T)
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, Bi * L, A, EpiStore<TS>{(TS*)P, A, nullptr, nullptr, 0},
+                           st)));
+  // mean over locations, then the two Linear layers of InitLSTM (no nonlinearity between, model.py:79)
+  const int NV = D / Vec16<TS>::N;
+  mean_L_kernel<TS><<<dim3((NV + 127) / 128, Bi), 128, 0, st>>>((const TS*)ann, (TS*)meanv, L, D);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(meanv, D, D), (const TS*)w.Wfact, D, Bi, E,
+                           EpiStore<TS>{(TS*)f1, E, w.bfact, nullptr, 0}, st)));
+  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(f1, E, E), (const TS*)w.Winit, E, Bi, 2 * H,
+                           EpiStore<float>{init_out, 2 * H, w.binit, nullptr, 0}, st)));
+  const int64_t n = 2 * (int64_t)B * H;
+  init_state_kernel<TS><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(init_out, (TS*)h0, c0, H, H, B, H, d.ncap);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
+
+template <typename TS, bool kExact>
+int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b, cudaStream_t st) {
+  const int B = d.B, Bi = d.Bi, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H, V = d.V, T = d.T;
+  const int NH3 = A + D + 4 * H;
+  const int caplen = T + 1;
+  const bool tc = d.use_tc != 0;
+  const TS* ann = (const TS*)b.ann;
+
+  // ---- once per image ------------------------------------------------------------------------
+  SAT_TRY(sat_prepare_images(&d, &w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st));
+
+  // ---- hoisted: embeddings of the (teacher-forced) previous words and their gate projection ---
+  embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.caps, (TS*)b.Xe, B, T, E, caplen);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xe, E, E), (const TS*)w.Wihe, E, T * B, 4 * H,
+                           EpiStore<float>{b.Gx, 4 * H, w.bg, nullptr, 0}, st)));
+
+  // ---- recurrence ------------------------------------------------------------------------------
+  const float scale = (float)(1.0 / sqrt((double)L));
+  const size_t att_smem = attention_fwd_smem(L, D, A, Vec16<TS>::N);
+  for (int t = 0; t < T; ++t) {
+    const TS* h_t = (const TS*)b.Hs + (int64_t)t * B * H;
+    const float* c_t = b.Cs + (int64_t)t * B * H;
+    // hp = h_t * [W_h | W_beta | W_hh]^T + [0 | b_beta | 0]
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_t, H, H), (const TS*)w.Whcat, H, B, NH3,
+                             EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0}, st)));
+    TS* z_t = (TS*)b.Z + (int64_t)t * B * D;
+    TS* gz_t = (TS*)b.GZ + (int64_t)t * B * D;
+    TS* beta_t = (TS*)b.Beta + (int64_t)t * B * D;
+    attention_step_fwd_kernel<TS, kExact><<<B, ATT_THREADS, att_smem, st>>>(
+        ann, (const TS*)b.P, w.wf, b.hp, NH3, b.lens, t, d.ncap, L, D, A, scale, b.alphas + (int64_t)t * L,
+        (int64_t)T * L, b.Q + (int64_t)t * B * A, z_t, gz_t, beta_t, D);
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+    // gates = gz * Wihz^T + Gx[t] + hp[:, A+D:]  -> LSTM cell -> h_{t+1}, c_{t+1}
+    EpiLstm<TS, kExact> epi{b.Gx + (int64_t)t * B * 4 * H, 4 * H, b.hp + A + D, NH3, h_t, c_t,
+                            (TS*)b.Hs + (int64_t)(t + 1) * B * H, b.Cs + (int64_t)(t + 1) * B * H, H, H,
+                            (TS*)b.Gates + (int64_t)t * B * 4 * H, 4 * H, b.lens, t};
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(gz_t, D, D), (const TS*)w.Wihz, D, B, 4 * H, epi, st)));
+  }
+
+  // ---- hoisted: deep output (model.py:127) and vocabulary projection (model.py:130) over all T*B rows
+  const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
+                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E}, st)));
+  if (b.logits_f32) {
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
+                             EpiStore<float>{(float*)b.logits, V, w.bo, nullptr, 0}, st)));
+  } else {
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
+                             EpiStore<TS>{(TS*)b.logits, V, w.bo, nullptr, 0}, st)));
+  }
+
+  // ---- loss ------------------------------------------------------------------------------------
+  ntok_kernel<<<1, 256, 0, st>>>(b.lens, B, b.out);
+  SAT_COUNT_LAUNCH();
+  const size_t ce_smem = sizeof(float) * (size_t)(V + 40);
+  if (b.logits_f32) {
+    auto k = ce_rows_kernel<float, TS, kExact>;
+    if (ce_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem));
+    k<<<T * B, 256, ce_smem, st>>>((float*)b.logits, (TS*)b.dlogits, b.caps, b.lens, b.out + 4, b.row_loss, b.row_argmax, B,
+                                   V, caplen, b.label_smoothing, 1);
+  } else {
+    auto k = ce_rows_kernel<TS, TS, kExact>;
+    if (ce_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem));
+    k<<<T * B, 256, ce_smem, st>>>((TS*)b.logits, (TS*)b.dlogits, b.caps, b.lens, b.out + 4, b.row_loss, b.row_argmax, B, V,
+                                   caplen, b.label_smoothing, 1);
+  }
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  alpha_sum_kernel<<<(B * L + 255) / 256, 256, 0, st>>>(b.alphas, b.S, B, T, L);
+  SAT_COUNT_LAUNCH();
+  loss_finalize_kernel<<<1, 1024, 0, st>>>(b.row_loss, b.row_argmax, b.caps, b.lens, b.S, B, T, L, caplen, b.att_gamma, b.out);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  (void)Bi;
+  return 0;
+}
+
+int check_dims(const SatDims* d) {
+  SAT_REQUIRE(d != nullptr, "dims is NULL");
+  SAT_REQUIRE(d->dtype == SAT_F32 || d->dtype == SAT_BF16, "unknown dtype %d", d->dtype);
+  SAT_REQUIRE(d->B > 0 && d->Bi > 0 && d->ncap > 0 && d->B == d->Bi * d->ncap, "B=%d must equal Bi*ncap=%d*%d", d->B, d->Bi,
+              d->ncap);
+  SAT_REQUIRE(d->L > 0 && d->T >= 0, "bad L=%d T=%d", d->L, d->T);
+  SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0 && d->D > 0 && d->A > 0 &&
+                  d->E > 0 && d->H > 0 && d->V > 0,
+              "D=%d A=%d E=%d H=%d V=%d must be positive multiples of 8", d->D, d->A, d->E, d->H, d->V);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sat_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int32_t M,
+               int32_t N, int32_t K, int32_t dtype, int32_t c_f32, int32_t use_tc, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SAT_REQUIRE(A && W && C, "sat_linear: NULL operand");
+  const bool tc = use_tc != 0;
+  if (dtype == SAT_F32) {
+    SAT_REQUIRE(c_f32, "sat_linear: fp32 operands need an fp32 output");
+    return gemm_tn<float, float>(false, gemm_a1(A, lda, K), (const float*)W, ldw, M, N,
+                                 EpiStore<float>{(float*)C, ldc, bias, nullptr, 0}, st);
+  } else if (dtype == SAT_BF16) {
+    if (c_f32)
+      return gemm_tn<bf16, bf16>(tc, gemm_a1(A, lda, K), (const bf16*)W, ldw, M, N,
+                                 EpiStore<float>{(float*)C, ldc, bias, nullptr, 0}, st);
+    return gemm_tn<bf16, bf16>(tc, gemm_a1(A, lda, K), (const bf16*)W, ldw, M, N, EpiStore<bf16>{(bf16*)C, ldc, bias, nullptr, 0},
+                               st);
+  }
+  SAT_REQUIRE(false, "sat_linear: unknown dtype %d", dtype);
+}
+
+int sat_prepare_images(const SatDims* d, const SatWeights* w, const void* ann, void* P, void* meanv, void* f1, float* init_out,
+                       void* h0, float* c0, void* stream) {
+  SAT_TRY(check_dims(d));
+  SAT_REQUIRE(w && ann && P && meanv && f1 && init_out && h0 && c0, "sat_prepare_images: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == SAT_F32) return prepare_images_impl<float>(*d, *w, ann, P, meanv, f1, init_out, h0, c0, st);
+  return prepare_images_impl<bf16>(*d, *w, ann, P, meanv, f1, init_out, h0, c0, st);
+}
+
+int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, const float* wf, const float* hp, int64_t ldhp,
+                           const int32_t* lens, int32_t t, float* alpha, int64_t ld_alpha, void* z, void* gz, void* beta,
+                           int64_t ld_z, void* stream) {
+  SAT_TRY(check_dims(d));
+  SAT_REQUIRE(ann && P && wf && hp && alpha && z && gz, "sat_attention_step_fwd: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float scale = (float)(1.0 / sqrt((double)d->L));
+#define SAT_LAUNCH_ATT(TS, EX)                                                                                          \
+  do {                                                                                                                  \
+    const size_t smem = attention_fwd_smem(d->L, d->D, d->A, Vec16<TS>::N);                                             \
+    attention_step_fwd_kernel<TS, EX><<<d->B, ATT_THREADS, smem, st>>>((const TS*)ann, (const TS*)P, wf, hp, ldhp, lens, t, \
+                                                                       d->ncap, d->L, d->D, d->A, scale, alpha, ld_alpha, \
+                                                                       nullptr, (TS*)z, (TS*)gz, (TS*)beta, ld_z);       \
+  } while (0)
+  if (d->dtype == SAT_F32) {
+    if (d->exact) SAT_LAUNCH_ATT(float, true); else SAT_LAUNCH_ATT(float, false);
+  } else {
+    if (d->exact) SAT_LAUNCH_ATT(bf16, true); else SAT_LAUNCH_ATT(bf16, false);
+  }
+#undef SAT_LAUNCH_ATT
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
+
+int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream) {
+  SAT_TRY(check_dims(d));
+  SAT_REQUIRE(w && b, "sat_train_forward: NULL struct");
+  SAT_REQUIRE(d->T > 0, "sat_train_forward: T must be > 0");
+  SAT_REQUIRE(b->ann && b->caps && b->lens && b->P && b->meanv && b->f1 && b->init_out && b->Xe && b->Gx && b->Hs && b->Cs &&
+                  b->hp && b->Q && b->alphas && b->Z && b->GZ && b->Beta && b->Gates && b->Xo && b->logits && b->row_loss &&
+                  b->row_argmax && b->S && b->out,
+              "sat_train_forward: NULL forward buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == SAT_F32) {
+    return d->exact ? train_forward_impl<float, true>(*d, *w, *b, st) : train_forward_impl<float, false>(*d, *w, *b, st);
+  }
+  return d->exact ? train_forward_impl<bf16, true>(*d, *w, *b, st) : train_forward_impl<bf16, false>(*d, *w, *b, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+"""Host side of the fused SAT decoder: buffer management and the calls into libsat_b200.so.
+
+Reference spans replaced: SAT.train_batch (model.py:474-557) + the loss of training_step
+(model.py:588-597, util.py:105-112) and, through autograd, their backward.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .packing import PackedWeights, deinterleave_gates
+
+
+def make_dims(B, Bi, L, D, A, E, H, V, T, dtype, exact, use_tc):
+    d = _lib.SatDims()
+    d.B, d.Bi, d.ncap = B, Bi, B // Bi
+    d.L, d.D, d.A, d.E, d.H, d.V, d.T = L, D, A, E, H, V, T
+    d.dtype = _lib.dtype_code(dtype)
+    d.exact = 1 if exact else 0
+    d.use_tc = 1 if use_tc else 0
+    return d
+
+
+class TrainBuffers:
+    """All device buffers of one training step (include/sat_b200.h: SatTrainBuffers)."""
+
+    def __init__(self, d, dtype, device, logits_f32=False, backward=True, keep_logits=False):
+        B, Bi, L, D, A, E, H, V, T = d.B, d.Bi, d.L, d.D, d.A, d.E, d.H, d.V, d.T
+        NH3 = A + D + 4 * H
+        s, f = dtype, torch.float32
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+        t = self.t = {}
+        t["P"] = mk((Bi, L, A), s)
+        t["meanv"] = mk((Bi, D), s)
+        t["f1"] = mk((Bi, E), s)
+        t["init_out"] = mk((Bi, 2 * H), f)
+        t["Xe"] = mk((T, B, E), s)
+        t["Gx"] = mk((T, B, 4 * H), f)
+        t["Hs"] = mk((T + 1, B, H), s)
+        t["Cs"] = mk((T + 1, B, H), f)
+        t["hp"] = mk((B, NH3), f)
+        t["Q"] = mk((T, B, A), f)
+        t["alphas"] = mk((B, T, L), f)
+        t["Z"] = mk((T, B, D), s)
+        t["GZ"] = mk((T, B, D), s)
+        t["Beta"] = mk((T, B, D), s)
+        t["Gates"] = mk((T, B, 4 * H), s)
+        t["Xo"] = mk((T, B, E), s)
+        t["logits"] = mk((T, B, V), f if logits_f32 else s)
+        if backward:
+            t["dlogits"] = mk((T, B, V), s) if (keep_logits or logits_f32) else t["logits"]
+        t["row_loss"] = mk((T, B), f)
+        t["row_argmax"] = mk((T, B), torch.int32)
+        t["S"] = mk((B, L), f)
+        t["out"] = torch.zeros(8, dtype=f, device=device)
+        if backward:
+            t["gscale"] = torch.ones(1, dtype=f, device=device)
+            t["dpre"] = mk((T, B, E), s)
+            t["dHZ"] = mk((T, B, H + D), f)
+            t["DY"] = mk((T, B, NH3), s)
+            t["dgz"] = mk((B, D), f)
+            t["dh"] = mk((B, H), f)
+            t["dc"] = mk((B, H), f)
+            t["dZ"] = mk((T, B, D), s)
+            t["dP"] = mk((B, L, A), f)
+            t["dwf_part"] = mk((T, B, A), f)
+            t["dXe"] = mk((T, B, E), f)
+            t["d_init_out"] = mk((Bi, 2 * H), f)
+            t["df1"] = mk((Bi, E), f)
+            t["dmean"] = mk((Bi, D), f)
+            t["d_ann"] = mk((Bi, L, D), s)
+        self.c = _lib.SatTrainBuffers()
+        for name, typ in _lib.SatTrainBuffers._fields_:
+            if typ is C.c_void_p and name in t:
+                setattr(self.c, name, _lib.ptr(t[name]))
+        self.c.logits_f32 = 1 if logits_f32 else 0
+        self.dims = d
+
+    def bind_inputs(self, ann, caps, lens, label_smoothing, att_gamma):
+        self.t["ann"], self.t["caps"], self.t["lens"] = ann, caps, lens   # keep alive
+        self.c.ann, self.c.caps, self.c.lens = _lib.ptr(ann), _lib.ptr(caps), _lib.ptr(lens)
+        self.c.label_smoothing = float(label_smoothing)
+        self.c.att_gamma = float(att_gamma)
+
+
+def annotations_as_bld(ann, dtype):
+    """[Bi,D,h,w] (any memory format) -> contiguous [Bi,L,D] of `dtype`.  Zero-copy when the encoder
+    produced channels_last output in `dtype`."""
+    Bi, D, h, w = ann.shape
+    x = ann.permute(0, 2, 3, 1).reshape(Bi, h * w, D)
+    if x.dtype != dtype:
+        x = x.to(dtype)
+    return x.contiguous()
+
+
+def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, exact=True, use_tc=False,
+                  logits_f32=False, backward=True, keep_logits=False, buffers=None):
+    """ann_bld [Bi,L,D] (pw.dtype, cuda); caps [Bi,ncap,T+1] or [B,T+1] int; lens [Bi,ncap] or [B].
+    Runs sat_train_forward; returns the TrainBuffers (loss etc. in .t['out'])."""
+    L_ = _lib.lib()
+    dev = ann_bld.device
+    Bi, L, D = ann_bld.shape
+    caps2 = caps.reshape(-1, caps.shape[-1]).to(device=dev, dtype=torch.int32).contiguous()
+    lens2 = lens.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    B, caplen = caps2.shape
+    dm = pw.dims
+    assert D == dm["D"], "annotation width %d != encoder_dim %d" % (D, dm["D"])
+    assert ann_bld.dtype == pw.dtype and ann_bld.is_contiguous()
+    d = make_dims(B, Bi, L, D, dm["A"], dm["E"], dm["H"], dm["V"], caplen - 1, pw.dtype, exact, use_tc)
+    if buffers is None:
+        buffers = TrainBuffers(d, pw.dtype, dev, logits_f32=logits_f32, backward=backward, keep_logits=keep_logits)
+    buffers.bind_inputs(ann_bld, caps2, lens2, label_smoothing, att_gamma)
+    buffers.dims = d
+    _lib.check(L_.sat_train_forward(C.byref(d), pw.ref(), C.byref(buffers.c), _lib.stream_ptr()), "sat_train_forward")
+    return buffers
