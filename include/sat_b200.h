@@ -109,6 +109,8 @@ typedef struct SatTrainBuffers {
   float* out;            /* [8]          loss, cross-entropy part, doubly-stochastic part, accuracy, 1/N_tok, N_tok */
   /* bwd */
   const float* gscale;   /* [1]          upstream d(loss) (device scalar)                          */
+  const float* dalpha_ext; /* [B,T,L] or NULL: extra upstream grad wrt alphas (API path: train_batch's alphas
+                                         used by a caller-side loss); the fused loss path leaves it NULL  */
   void* dpre;            /* [T,B,E] s    grad wrt deep-output pre-activation                       */
   float* dHZ;            /* [T,B,H+D]    dpre * [W_ho|W_zo]                                        */
   void* DY;              /* [T,B,A+D+4H] s: dq | dbeta_pre | dG (gate-interleaved)                 */
@@ -122,7 +124,7 @@ typedef struct SatTrainBuffers {
   float* d_init_out;     /* [Bi,2H]                                                               */
   float* df1;            /* [Bi,E]                                                                */
   float* dmean;          /* [Bi,D]                                                                */
-  void* d_ann;           /* [Bi,L,D] s   grad wrt annotations                                      */
+  void* d_ann;           /* [B,L,D] s    grad wrt annotations, one slab per caption row (host sums the ncap rows of an image) */
   /* scalars */
   float label_smoothing;
   float att_gamma;

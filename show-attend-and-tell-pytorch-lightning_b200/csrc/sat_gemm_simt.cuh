@@ -133,13 +133,13 @@ static int launch_gemm_tn_simt(const GemmOperandA& A, const TW* W, int64_t ldw, 
 
 // ---- epilogues -----------------------------------------------------------------------------
 
-// C = acc + bias (+ residual)
-template <typename TO>
+// C = acc + bias (+ residual of type TR)
+template <typename TO, typename TR = float>
 struct EpiStore {
   TO* C;
   int64_t ldc;
   const float* bias;        // [N] or nullptr
-  const float* res;         // fp32 residual [M, ldr] or nullptr
+  const TR* res;            // residual [M, ldr] or nullptr
   int64_t ldr;
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
     float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -149,6 +149,35 @@ struct EpiStore {
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     st4(C + (int64_t)m * ldc + n, v);
+  }
+};
+
+// h-chain of the backward pass: dh[b,:] = acc for rows active at step t, unchanged otherwise
+struct EpiDh {
+  float* dh; int64_t ld; const int32_t* lens; int t;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+    if (t < lens[m]) st4(dh + (int64_t)m * ld + n, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  }
+};
+
+// d_ann[b,l,:] = acc (= dP[b,l,:] * Wa) + sum_t alpha[b,t,l] * dZ[t,b,:] + dmean[img,:] * mean_scale
+// rows m = b*L + l   (d_a += alpha (x) dz ; d_a += dP W_a ; mean path)
+template <typename TS>
+struct EpiDAnn {
+  TS* d_ann; const float* alphas; const TS* dZ; const float* dmean;
+  int B, T, L, D, ncap; float mean_scale;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+    const int b = m / L, l = m - b * L;
+    const float4 dm = ld4(dmean + (int64_t)(b / ncap) * D + n);
+    float4 v = make_float4(acc[0] + dm.x * mean_scale, acc[1] + dm.y * mean_scale, acc[2] + dm.z * mean_scale,
+                           acc[3] + dm.w * mean_scale);
+    const float* al = alphas + ((int64_t)b * T) * L + l;
+    for (int t = 0; t < T; ++t) {
+      const float a = al[(int64_t)t * L];
+      const float4 dz = ld4(dZ + ((int64_t)t * B + b) * D + n);
+      v.x = fmaf(a, dz.x, v.x); v.y = fmaf(a, dz.y, v.y); v.z = fmaf(a, dz.z, v.z); v.w = fmaf(a, dz.w, v.w);
+    }
+    st4(d_ann + (int64_t)m * D + n, v);
   }
 };
 

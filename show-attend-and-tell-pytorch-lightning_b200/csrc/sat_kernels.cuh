@@ -215,7 +215,7 @@ __global__ void init_state_kernel(const float* __restrict__ init_out, T* __restr
 }
 
 // inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i
-__global__ void init_state_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ dc0,
+static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ dc0,
                                       float* __restrict__ d_init_out, int B, int H, int ncap) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, 2H]
   const int Bi = B / ncap;
@@ -319,7 +319,7 @@ ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t*
 }
 
 // ntok = sum_b lens[b] ; out[4] = 1/ntok        (single CTA)
-__global__ void ntok_kernel(const int32_t* __restrict__ lens, int B, float* __restrict__ out) {
+static __global__ void ntok_kernel(const int32_t* __restrict__ lens, int B, float* __restrict__ out) {
   __shared__ int sh[32];
   int s = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) s += lens[b];
@@ -335,7 +335,7 @@ __global__ void ntok_kernel(const int32_t* __restrict__ lens, int B, float* __re
 }
 
 // S[b,l] = sum_t alphas[b,t,l]                                                  model.py:594
-__global__ void alpha_sum_kernel(const float* __restrict__ alphas, float* __restrict__ S, int B, int T_, int L) {
+static __global__ void alpha_sum_kernel(const float* __restrict__ alphas, float* __restrict__ S, int B, int T_, int L) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * L) return;
   const int64_t b = idx / L;
@@ -346,7 +346,7 @@ __global__ void alpha_sum_kernel(const float* __restrict__ alphas, float* __rest
 }
 
 // loss = mean_tok(row_loss) + gamma * mean_{b,l} (1-S)^2 ; accuracy.  Single CTA, fixed summation order.
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_argmax,
                      const int32_t* __restrict__ caps, const int32_t* __restrict__ lens, const float* __restrict__ S,
                      int B, int T_, int L, int caplen, float gamma, float* __restrict__ out) {
@@ -374,4 +374,174 @@ loss_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restri
     out[2] = regm;
     out[3] = hit * inv;
   }
+}
+
+// =============================================================================================
+// LSTM cell backward for one step (elementwise over [B,H]); see SURVEY.md appendix E.
+//   dh (in) = grad wrt h_{t+1} from later steps; dHo = grad from the deep-output path at step t.
+//   Writes dG (gate-interleaved, pre-activation grads) into DY[t,:,A+D:], updates dc in place and
+//   leaves dh untouched (the h-chain GEMM that follows overwrites it for active rows).
+// =============================================================================================
+template <typename TS, bool kExact>
+__global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* __restrict__ c_prev,
+                                     const float* __restrict__ c_next, const float* __restrict__ dh,
+                                     const float* __restrict__ dHo, int64_t ld_dho, float* __restrict__ dc,
+                                     TS* __restrict__ dG, int64_t ld_dg, const int32_t* __restrict__ lens, int t, int B,
+                                     int H) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, j = idx - b * H;
+  TS* dg = dG + (int64_t)b * ld_dg + 4 * j;
+  if (t >= lens[b]) {
+    st4(dg, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const float4 g4 = ld4(gates + (int64_t)b * 4 * H + 4 * j);
+  const float gi = g4.x, gf = g4.y, gg = g4.z, go = g4.w;
+  const float cp = c_prev[idx], cn = c_next[idx];
+  const float tc = sat_tanh<kExact>(cn);
+  const float dht = dh[idx] + dHo[(int64_t)b * ld_dho + j];
+  const float dct = dc[idx] + dht * go * (1.0f - tc * tc);
+  st4(dg, make_float4(dct * gg * gi * (1.0f - gi), dct * cp * gf * (1.0f - gf), dct * gi * (1.0f - gg * gg),
+                      dht * tc * go * (1.0f - go)));
+  dc[idx] = dct * gf;
+}
+
+// =============================================================================================
+// K1b  fused attention step, backward.  One CTA per caption row b.
+//   dz      = dZout + dgz * beta                      dbeta_pre = dgz * z * beta (1-beta)
+//   dalpha_l= a_l . dz  +  g * gamma * (-2)(1 - S_l)/(B L)
+//   de_l    = alpha_l (dalpha_l - sum_l' alpha_l' dalpha_l')
+//   dpu_la  = scale * de_l * wf_a * (1 - u_la^2),  u = tanh(P + q)  (recomputed)
+//   dP[b,l,a] += dpu ;  dq_a = sum_l dpu_la ;  dwf_a = scale * sum_l de_l u_la
+// Algorithmic traffic per active row: L*(A+D)*sizeof(T) read + 2*L*A*4 (dP read-modify-write).
+// =============================================================================================
+constexpr int ATTB_MAXKA = 4;   // attention_dim <= 512
+
+template <typename T, bool kExact>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, const float* __restrict__ wf,
+                          const float* __restrict__ q_t, const float* __restrict__ alpha, int64_t ld_alpha,
+                          const float* __restrict__ S, const T* __restrict__ z_t, const T* __restrict__ beta_t,
+                          const float* __restrict__ dgz, const float* __restrict__ dZout, int64_t ld_dzout,
+                          const int32_t* __restrict__ lens, int t, int ncap, int B, int L, int D, int A, float scale,
+                          float gamma, const float* __restrict__ gscale, const float* __restrict__ dalpha_ext,
+                          float* __restrict__ dP, T* __restrict__ dZ_t,
+                          T* __restrict__ DY_t, int64_t ld_dy, float* __restrict__ dwf_t) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int VN = Vec16<T>::N;
+  constexpr int NW = ATT_THREADS / 32;
+  float* dz_s = smem;                         // [D]
+  float* dal = dz_s + D;                      // [L] (padded to 4)
+  float* qs = dal + ((L + 3) & ~3);           // [A]
+  float* ws = qs + A;                         // [A]
+  float* red = ws + A;                        // [NW][2A]
+  float* scratch = red + NW * 2 * A;          // [33]
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  T* dy_b = DY_t + (int64_t)b * ld_dy;
+  if (t >= lens[b]) {
+    for (int i = tid; i < A + D; i += ATT_THREADS) dy_b[i] = from_f<T>(0.f);
+    for (int d = tid; d < D; d += ATT_THREADS) dZ_t[(int64_t)b * D + d] = from_f<T>(0.f);
+    for (int a = tid; a < A; a += ATT_THREADS) dwf_t[(int64_t)b * A + a] = 0.0f;
+    return;
+  }
+  const int img = b / ncap;
+  const float g = gscale ? *gscale : 1.0f;
+  // phase A
+  for (int d = tid; d < D; d += ATT_THREADS) {
+    const float dg = dgz[(int64_t)b * D + d];
+    const float bt = to_f(beta_t[(int64_t)b * D + d]);
+    const float zz = to_f(z_t[(int64_t)b * D + d]);
+    const float dzv = dZout[(int64_t)b * ld_dzout + d] + dg * bt;
+    dz_s[d] = dzv;
+    dZ_t[(int64_t)b * D + d] = from_f<T>(dzv);
+    dy_b[A + d] = from_f<T>(dg * zz * bt * (1.0f - bt));
+  }
+  for (int a = tid; a < A; a += ATT_THREADS) {
+    qs[a] = q_t[(int64_t)b * A + a];
+    ws[a] = wf[a];
+  }
+  __syncthreads();
+  // phase B: dalpha_l = a_l . dz + regulariser
+  const T* ab = ann + (int64_t)img * L * D;
+  const float* alpha_b = alpha + (int64_t)b * ld_alpha;
+  const float regc = g * gamma * (-2.0f) / ((float)B * (float)L);
+  const int NV = D / VN;
+  for (int l = warp; l < L; l += NW) {
+    float s = 0.0f;
+    for (int cv = lane; cv < NV; cv += 32) {
+      float v[VN];
+      Vec16<T>::load(ab + (int64_t)l * D + cv * VN, v);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) s = fmaf(v[i], dz_s[cv * VN + i], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      float v = s + regc * (1.0f - S[(int64_t)b * L + l]);
+      if (dalpha_ext) v += dalpha_ext[(int64_t)b * ld_alpha + l];
+      dal[l] = v;
+    }
+  }
+  __syncthreads();
+  // phase C: softmax backward
+  float dot = 0.0f;
+  for (int l = tid; l < L; l += ATT_THREADS) dot = fmaf(alpha_b[l], dal[l], dot);
+  dot = block_sum(dot, scratch);
+  for (int l = tid; l < L; l += ATT_THREADS) dal[l] = alpha_b[l] * (dal[l] - dot);   // de_l
+  __syncthreads();
+  // phase D: through tanh into P, q, wf
+  const T* Pb = P + (int64_t)img * L * A;
+  float* dPb = dP + (int64_t)b * L * A;
+  float dq[ATTB_MAXKA][4], dw[ATTB_MAXKA][4];
+#pragma unroll
+  for (int k = 0; k < ATTB_MAXKA; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dq[k][i] = 0.0f; dw[k][i] = 0.0f; }
+  for (int l = warp; l < L; l += NW) {
+    const float de = dal[l] * scale;
+#pragma unroll
+    for (int k = 0; k < ATTB_MAXKA; ++k) {
+      const int a = lane * 4 + k * 128;
+      if (a < A) {
+        const float4 p = ld4(Pb + (int64_t)l * A + a);
+        const float pv[4] = {p.x, p.y, p.z, p.w};
+        float4 acc = *reinterpret_cast<float4*>(dPb + (int64_t)l * A + a);
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float u = sat_tanh<kExact>(pv[i] + qs[a + i]);
+          const float dpu = de * ws[a + i] * (1.0f - u * u);
+          o[i] = dpu;
+          dq[k][i] += dpu;
+          dw[k][i] = fmaf(de, u, dw[k][i]);
+        }
+        acc.x += o[0]; acc.y += o[1]; acc.z += o[2]; acc.w += o[3];
+        *reinterpret_cast<float4*>(dPb + (int64_t)l * A + a) = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ATTB_MAXKA; ++k) {
+    const int a = lane * 4 + k * 128;
+    if (a < A) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        red[warp * 2 * A + a + i] = dq[k][i];
+        red[warp * 2 * A + A + a + i] = dw[k][i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int a = tid; a < A; a += ATT_THREADS) {
+    float sq = 0.0f, sw = 0.0f;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) { sq += red[w2 * 2 * A + a]; sw += red[w2 * 2 * A + A + a]; }
+    dy_b[a] = from_f<T>(sq);
+    dwf_t[(int64_t)b * A + a] = sw;
+  }
+}
+
+static inline size_t attention_bwd_smem(int L, int D, int A) {
+  return sizeof(float) * (size_t)(D + ((L + 3) & ~3) + 2 * A + (ATT_THREADS / 32) * 2 * A + 40);
 }

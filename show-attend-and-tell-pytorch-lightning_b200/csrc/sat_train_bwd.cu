@@ -1,5 +1,97 @@
-#include "sat_common.cuh"
+// Hand-written BPTT of the teacher-forced SAT decoder step (what autograd
+// derives from model.py:510-548 when PL calls loss.backward()).
+//
+// Only the dh/dc/dz chain is sequential; it costs three launches per step:
+//   lstm_bwd_step (elementwise)  ->  GEMM dgz = dG * Wihz  ->  fused attention backward  ->
+//   GEMM dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (one GEMM, K = A+D+4H)
+// Everything else is hoisted to whole-sequence GEMMs over T*B rows (dpre, dHZ, dXe, d_ann), and
+// the parameter gradients are plain reductions over (t,b) of the buffers written here.
+#include "sat_gemm.cuh"
+#include "sat_kernels.cuh"
+
+namespace {
+
+template <typename TS, bool kExact>
+int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b, cudaStream_t st) {
+  const int B = d.B, Bi = d.Bi, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H, V = d.V, T = d.T;
+  const int NH3 = A + D + 4 * H;
+  const bool tc = d.use_tc != 0;
+  const TS* ann = (const TS*)b.ann;
+  const int M = T * B;
+
+  // dpre = g * (dlogits * Wo) * (1 - Xo^2)            [M,E]
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dlogits, V, V), (const TS*)w.WoT, V, M, E,
+                           EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale}, st)));
+  // dHZ = dpre * [W_ho | W_zo]                         [M,H+D]
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dpre, E, E), (const TS*)w.WhozoT, E, M, H + D,
+                           EpiStore<float>{b.dHZ, H + D, nullptr, nullptr, 0}, st)));
+
+  SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)B * H, st));
+  SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)B * H, st));
+  SAT_CUDA(cudaMemsetAsync(b.dP, 0, sizeof(float) * (size_t)B * L * A, st));
+
+  const float scale = (float)(1.0 / sqrt((double)L));
+  const size_t att_smem = attention_bwd_smem(L, D, A);
+  auto att_k = attention_step_bwd_kernel<TS, kExact>;
+  if (att_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(att_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+
+  for (int t = T - 1; t >= 0; --t) {
+    TS* DY_t = (TS*)b.DY + (int64_t)t * B * NH3;
+    const float* dHZ_t = b.dHZ + (int64_t)t * B * (H + D);
+    lstm_bwd_step_kernel<TS, kExact><<<(B * H + 255) / 256, 256, 0, st>>>(
+        (const TS*)b.Gates + (int64_t)t * B * 4 * H, b.Cs + (int64_t)t * B * H, b.Cs + (int64_t)(t + 1) * B * H, b.dh, dHZ_t,
+        H + D, b.dc, DY_t + A + D, NH3, b.lens, t, B, H);
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+    // dgz = dG * Wihz     (A operand: DY_t[:, A+D:], K = 4H)
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + A + D, NH3, 4 * H), (const TS*)w.WihzT, 4 * H, B, D,
+                             EpiStore<float>{b.dgz, D, nullptr, nullptr, 0}, st)));
+    att_k<<<B, ATT_THREADS, att_smem, st>>>(ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
+                                            (int64_t)T * L, b.S, (const TS*)b.Z + (int64_t)t * B * D,
+                                            (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, dHZ_t + H, H + D, b.lens, t, d.ncap,
+                                            B, L, D, A, scale, b.att_gamma, b.gscale,
+                                            b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, (TS*)b.dZ + (int64_t)t * B * D,
+                                            DY_t, NH3, b.dwf_part + (int64_t)t * B * A);
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+    // dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (rows inactive at t keep their dh)
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t, NH3, NH3), (const TS*)w.WhcatT, NH3, B, H, EpiDh{b.dh, H, b.lens, t}, st)));
+  }
+
+  // dXe = dG * Wihe + dpre                               [M,E]
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.DY + A + D, NH3, 4 * H), (const TS*)w.WiheT, 4 * H, M, E,
+                           EpiStore<float, TS>{b.dXe, E, nullptr, (const TS*)b.dpre, E}, st)));
+
+  // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
+  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, b.dc, b.d_init_out, B, H, d.ncap);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.d_init_out, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,
+                              EpiStore<float>{b.df1, E, nullptr, nullptr, 0}, st)));
+  SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.df1, E, E), (const TS*)w.WfactT, E, Bi, D,
+                              EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));
+
+  // d_ann[b,l,:] = dP[b,l,:] * Wa + sum_t alpha[b,t,l] dZ[t,b,:] + dmean[img]/(L*ncap)
+  // (for ncap > 1 the buffer holds per-caption rows [B,L,D]; the host sums the ncap rows of an image)
+  SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.dP, A, A), (const TS*)w.WaT, A, B * L, D,
+                              EpiDAnn<TS>{(TS*)b.d_ann, b.alphas, (const TS*)b.dZ, b.dmean, B, T, L, D, d.ncap,
+                                          1.0f / ((float)L * (float)d.ncap)},
+                              st)));
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int sat_train_backward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream) {
-  (void)d; (void)w; (void)b; (void)stream;
-  SAT_REQUIRE(false, "sat_train_backward: not built yet");
+  SAT_REQUIRE(d && w && b, "sat_train_backward: NULL struct");
+  SAT_REQUIRE(d->A <= 128 * ATTB_MAXKA, "sat_train_backward: attention_dim %d > %d", d->A, 128 * ATTB_MAXKA);
+  SAT_REQUIRE(b->dlogits && b->gscale && b->dpre && b->dHZ && b->DY && b->dgz && b->dh && b->dc && b->dZ && b->dP &&
+                  b->dwf_part && b->dXe && b->d_init_out && b->df1 && b->dmean && b->d_ann,
+              "sat_train_backward: NULL backward buffer");
+  SAT_REQUIRE(w->WoT && w->WhozoT && w->WihzT && w->WiheT && w->WhcatT && w->WaT && w->WinitT && w->WfactT,
+              "sat_train_backward: transposed weights missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == SAT_F32)
+    return d->exact ? train_backward_impl<float, true>(*d, *w, *b, st) : train_backward_impl<float, false>(*d, *w, *b, st);
+  return d->exact ? train_backward_impl<bf16, true>(*d, *w, *b, st) : train_backward_impl<bf16, false>(*d, *w, *b, st);
 }

@@ -68,7 +68,7 @@ class TrainBuffers:
             t["d_init_out"] = mk((Bi, 2 * H), f)
             t["df1"] = mk((Bi, E), f)
             t["dmean"] = mk((Bi, D), f)
-            t["d_ann"] = mk((Bi, L, D), s)
+            t["d_ann"] = mk((B, L, D), s)          # per caption row; the host sums the ncap rows of an image
         self.c = _lib.SatTrainBuffers()
         for name, typ in _lib.SatTrainBuffers._fields_:
             if typ is C.c_void_p and name in t:
@@ -113,3 +113,87 @@ def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, e
     buffers.dims = d
     _lib.check(L_.sat_train_forward(C.byref(d), pw.ref(), C.byref(buffers.c), _lib.stream_ptr()), "sat_train_forward")
     return buffers
+
+
+def _mm_tn(a, b):
+    """a^T @ b with fp32 output (plain library GEMM: cuBLAS through torch).  a [M,N1], b [M,N2]."""
+    if a.dtype != b.dtype:
+        a, b = a.float(), b.float()
+    if a.dtype == torch.float32:
+        return a.t() @ b
+    try:
+        return torch.mm(a.t(), b, out_dtype=torch.float32)
+    except TypeError:
+        return (a.t() @ b).float()
+
+
+def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalpha_ext=None):
+    """Runs sat_train_backward on the buffers of a finished train_forward, then reduces the saved
+    per-(t,b) buffers into parameter gradients (reference names / shapes) with plain GEMMs.
+    Returns (grads dict, d_ann [Bi,L,D])."""
+    L_ = _lib.lib()
+    t, d = buf.t, buf.dims
+    B, Bi, ncap, L, D, A, E, H, V, T = d.B, d.Bi, d.ncap, d.L, d.D, d.A, d.E, d.H, d.V, d.T
+    NH3 = A + D + 4 * H
+    M = T * B
+    if grad_loss is None:
+        t["gscale"].fill_(1.0)
+    else:
+        t["gscale"].copy_(grad_loss.detach().reshape(1).to(torch.float32))
+    if dalpha_ext is not None:
+        t["dalpha_ext"] = dalpha_ext.to(torch.float32).contiguous()
+        buf.c.dalpha_ext = _lib.ptr(t["dalpha_ext"])
+    else:
+        buf.c.dalpha_ext = None
+    _lib.check(L_.sat_train_backward(C.byref(d), pw.ref(), C.byref(buf.c), _lib.stream_ptr()), "sat_train_backward")
+    g = t["gscale"]
+    G = {}
+    dlog = t["dlogits"].reshape(M, V)
+    Xo = t["Xo"].reshape(M, E)
+    dWo = _mm_tn(dlog, Xo) * g
+    G["output.output.bias"] = dlog.sum(0, dtype=torch.float32) * g
+    dpre = t["dpre"].reshape(M, E)
+    Hn = t["Hs"][1:].reshape(M, H)
+    G["output.hidden.weight"] = _mm_tn(dpre, Hn)
+    G["output.context.weight"] = _mm_tn(dpre, t["Z"].reshape(M, D))
+    DY = t["DY"].reshape(M, NH3)
+    dWh3 = _mm_tn(DY, t["Hs"][:T].reshape(M, H))
+    G["attention.decoder_att.weight"] = dWh3[:A]
+    G["beta.0.weight"] = dWh3[A:A + D]
+    G["lstm.weight_hh_l0"] = deinterleave_gates(dWh3[A + D:])
+    G["beta.0.bias"] = DY[:, A:A + D].sum(0, dtype=torch.float32)
+    dG = DY[:, A + D:]
+    dWihe = _mm_tn(dG, t["Xe"].reshape(M, E))
+    dWihz = _mm_tn(dG, t["GZ"].reshape(M, D))
+    G["lstm.weight_ih_l0"] = deinterleave_gates(torch.cat([dWihe, dWihz], 1))
+    db = deinterleave_gates(dG.sum(0, dtype=torch.float32))
+    G["lstm.bias_ih_l0"] = db
+    G["lstm.bias_hh_l0"] = db.clone()
+    G["attention.f_att.weight"] = t["dwf_part"].sum((0, 1)).reshape(1, A)
+    dP = t["dP"]
+    if ncap > 1:
+        dP = dP.reshape(Bi, ncap, L, A).sum(1)
+    ann = t["ann"].reshape(Bi * L, D)
+    dPm = dP.reshape(Bi * L, A)
+    G["attention.encoder_att.weight"] = _mm_tn(dPm if ann.dtype == torch.float32 else dPm.to(ann.dtype), ann)
+    dio = t["d_init_out"]
+    G["init_lstm.init.weight"] = _mm_tn(dio, t["f1"].float())
+    G["init_lstm.init.bias"] = dio.sum(0)
+    G["init_lstm.factorize.weight"] = _mm_tn(t["df1"], t["meanv"].float())
+    G["init_lstm.factorize.bias"] = t["df1"].sum(0)
+    tok = t["caps"][:, :T].t().reshape(M).long()
+    dEmb = torch.zeros(V, E, dtype=torch.float32, device=dlog.device)
+    dEmb.index_add_(0, tok, t["dXe"].reshape(M, E))
+    if pad_idx is not None:
+        dEmb[pad_idx].zero_()                                   # nn.Embedding(padding_idx=<PAD>), model.py:162
+    if weight_tying:
+        dEmb = dEmb + dWo
+    else:
+        G["output.output.weight"] = dWo
+    G["embedding.weight"] = dEmb
+    d_ann = t["d_ann"]
+    if ncap > 1:
+        d_ann = d_ann.reshape(Bi, ncap, L, D).sum(1, dtype=torch.float32)
+    else:
+        d_ann = d_ann.reshape(Bi, L, D)
+    return G, d_ann
