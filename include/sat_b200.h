@@ -139,6 +139,12 @@ int sat_abi_sizeof(int which);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 unsigned long long sat_launch_count(void);
 
+/* Kernel timing for bench.py's roofline entry: while enabled, every launch of the selected kernel kind
+ * (1 = attention step forward, 2 = attention step backward, 3 = vocabulary GEMM) is bracketed by CUDA
+ * events on its own stream.  sat_profile_end synchronises, returns the summed device time and count. */
+int sat_profile_begin(int kind);
+int sat_profile_end(float* total_ms, int* count);
+
 /* C[M,N] (ldc) = A[M,K] (lda) * W[N,K]^T (ldw) + bias[N] (optional).  a/w dtype = dtype, C fp32 when
  * c_f32 != 0 else dtype.  The GEMM core shared by every projection below; exported for unit tests.
  * Replaces torch.nn.Linear call sites model.py:72-73,90-92,119-123,188. */

@@ -34,7 +34,8 @@ class SatTrainBuffers(C.Structure):
                 ("reserved", C.c_int32)]
 
 
-EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_linear", "sat_prepare_images",
+EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end",
+           "sat_linear", "sat_prepare_images",
            "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward"]
 
 _lib = None
@@ -69,6 +70,8 @@ def lib():
     for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers)):
         if L.sat_abi_sizeof(i) != C.sizeof(st):
             raise SatError("ABI mismatch for %s: lib %d vs ctypes %d" % (st.__name__, L.sat_abi_sizeof(i), C.sizeof(st)))
+    L.sat_profile_begin.argtypes = [C.c_int]
+    L.sat_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.sat_linear.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                              C.c_int32, C.c_int32, C.c_int32, vp]
     L.sat_prepare_images.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), vp, vp, vp, vp, vp, vp, vp, vp]
@@ -104,6 +107,16 @@ def dtype_code(dt):
     if dt == torch.bfloat16:
         return SAT_BF16
     raise SatError("unsupported dtype %s" % dt)
+
+
+def profile_begin(kind):
+    check(lib().sat_profile_begin(kind), "sat_profile_begin")
+
+
+def profile_end():
+    ms, n = C.c_float(0), C.c_int(0)
+    check(lib().sat_profile_end(C.byref(ms), C.byref(n)), "sat_profile_end")
+    return float(ms.value), int(n.value)
 
 
 def launch_count():

@@ -14,7 +14,43 @@ void sat_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- optional per-kernel event timing (bench.py roofline) --------------------------------------
+#include <vector>
+int g_sat_prof_kind = 0;
+static std::vector<cudaEvent_t> g_prof_events;
+void sat_prof_mark(cudaStream_t st) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof_events.push_back(e);
+}
+
 extern "C" {
+
+int sat_profile_begin(int kind) {
+  for (auto e : g_prof_events) cudaEventDestroy(e);
+  g_prof_events.clear();
+  g_sat_prof_kind = kind;
+  return 0;
+}
+
+int sat_profile_end(float* total_ms, int* count) {
+  g_sat_prof_kind = 0;
+  float tot = 0.0f;
+  int n = 0;
+  for (size_t i = 0; i + 1 < g_prof_events.size(); i += 2) {
+    SAT_CUDA(cudaEventSynchronize(g_prof_events[i + 1]));
+    float ms = 0.0f;
+    SAT_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  for (auto e : g_prof_events) cudaEventDestroy(e);
+  g_prof_events.clear();
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  return 0;
+}
 
 int sat_version(void) { return SAT_ABI_VERSION; }
 

@@ -41,6 +41,11 @@ void sat_set_error(const char* fmt, ...);
 extern unsigned long long g_sat_launches;
 #define SAT_COUNT_LAUNCH() (++g_sat_launches)
 
+// optional per-kernel event timing (sat_profile_begin / sat_profile_end)
+extern int g_sat_prof_kind;
+void sat_prof_mark(cudaStream_t st);
+#define SAT_PROF(kind, st) do { if (g_sat_prof_kind == (kind)) sat_prof_mark(st); } while (0)
+
 // ---- typed loads / stores ------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

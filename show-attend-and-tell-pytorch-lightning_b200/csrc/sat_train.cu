@@ -69,9 +69,11 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
     TS* z_t = (TS*)b.Z + (int64_t)t * B * D;
     TS* gz_t = (TS*)b.GZ + (int64_t)t * B * D;
     TS* beta_t = (TS*)b.Beta + (int64_t)t * B * D;
+    SAT_PROF(1, st);
     attention_step_fwd_kernel<TS, kExact><<<B, ATT_THREADS, att_smem, st>>>(
         ann, (const TS*)b.P, w.wf, b.hp, NH3, b.lens, t, d.ncap, L, D, A, scale, b.alphas + (int64_t)t * L,
         (int64_t)T * L, b.Q + (int64_t)t * B * A, z_t, gz_t, beta_t, D);
+    SAT_PROF(1, st);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     // gates = gz * Wihz^T + Gx[t] + hp[:, A+D:]  -> LSTM cell -> h_{t+1}, c_{t+1}
@@ -85,6 +87,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
                            EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E}, st)));
+  SAT_PROF(3, st);
   if (b.logits_f32) {
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
                              EpiStore<float>{(float*)b.logits, V, w.bo, nullptr, 0}, st)));
@@ -92,6 +95,8 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
                              EpiStore<TS>{(TS*)b.logits, V, w.bo, nullptr, 0}, st)));
   }
+
+  SAT_PROF(3, st);
 
   // ---- loss ------------------------------------------------------------------------------------
   ntok_kernel<<<1, 256, 0, st>>>(b.lens, B, b.out);

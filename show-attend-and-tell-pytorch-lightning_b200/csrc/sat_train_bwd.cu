@@ -46,12 +46,14 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     // dgz = dG * Wihz     (A operand: DY_t[:, A+D:], K = 4H)
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + A + D, NH3, 4 * H), (const TS*)w.WihzT, 4 * H, B, D,
                              EpiStore<float>{b.dgz, D, nullptr, nullptr, 0}, st)));
+    SAT_PROF(2, st);
     att_k<<<B, ATT_THREADS, att_smem, st>>>(ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
                                             (int64_t)T * L, b.S, (const TS*)b.Z + (int64_t)t * B * D,
                                             (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, dHZ_t + H, H + D, b.lens, t, d.ncap,
                                             B, L, D, A, scale, b.att_gamma, b.gscale,
                                             b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, (TS*)b.dZ + (int64_t)t * B * D,
                                             DY_t, NH3, b.dwf_part + (int64_t)t * B * A);
+    SAT_PROF(2, st);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     // dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (rows inactive at t keep their dh)

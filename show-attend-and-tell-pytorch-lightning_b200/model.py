@@ -1,0 +1,506 @@
+"""Drop-in counterpart of the reference's model.py: get_encoder, InitLSTM, SoftAttention, DeepOutput
+and the SAT (Lightning)Module with the same constructor kwargs, attribute / parameter names
+(state_dict compatible) and method signatures -- with the per-timestep decoder
+hot path running in libsat_b200.so (hand-written sm_100a kernels) instead of ~136 ATen ops / step.
+
+Reference spans mirrored (citations are file:line into the reference repository):
+  get_encoder model.py:16-63 (+ readme.md:118-121 encoder_size) | InitLSTM model.py:66-81 |
+  SoftAttention model.py:84-109 | DeepOutput model.py:112-131 | SAT model.py:134-817.
+The CNN trunk stays on cuDNN through PyTorch (it is the boundary, not the target).
+There is no CPU fallback: decoder methods need a CUDA device and the built library.
+"""
+import inspect
+import math
+
+import torch
+from torch import nn
+from torch.nn.utils.rnn import pack_padded_sequence
+
+from . import _lib, decoder
+from .packing import PARAM_NAMES, PackedWeights
+
+try:  # PyTorch-Lightning is optional (not installed in the build image)
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+    _HAVE_PL = True
+except Exception:  # pragma: no cover - exercised in this image
+    pl = None
+    _HAVE_PL = False
+
+    class _HParams(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError as e:
+                raise AttributeError(k) from e
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    class _Base(nn.Module):
+        """Minimal stand-in for pl.LightningModule (hparams, device, no-op logging hooks)."""
+
+        def __init__(self):
+            super().__init__()
+            self.current_epoch = 0
+            self.global_step = 0
+            self.logger = None
+            self.trainer = None
+
+        def save_hyperparameters(self):
+            frame = inspect.currentframe().f_back
+            object.__setattr__(self, "_hparams", _HParams(frame.f_locals.get("kwargs", {})))
+
+        @property
+        def hparams(self):
+            return self._hparams
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        def log(self, *a, **k):
+            pass
+
+        def optimizers(self):
+            return getattr(self, "_optimizer", None)
+
+
+def _hp(args, name, default=None):
+    try:
+        return getattr(args, name)
+    except AttributeError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder (boundary; cuDNN through PyTorch)
+# ------------------------------------------------------------------------------------------------
+class _Normalize(nn.Module):
+    """In-place channel normalisation of [0,1] images: layer 0 of the encoder, as in model.py:59
+    (the caller's image tensor is modified)."""
+
+    def __init__(self, mean, std):
+        super().__init__()
+        self.mean, self.std = list(mean), list(std)
+
+    def forward(self, x):
+        mean = torch.as_tensor(self.mean, dtype=x.dtype, device=x.device).view(1, -1, 1, 1)
+        std = torch.as_tensor(self.std, dtype=x.dtype, device=x.device).view(1, -1, 1, 1)
+        return x.sub_(mean).div_(std)
+
+
+_TRUNK_CUT = (("resnet", -2), ("resnext", -2), ("shufflenet", -1), ("squeezenet", -1), ("densenet", -1),
+              ("mobilenet_v2", -1), ("mobilenet_v3", -2), ("mnasnet", -1))
+
+
+def get_encoder(args):
+    """torchvision trunk without pooling/classifier -> annotations [B, encoder_dim, h, w]
+    (model.py:16-63).  Writes the trunk width back into args.encoder_dim when no 1x1 conv is
+    added (model.py:56).  Optional `encoder_size` appends the resize of readme.md:118-121."""
+    from torchvision import models
+    arch = args.encoder_arch
+    ctor = models.__dict__.get(arch, None)
+    if not callable(ctor):
+        raise ValueError("Unknown model arg: {}".format(arch))
+    pretrained = bool(_hp(args, "pretrained", False))
+    try:
+        m = ctor(weights="DEFAULT" if pretrained else None)
+    except TypeError:
+        m = ctor(pretrained=pretrained)
+    if pretrained:
+        for p in m.parameters():
+            p.requires_grad = False
+    cut = None
+    for key, c in _TRUNK_CUT:
+        if key in arch:
+            cut = c
+            break
+    if cut is None:
+        raise ValueError("Encoder not supported : {}".format(arch))
+    layers = list(m.children())[:cut]
+    with torch.no_grad():
+        probe = nn.Sequential(*layers)(torch.zeros(1, 3, args.input_size, args.input_size))
+    final_dim, final_size = probe.shape[1], probe.shape[2]
+    if args.encoder_dim is not None and args.encoder_dim != final_dim:
+        layers.append(nn.Conv2d(final_dim, args.encoder_dim, kernel_size=1, stride=1, bias=True))
+    else:
+        args.encoder_dim = final_dim
+    size = _hp(args, "encoder_size", None)
+    if size is not None:
+        if size < final_size:
+            layers.append(nn.AdaptiveAvgPool2d((size, size)))
+        elif size > final_size:
+            layers.append(nn.Upsample((size, size), mode="bilinear", align_corners=False))
+    return nn.Sequential(_Normalize(args.mean, args.std), *layers)
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder modules: parameter containers with the reference's names; forward() runs the CUDA kernels
+# ------------------------------------------------------------------------------------------------
+def _as_bld(annotations, dtype):
+    if annotations.dim() == 3:          # [B,L,D] accepted as well
+        x = annotations
+        return (x if x.dtype == dtype else x.to(dtype)).contiguous(), None
+    return decoder.annotations_as_bld(annotations, dtype), annotations.shape[2:]
+
+
+def _linear(x, weight, bias=None):
+    """x [M,K] fp32 cuda, weight [N,K] -> [M,N] through libsat_b200's GEMM core (sat_linear)."""
+    import ctypes as C
+    x = x.contiguous().float()
+    w = weight.detach().contiguous().float()
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    b = bias.detach().contiguous().float() if bias is not None else None
+    _lib.check(_lib.lib().sat_linear(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(out), N, M, N, K,
+                                     _lib.SAT_F32, 1, 0, _lib.stream_ptr()), "sat_linear")
+    return out
+
+
+class InitLSTM(nn.Module):
+    """model.py:66-81: mean over locations -> factorize -> init -> [B,2H] read back as [2*layers,B,H]."""
+
+    def __init__(self, args, bias=True):
+        super().__init__()
+        self.decoder_dim = args.decoder_dim
+        self.decoder_layers = args.decoder_layers
+        self.factorize = nn.Linear(args.encoder_dim, args.embed_dim, bias=bias)
+        self.init = nn.Linear(args.embed_dim, 2 * args.decoder_dim * args.decoder_layers, bias=bias)
+        self.dropout = nn.Dropout(p=args.dropout)
+
+    @torch.no_grad()
+    def forward(self, annotations):
+        bld, _ = _as_bld(annotations, torch.float32)
+        mean = self.dropout(bld.mean(1))
+        out = _linear(_linear(mean, self.factorize.weight, self.factorize.bias), self.init.weight, self.init.bias)
+        st = out.reshape(2 * self.decoder_layers, mean.shape[0], self.decoder_dim)
+        return st[:self.decoder_layers], st[self.decoder_layers:]
+
+
+class SoftAttention(nn.Module):
+    """model.py:84-109 (additive attention, L^-0.5 score scale, no biases)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.encoder_att = nn.Linear(args.encoder_dim, args.attention_dim, bias=False)
+        self.decoder_att = nn.Linear(args.decoder_dim, args.attention_dim, bias=False)
+        self.f_att = nn.Linear(args.attention_dim, 1, bias=False)
+
+    @torch.no_grad()
+    def forward(self, annotations, decoder_hidden):
+        """-> (z [B,D], alpha [B,h,w])  (alpha [B,L] for 3-D annotations)."""
+        import ctypes as C
+        bld, hw = _as_bld(annotations, torch.float32)
+        B, L, D = bld.shape
+        A = self.encoder_att.weight.shape[0]
+        P = _linear(bld.reshape(B * L, D), self.encoder_att.weight).reshape(B, L, A)
+        hp = torch.zeros(B, A + D, dtype=torch.float32, device=bld.device)
+        hp[:, :A] = _linear(decoder_hidden, self.decoder_att.weight)
+        d = decoder.make_dims(B, B, L, D, A, 8, decoder_hidden.shape[1], 8, 1, torch.float32, True, False)
+        alpha = torch.empty(B, L, dtype=torch.float32, device=bld.device)
+        z = torch.empty(B, D, dtype=torch.float32, device=bld.device)
+        gz = torch.empty_like(z)
+        wf = self.f_att.weight.detach().reshape(-1).contiguous().float()
+        _lib.check(_lib.lib().sat_attention_step_fwd(C.byref(d), _lib.ptr(bld), _lib.ptr(P), _lib.ptr(wf), _lib.ptr(hp),
+                                                     A + D, None, 0, _lib.ptr(alpha), L, _lib.ptr(z), _lib.ptr(gz), None, D,
+                                                     _lib.stream_ptr()), "sat_attention_step_fwd")
+        return z, (alpha.reshape(B, *hw) if hw is not None else alpha)
+
+
+class DeepOutput(nn.Module):
+    """model.py:112-131."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.deep = args.deep_output
+        self.dropout = nn.Dropout(p=args.dropout)
+        self.hidden = nn.Linear(args.decoder_dim, args.embed_dim, bias=False)
+        if self.deep:
+            self.context = nn.Linear(args.encoder_dim, args.embed_dim, bias=False)
+        self.output = nn.Linear(args.embed_dim, args.vocab_size, bias=(not args.weight_tying))
+
+    @torch.no_grad()
+    def forward(self, prev_embed, hidden, context):
+        if self.deep:
+            x = torch.tanh(prev_embed.float() + _linear(torch.cat([hidden.float(), context.float()], 1),
+                                                        torch.cat([self.hidden.weight, self.context.weight], 1)))
+        else:
+            x = _linear(hidden, self.hidden.weight)
+        return _linear(self.dropout(x), self.output.weight, self.output.bias)
+
+
+class LabelSmoothing(nn.Module):
+    """util.py:91-112 (kept as `criterion` for callers that score packed logits themselves)."""
+
+    def __init__(self, smoothing=0.0):
+        super().__init__()
+        self.confidence = 1.0 - smoothing
+        self.smoothing = smoothing
+
+    def forward(self, x, target):
+        lp = torch.log_softmax(x, dim=-1)
+        nll = -lp.gather(-1, target.unsqueeze(1)).squeeze(1)
+        return (self.confidence * nll + self.smoothing * (-lp.mean(-1))).mean()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd bridges
+# ------------------------------------------------------------------------------------------------
+class _FusedTrainLoss(torch.autograd.Function):
+    """loss (+ aux) of one teacher-forced step; backward = hand-written BPTT (sat_train_backward)."""
+
+    @staticmethod
+    def forward(ctx, ann, caps, lens, cfg, *params):
+        W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
+        pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
+        bld = decoder.annotations_as_bld(ann, cfg["dtype"])
+        buf = decoder.train_forward(pw, bld, caps, lens, cfg["label_smoothing"], cfg["att_gamma"], exact=cfg["exact"],
+                                    use_tc=cfg["use_tc"], logits_f32=False, backward=True, keep_logits=False)
+        ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
+        ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
+        ctx.have = [p is not None for p in params]
+        out = buf.t["out"]
+        aux = out.detach().clone()
+        ctx.mark_non_differentiable(aux)
+        return out[0].clone(), aux
+
+    @staticmethod
+    def backward(ctx, gloss, _gaux):
+        cfg = ctx.cfg
+        G, d_ann = decoder.train_backward(ctx.pw, ctx.buf, gloss, pad_idx=cfg["pad_idx"], weight_tying=cfg["weight_tying"])
+        Bi, D, h, w = ctx.ann_shape
+        d_ann = d_ann.reshape(Bi, h, w, D).permute(0, 3, 1, 2).to(ctx.ann_dtype)
+        grads = [G.get(n) if have else None for n, have in zip(PARAM_NAMES, ctx.have)]
+        ctx.buf = None
+        return (d_ann, None, None, None, *grads)
+
+
+class _TrainLogits(torch.autograd.Function):
+    """API path of train_batch: returns padded fp32 logits [B,T,V] and alphas [B,T,L]; backward takes
+    arbitrary upstream grads for both (the caller computes its own loss, e.g. temperature_scaling.py:38)."""
+
+    @staticmethod
+    def forward(ctx, ann, caps, lens, cfg, *params):
+        W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
+        pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
+        bld = decoder.annotations_as_bld(ann, cfg["dtype"])
+        buf = decoder.train_forward(pw, bld, caps, lens, 0.0, 0.0, exact=cfg["exact"], use_tc=cfg["use_tc"],
+                                    logits_f32=True, backward=True, keep_logits=True)
+        ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
+        ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
+        ctx.have = [p is not None for p in params]
+        logits = buf.t["logits"].permute(1, 0, 2).contiguous()          # [B,T,V] fp32 (model.py:504)
+        return logits, buf.t["alphas"].clone()
+
+    @staticmethod
+    def backward(ctx, glogits, galphas):
+        cfg, buf = ctx.cfg, ctx.buf
+        buf.t["dlogits"].copy_(glogits.permute(1, 0, 2))
+        saved_gamma = buf.c.att_gamma
+        buf.c.att_gamma = 0.0
+        G, d_ann = decoder.train_backward(ctx.pw, buf, None, pad_idx=cfg["pad_idx"], weight_tying=cfg["weight_tying"],
+                                          dalpha_ext=galphas)
+        buf.c.att_gamma = saved_gamma
+        Bi, D, h, w = ctx.ann_shape
+        d_ann = d_ann.reshape(Bi, h, w, D).permute(0, 3, 1, 2).to(ctx.ann_dtype)
+        grads = [G.get(n) if have else None for n, have in zip(PARAM_NAMES, ctx.have)]
+        ctx.buf = None
+        return (d_ann, None, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# SAT
+# ------------------------------------------------------------------------------------------------
+class SAT(_Base):
+    """Show, Attend and Tell (model.py:134-817) with the decoder on libsat_b200.so.
+
+    Extra (optional) hparams: encoder_size (readme.md:118-121), precision in {"fp32","bf16"}
+    (fp32 = parity mode with exact transcendental paths; bf16 = tcgen05 tensor-core mode).
+    """
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.save_hyperparameters()
+        hp = self.hparams
+        self.scheduler = None
+        self.opt_init_lr = None
+        for k, v in (("decoder_layers", 1), ("dropout", 0.0), ("embedding_dropout", 0.0), ("label_smoothing", 0.0),
+                     ("weight_tying", False), ("deep_output", False), ("embed_norm", None), ("pretrained_embedding", None),
+                     ("att_gamma", 1.0), ("decoder_tf", None), ("encoder_size", None), ("precision", "fp32"),
+                     ("encoder_finetune_after", -1), ("lr_warmup_steps", 0)):
+            if k not in hp:
+                hp[k] = v
+        assert 0 <= hp.label_smoothing < (hp.vocab_size - 1) / hp.vocab_size
+        if hp.decoder_layers != 1:
+            raise NotImplementedError("decoder_layers > 1 is not on the accelerated path (BASELINE configs use 1 layer)")
+        self.criterion = LabelSmoothing(hp.label_smoothing)
+        self.special_idxs = [self.stoi("<PAD>"), self.stoi("<START>"), self.stoi("<END>")]
+        # module construction order follows model.py:154-195 so that a seeded default init is identical
+        self.encoder = get_encoder(hp)
+        self.embedding = nn.Embedding(num_embeddings=hp.vocab_size, embedding_dim=hp.embed_dim, max_norm=hp.embed_norm,
+                                      padding_idx=self.stoi("<PAD>"))
+        self.embedding_dropout = nn.Dropout(p=hp.embedding_dropout)
+        if hp.pretrained_embedding is not None:
+            import numpy as np
+            self.embedding.weight = nn.Parameter(torch.tensor(np.load(hp.pretrained_embedding), dtype=torch.float32))
+        self.init_lstm = InitLSTM(hp, bias=True)
+        self.lstm = nn.LSTM(input_size=hp.embed_dim + hp.encoder_dim, hidden_size=hp.decoder_dim,
+                            num_layers=hp.decoder_layers, bias=True)      # parameter container (names/shapes/init)
+        self.attention = SoftAttention(hp)
+        self.beta = nn.Sequential(nn.Linear(hp.decoder_dim, hp.encoder_dim, bias=True), nn.Sigmoid())
+        fan_in = self.beta[0].weight.shape[1]
+        self.beta[0].bias.data.fill_(1 / fan_in)                            # model.py:191-192
+        self.output = DeepOutput(hp)
+        if hp.weight_tying and hp.deep_output:
+            self.output.output.weight = self.embedding.weight
+        self._packed_infer = None
+
+    # ---- vocabulary helpers (model.py:202-212) ------------------------------------------------
+    def stoi(self, s):
+        return int(self.hparams.vocab_stoi.get(s, self.hparams.vocab_stoi["<UNK>"]))
+
+    def itos(self, i):
+        return str(self.hparams.vocab_itos.get(int(i), "<UNK>"))
+
+    def decode_seq(self, seq, remove_special=False):
+        return [str(self.itos(t)) for t in seq if not (remove_special and t in self.special_idxs)]
+
+    # ---- plumbing -----------------------------------------------------------------------------
+    def _dtype(self):
+        return torch.bfloat16 if str(self.hparams.precision).lower() in ("bf16", "bfloat16") else torch.float32
+
+    def _cfg(self):
+        dt = self._dtype()
+        return dict(dtype=dt, exact=(dt == torch.float32), use_tc=(dt == torch.bfloat16),
+                    label_smoothing=float(self.hparams.label_smoothing), att_gamma=float(self.hparams.att_gamma),
+                    pad_idx=self.stoi("<PAD>"), weight_tying=bool(self.hparams.weight_tying and self.hparams.deep_output))
+
+    def decoder_weights(self):
+        """reference-named decoder parameters in PARAM_NAMES order (None where absent)."""
+        sd = dict(self.named_parameters())
+        if "output.output.weight" not in sd:           # tied: shares embedding.weight
+            sd["output.output.weight"] = self.embedding.weight
+        return [sd.get(n) for n in PARAM_NAMES]
+
+    def encode(self, img):
+        """images -> annotations [B,D,h,w]; bf16 mode runs the trunk channels_last under autocast so the
+        result is physically the [B,L,D] array the kernels read (zero-copy)."""
+        if self._dtype() == torch.bfloat16 and img.is_cuda:
+            img = img.contiguous(memory_format=torch.channels_last)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.encoder(img)
+        return self.encoder(img)
+
+    # ---- training (model.py:474-628) ----------------------------------------------------------
+    def train_batch(self, batch, epsilon=0):
+        """-> (PackedSequence logits fp32, PackedSequence targets, alphas [B,T,L])  (model.py:557)."""
+        if float(epsilon) < 1.0:
+            raise NotImplementedError("scheduled sampling (epsilon < 1, model.py:518-523) is not on the accelerated "
+                                      "path yet; use epsilon=1 / decoder_tf='always'")
+        if self.training and (self.hparams.dropout > 0 or self.hparams.embedding_dropout > 0):
+            raise NotImplementedError("dropout > 0 is not on the accelerated path yet")
+        img, encoded_captions, lengths = batch
+        ann = self.encode(img)
+        logits, alphas = _TrainLogits.apply(ann, encoded_captions, lengths, self._cfg(), *self.decoder_weights())
+        caps = encoded_captions.reshape(-1, encoded_captions.size(2))
+        lens = lengths.reshape(-1).tolist()
+        logits_packed = pack_padded_sequence(logits, lens, batch_first=True, enforce_sorted=False)
+        targets_packed = pack_padded_sequence(caps[:, 1:], lens, batch_first=True, enforce_sorted=False)
+        return logits_packed, targets_packed, alphas
+
+    def fused_loss(self, batch):
+        """Fused forward + loss of one teacher-forced step: (loss with grad, aux[8] = loss, ce, reg,
+        accuracy, 1/ntok, ntok).  This is what training_step runs."""
+        if self.training and (self.hparams.dropout > 0 or self.hparams.embedding_dropout > 0):
+            raise NotImplementedError("dropout > 0 is not on the accelerated path yet")
+        img, encoded_captions, lengths = batch
+        ann = self.encode(img)
+        return _FusedTrainLoss.apply(ann, encoded_captions, lengths, self._cfg(), *self.decoder_weights())
+
+    def _epsilon(self):
+        hp = self.hparams
+        tf = hp.decoder_tf
+        if tf is None:
+            return 0.0
+        if tf == "always":
+            return 1.0
+        if tf == "linear":
+            return 1 - (1 - hp.decoder_tf_min) * self.current_epoch / hp.epochs
+        if tf == "inv_sigmoid":
+            l = -math.log(hp.decoder_tf_min / (1 - hp.decoder_tf_min))
+            g = 5.0
+            b = (1 / ((l / g) + 1)) * hp.epochs
+            return 1 / (1 + math.exp((g / b) * (self.current_epoch - b)))
+        if tf == "exp":
+            return math.exp(math.log(hp.decoder_tf_min) / hp.epochs) ** self.current_epoch
+        raise ValueError("unknown decoder_tf {}".format(tf))
+
+    def training_step(self, batch, batch_idx):
+        hp = self.hparams
+        epsilon = self._epsilon()
+        if epsilon < 1.0:
+            raise NotImplementedError("decoder_tf != 'always' (scheduled sampling) is not on the accelerated path yet")
+        if self.global_step == hp.encoder_finetune_after and hp.encoder_finetune_after >= 0:
+            for p in self.encoder.parameters():
+                p.requires_grad = True
+        loss, aux = self.fused_loss(batch)
+        metrics = {"loss": loss, "accuracy": aux[3], "epsilon_tf": float(epsilon)}   # device scalars: no sync here
+        logger = getattr(self, "logger", None)
+        if logger is not None and getattr(logger, "experiment", None) is not None:
+            for k, v in metrics.items():
+                logger.experiment.add_scalar("{}/train".format(k), float(v), global_step=self.global_step)
+        return metrics
+
+    # ---- inference (model.py:214-472) ---------------------------------------------------------
+    @torch.no_grad()
+    def caption(self, img_tensor, beamk=3, max_gen_length=32, temperature=1.0, sample_method="beam", sample_topk=3,
+                decoder_noise=None, rescore_method=None, rescore_reward=0.5, return_all=False):
+        self.eval()
+        return self.forward(img_tensor, beamk, max_gen_length, temperature, sample_method, sample_topk, decoder_noise,
+                            rescore_method, rescore_reward, return_all)
+
+    @torch.no_grad()
+    def forward(self, img, beamk=3, max_gen_length=32, temperature=1.0, sample_method="beam", sample_topk=3,
+                decoder_noise=None, rescore_method=None, rescore_reward=0.5, return_all=False):
+        assert sample_method in ["beam", "multinomial", "topk"]
+        if sample_method != "beam" or (decoder_noise is not None and decoder_noise != 0.0):
+            raise NotImplementedError("only sample_method='beam' without decoder noise is on the accelerated path")
+        from . import decode
+        ann = self.encode(img)
+        return decode.caption_from_annotations(self, ann, beamk, max_gen_length, temperature, rescore_method,
+                                               rescore_reward, return_all)
+
+    # ---- optimisers (model.py:720-817; host-side, stock torch) ---------------------------------
+    def configure_optimizers(self):
+        hp = self.hparams
+
+        def groups(modules, wd, lr):
+            decay, no_decay = [], []
+            for m in modules:
+                for _, p in m.named_parameters():
+                    if p.requires_grad:
+                        (no_decay if p.dim() == 1 else decay).append(p)
+            return [{"params": no_decay, "lr": lr, "weight_decay": 0.0}, {"params": decay, "lr": lr, "weight_decay": wd}]
+
+        wd = _hp(hp, "weight_decay", 0.0)
+        lr = _hp(hp, "decoder_lr", 1e-3)
+        params = groups([self.init_lstm, self.lstm, self.attention, self.beta, self.output], wd, lr)
+        if _hp(hp, "embedding_lr", lr) > 0 and not hp.weight_tying:
+            params += [{"params": self.embedding.parameters(), "lr": _hp(hp, "embedding_lr", lr), "weight_decay": 0.0}]
+        if _hp(hp, "encoder_lr", 0.0) > 0 and (_hp(hp, "encoder_finetune_after", -1) > 0 or not hp.pretrained):
+            params += groups([self.encoder], wd, hp.encoder_lr)
+        opt = _hp(hp, "opt", "adam")
+        if opt == "sgd":
+            optimizer = torch.optim.SGD(params, lr=lr, momentum=_hp(hp, "momentum", 0.9), nesterov=_hp(hp, "nesterov", False))
+        elif opt == "adamw":
+            optimizer = torch.optim.AdamW(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)))
+        else:
+            optimizer = torch.optim.Adam(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)))
+        self.opt_init_lr = [pg["lr"] for pg in optimizer.param_groups]
+        self._optimizer = optimizer
+        return optimizer

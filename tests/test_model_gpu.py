@@ -1,0 +1,103 @@
+"""GPU: the SAT module API (train_batch / fused training loss / autograd) against the CPU oracle, with the CNN
+trunk replaced by nn.Identity() so that decoder parity is measured on identical annotations."""
+import warnings
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import ref_harness as rh
+from oracle import sat_oracle as O
+from test_train_forward_gpu import relerr
+
+warnings.filterwarnings("ignore")
+pytestmark = pytest.mark.gpu
+
+
+def build(seed=0, **over):
+    from sat_b200.model import SAT
+    torch.manual_seed(seed)
+    hp = rh.default_hparams(encoder_dim=64, attention_dim=32, embed_dim=32, decoder_dim=64, vocab_size=128, input_size=64, **over)
+    m = SAT(**hp)
+    m.encoder = nn.Identity()
+    with torch.no_grad():
+        m.attention.f_att.weight *= 10
+    return m.cuda()
+
+
+def batch(seed, Bi=5, ncap=2, T=7, V=128, D=64, hw=(4, 3)):
+    g = torch.Generator().manual_seed(seed)
+    ann = torch.randn(Bi, D, hw[0], hw[1], generator=g)
+    caps = torch.randint(1, V - 3, (Bi, ncap, T + 1), generator=g)
+    caps[:, :, 0] = V - 2
+    lens = torch.randint(2, T + 1, (Bi, ncap), generator=g)
+    return ann, caps, lens
+
+
+def weights_cpu(m):
+    return {k: v.detach().cpu().clone() for k, v in m.state_dict().items() if not k.startswith("encoder")}
+
+
+def test_train_batch_matches_oracle_and_is_differentiable():
+    m = build(label_smoothing=0.1)
+    ann, caps, lens = batch(1)
+    W = {k: v.requires_grad_(True) for k, v in weights_cpu(m).items()}
+    a_ref = ann.clone().requires_grad_(True)
+    ref = O.train_loss(W, a_ref, caps, lens, 0.1, 1.0)
+    ref["loss"].backward()
+    m.train()
+    a = ann.cuda().requires_grad_(True)
+    lp, tp, alphas = m.train_batch((a, caps.cuda(), lens.cuda()), epsilon=1)
+    assert lp.data.dtype == torch.float32                                  # model.py:504
+    assert torch.equal(tp.data.cpu(), ref["targets_packed"].data)
+    assert torch.equal(lp.batch_sizes, ref["logits_packed"].batch_sizes)
+    assert relerr(lp.data, ref["logits_packed"].data) < 1e-5
+    assert relerr(alphas, ref["alphas"]) < 1e-5
+    loss = m.criterion(lp.data, tp.data) + m.hparams.att_gamma * ((1 - alphas.sum(dim=1)) ** 2).mean()   # model.py:592-594
+    assert abs(float(loss) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        assert relerr(p.grad, W[k].grad) < 5e-5, k
+    assert relerr(a.grad, a_ref.grad) < 5e-5
+
+
+def test_training_step_fused_loss_and_grads():
+    m = build(seed=1, label_smoothing=0.05)
+    ann, caps, lens = batch(2, ncap=1)
+    W = {k: v.requires_grad_(True) for k, v in weights_cpu(m).items()}
+    ref = O.train_loss(W, ann, caps, lens, 0.05, 1.0)
+    ref["loss"].backward()
+    m.train()
+    out = m.training_step((ann.cuda(), caps.cuda(), lens.cuda()), 0)
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    assert abs(float(out["accuracy"]) - float(ref["acc"])) < 1e-6
+    out["loss"].backward()
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, W[k].grad) < 5e-5, k
+
+
+def test_module_forwards_match_oracle():
+    m = build(seed=2)
+    ann, _, _ = batch(3, ncap=1)
+    W = weights_cpu(m)
+    h = torch.randn(5, 64)
+    z_ref, al_ref = O.attention(W, ann, h)
+    z, al = m.attention(ann.cuda(), h.cuda())
+    assert al.shape == (5, 4, 3)
+    assert relerr(z, z_ref) < 1e-5 and relerr(al.reshape(5, -1), al_ref) < 1e-5
+    h0_ref, c0_ref = O.init_lstm(W, ann)
+    h0, c0 = m.init_lstm(ann.cuda())
+    assert h0.shape == (1, 5, 64)
+    assert relerr(h0[0], h0_ref) < 1e-5 and relerr(c0[0], c0_ref) < 1e-5
+    xe = torch.randn(5, 32)
+    lo_ref = O.deep_output(W, xe, h, z_ref)
+    lo = m.output(xe.cuda(), h.cuda(), z_ref.cuda())
+    assert relerr(lo, lo_ref) < 1e-5
+
+
+def test_scheduled_sampling_not_silently_wrong():
+    m = build()
+    ann, caps, lens = batch(1)
+    with pytest.raises(NotImplementedError):
+        m.train_batch((ann.cuda(), caps.cuda(), lens.cuda()), epsilon=0)
