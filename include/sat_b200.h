@@ -132,9 +132,50 @@ typedef struct SatTrainBuffers {
   int32_t reserved;
 } SatTrainBuffers;
 
+/* Buffers of one batched greedy / beam decode (SAT.forward / SAT.caption, model.py:214-472, sample_method
+ * "beam", no decoder noise).  All images advance together; R = n_img * k rows, the beams of image n are rows
+ * n*k .. n*k+kcur[n]-1 (order-preserving compaction, like the reference's boolean indexing). */
+typedef struct SatDecodeBuffers {
+  const void* ann;       /* [n_img,L,D] s                                                        */
+  void* P;               /* [n_img,L,A] s                                                        */
+  void* meanv;           /* [n_img,D] s                                                          */
+  void* f1;              /* [n_img,E] s                                                          */
+  float* init_out;       /* [n_img,2H]                                                           */
+  const float* GxV;      /* [V,4H]  Emb * Wihe^T + bg per vocabulary entry (sat_decode_prepare_weights) */
+  void* h;               /* [R,H] s   state entering the step                                     */
+  float* c;              /* [R,H]                                                                 */
+  void* hn;              /* [R,H] s   state after the LSTM update, before the beam reorder         */
+  float* cn;             /* [R,H]                                                                 */
+  float* hp;             /* [R,A+D+4H]                                                            */
+  void* z;               /* [R,D] s                                                               */
+  void* gz;              /* [R,D] s                                                               */
+  void* xo;              /* [R,E] s                                                               */
+  float* logits;         /* [R,V]                                                                 */
+  float* alpha_all;      /* [S+1,R,L]  alpha of every step and row (histories hold row indices)    */
+  float* cand_val;       /* [R,k]                                                                 */
+  int32_t* cand_idx;     /* [R,k]                                                                 */
+  int32_t* tok_hist;     /* [2,R,S+1]  generated words per live beam (ping-pong)                   */
+  int32_t* asrc_hist;    /* [2,R,S+1]  row of alpha_all[step] that belongs to the beam's ancestry  */
+  float* top_scores;     /* [R]                                                                   */
+  int32_t* cur_tok;      /* [R]        previous word of each beam                                 */
+  int32_t* src_row;      /* [R]        row of hn/cn each new beam continues from                   */
+  int32_t* alive;        /* [R]                                                                   */
+  int32_t* kcur;         /* [n_img]    live beams per image                                       */
+  int32_t* fin_tokens;   /* [n_img,k,S+1]  finished captions (START/END stripped), in finishing order */
+  int32_t* fin_asrc;     /* [n_img,k,S+1]                                                         */
+  int32_t* fin_len;      /* [n_img,k]                                                             */
+  float* fin_score;      /* [n_img,k]  rescored (None / LN / WR / BAR, model.py:405-417)           */
+  float* fin_ppl;        /* [n_img,k]  exp(-score/step) (model.py:425)                             */
+  int32_t* fin_count;    /* [n_img]                                                               */
+  const float* temps;    /* HOST pointer, [S+1]: temperature per step (model.py:292)              */
+  int32_t k, max_gen_length, rescore;   /* rescore: 0 none, 1 LN, 2 WR, 3 BAR                      */
+  float reward;
+  int32_t tokPAD, tokSTART, tokEND, tokUNK;
+} SatDecodeBuffers;
+
 int sat_version(void);
 const char* sat_last_error(void);
-/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers */
+/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers, 3 SatDecodeBuffers */
 int sat_abi_sizeof(int which);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 unsigned long long sat_launch_count(void);
@@ -174,6 +215,13 @@ int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b,
  * reductions over (b,t) that produce parameter gradients are plain GEMMs on these buffers and
  * are done by the host (cuBLAS through torch). */
 int sat_train_backward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
+
+/* GxV[v,:] = Emb[v,:] * Wihe^T + bg for every vocabulary entry (once per set of weights). */
+int sat_decode_prepare_weights(const SatDims* d, const SatWeights* w, float* GxV, void* stream);
+
+/* Batched greedy (k = 1) / beam decode; d->B = n_img * k rows, d->Bi = n_img, d->ncap = k.  Runs
+ * max_gen_length + 1 steps with device-side bookkeeping (no host sync); results are in the fin_* buffers. */
+int sat_decode(const SatDims* d, const SatWeights* w, SatDecodeBuffers* b, void* stream);
 
 #ifdef __cplusplus
 }

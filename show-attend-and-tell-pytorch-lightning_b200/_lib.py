@@ -34,9 +34,18 @@ class SatTrainBuffers(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class SatDecodeBuffers(C.Structure):
+    _fields_ = [(n, vp) for n in
+                ("ann", "P", "meanv", "f1", "init_out", "GxV", "h", "c", "hn", "cn", "hp", "z", "gz", "xo", "logits",
+                 "alpha_all", "cand_val", "cand_idx", "tok_hist", "asrc_hist", "top_scores", "cur_tok", "src_row", "alive",
+                 "kcur", "fin_tokens", "fin_asrc", "fin_len", "fin_score", "fin_ppl", "fin_count", "temps")] + \
+               [("k", C.c_int32), ("max_gen_length", C.c_int32), ("rescore", C.c_int32), ("reward", C.c_float),
+                ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32)]
+
+
 EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end",
            "sat_linear", "sat_prepare_images",
-           "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward"]
+           "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward", "sat_decode_prepare_weights", "sat_decode"]
 
 _lib = None
 
@@ -67,7 +76,7 @@ def lib():
     L.sat_last_error.restype = C.c_char_p
     L.sat_launch_count.restype = C.c_ulonglong
     L.sat_abi_sizeof.argtypes = [C.c_int]
-    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers)):
+    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers, SatDecodeBuffers)):
         if L.sat_abi_sizeof(i) != C.sizeof(st):
             raise SatError("ABI mismatch for %s: lib %d vs ctypes %d" % (st.__name__, L.sat_abi_sizeof(i), C.sizeof(st)))
     L.sat_profile_begin.argtypes = [C.c_int]
@@ -79,6 +88,8 @@ def lib():
                                          vp, vp, vp, C.c_int64, vp]
     L.sat_train_forward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
     L.sat_train_backward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
+    L.sat_decode_prepare_weights.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), vp, vp]
+    L.sat_decode.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatDecodeBuffers), vp]
     _lib = L
     return L
 

@@ -63,6 +63,7 @@ int sat_abi_sizeof(int which) {
     case 0: return (int)sizeof(SatDims);
     case 1: return (int)sizeof(SatWeights);
     case 2: return (int)sizeof(SatTrainBuffers);
+    case 3: return (int)sizeof(SatDecodeBuffers);
     default: return -1;
   }
 }

@@ -1,0 +1,113 @@
+// Batched greedy / beam decode driver (SAT.forward, model.py:237-472): every image of the batch advances
+// together, beams live in device memory, and one step is
+//   h-projection GEMM -> fused attention -> gate GEMM + LSTM epilogue -> deep-output GEMM -> vocabulary GEMM
+//   -> row top-k (log-softmax, masks, parent score) -> per-image beam update -> state gather
+// with no host synchronisation (the reference loops over images one at a time and syncs several times a step).
+#include "sat_decode_kernels.cuh"
+#include "sat_gemm.cuh"
+#include "sat_kernels.cuh"
+
+namespace {
+
+template <typename TS, bool kExact>
+int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cudaStream_t st) {
+  const int R = d.B, n_img = d.Bi, k = d.ncap, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H, V = d.V;
+  const int S = b.max_gen_length;
+  const int NH3 = A + D + 4 * H;
+  const bool tc = d.use_tc != 0;
+  const TS* ann = (const TS*)b.ann;
+
+  // once per image: P = ann * Wa^T, mean, InitLSTM
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, n_img * L, A,
+                           EpiStore<TS>{(TS*)b.P, A, nullptr, nullptr, 0}, st)));
+  const int NV = D / Vec16<TS>::N;
+  mean_L_kernel<TS><<<dim3((NV + 127) / 128, n_img), 128, 0, st>>>(ann, (TS*)b.meanv, L, D);
+  SAT_COUNT_LAUNCH();
+  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(b.meanv, D, D), (const TS*)w.Wfact, D, n_img, E,
+                           EpiStore<TS>{(TS*)b.f1, E, w.bfact, nullptr, 0}, st)));
+  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(b.f1, E, E), (const TS*)w.Winit, E, n_img, 2 * H,
+                           EpiStore<float>{b.init_out, 2 * H, w.binit, nullptr, 0}, st)));
+  init_state_decode_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>(b.init_out, (TS*)b.h, b.c, n_img, k, H);
+  SAT_COUNT_LAUNCH();
+  decode_init_kernel<<<(R + 255) / 256, 256, 0, st>>>(b.cur_tok, b.alive, b.top_scores, b.kcur, b.fin_count, b.fin_len, R, n_img, k,
+                                                      b.tokSTART);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+
+  const float scale = (float)(1.0 / sqrt((double)L));
+  const size_t att_smem = attention_fwd_smem(L, D, A, Vec16<TS>::N);
+  const size_t topk_smem = sizeof(float) * (size_t)(V + 40);
+  if (topk_smem > 48 * 1024)
+    SAT_CUDA(cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+  BeamParams bp{k, V, S, b.tokEND, b.rescore, b.reward, S + 1};
+  const int64_t hist_sz = (int64_t)R * (S + 1);
+
+  for (int step = 0; step <= S; ++step) {
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.h, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
+                             st)));
+    SAT_PROF(1, st);
+    attention_step_fwd_kernel<TS, kExact><<<R, ATT_THREADS, att_smem, st>>>(
+        ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, k, L, D, A, scale, b.alpha_all + (int64_t)step * R * L, L, nullptr,
+        (TS*)b.z, (TS*)b.gz, (TS*)nullptr, D);
+    SAT_PROF(1, st);
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+    EpiLstm<TS, kExact> epi{b.GxV, 4 * H, b.hp + A + D, NH3, (const TS*)b.h, b.c, (TS*)b.hn, b.cn, H, H,
+                            (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.gz, D, D), (const TS*)w.Wihz, D, R, 4 * H, epi, st)));
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(b.hn, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
+                             EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok}, st)));
+    SAT_PROF(3, st);
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
+    SAT_PROF(3, st);
+    row_topk_kernel<<<R, 256, topk_smem, st>>>(b.logits, b.top_scores, b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART,
+                                               b.tokEND, b.tokUNK, b.cand_val, b.cand_idx);
+    SAT_COUNT_LAUNCH();
+    const int in = step & 1, out = in ^ 1;
+    beam_update_kernel<<<n_img, 32, 0, st>>>(bp, step, b.cand_val, b.cand_idx, b.kcur, b.top_scores, b.cur_tok, b.src_row, b.alive,
+                                             b.tok_hist + in * hist_sz, b.asrc_hist + in * hist_sz, b.tok_hist + out * hist_sz,
+                                             b.asrc_hist + out * hist_sz, b.fin_tokens, b.fin_asrc, b.fin_len, b.fin_score,
+                                             b.fin_ppl, b.fin_count);
+    SAT_COUNT_LAUNCH();
+    gather_state_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>((const TS*)b.hn, b.cn, b.src_row, b.alive,
+                                                                                      (TS*)b.h, b.c, R, H);
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sat_decode_prepare_weights(const SatDims* d, const SatWeights* w, float* GxV, void* stream) {
+  SAT_REQUIRE(d && w && GxV && w->Emb && w->Wihe && w->bg, "sat_decode_prepare_weights: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = d->use_tc != 0;
+  if (d->dtype == SAT_F32)
+    return gemm_tn<float, float>(false, gemm_a1(w->Emb, d->E, d->E), (const float*)w->Wihe, d->E, d->V, 4 * d->H,
+                                 EpiStore<float>{GxV, 4 * d->H, w->bg, nullptr, 0}, st);
+  return gemm_tn<bf16, bf16>(tc, gemm_a1(w->Emb, d->E, d->E), (const bf16*)w->Wihe, d->E, d->V, 4 * d->H,
+                             EpiStore<float>{GxV, 4 * d->H, w->bg, nullptr, 0}, st);
+}
+
+int sat_decode(const SatDims* d, const SatWeights* w, SatDecodeBuffers* b, void* stream) {
+  SAT_REQUIRE(d && w && b, "sat_decode: NULL struct");
+  SAT_REQUIRE(d->dtype == SAT_F32 || d->dtype == SAT_BF16, "unknown dtype %d", d->dtype);
+  SAT_REQUIRE(d->B == d->Bi * d->ncap && d->ncap == b->k && b->k >= 1 && b->k <= 32, "sat_decode: rows %d != n_img %d * k %d (k <= 32)",
+              d->B, d->Bi, b->k);
+  SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0, "dims must be multiples of 8");
+  SAT_REQUIRE(b->max_gen_length >= 1 && b->temps, "sat_decode: max_gen_length >= 1 and temps required");
+  SAT_REQUIRE(b->k + 4 <= d->V, "sat_decode: beam width %d too large for vocab %d", b->k, d->V);
+  SAT_REQUIRE(b->ann && b->P && b->meanv && b->f1 && b->init_out && b->GxV && b->h && b->c && b->hn && b->cn && b->hp && b->z &&
+                  b->gz && b->xo && b->logits && b->alpha_all && b->cand_val && b->cand_idx && b->tok_hist && b->asrc_hist &&
+                  b->top_scores && b->cur_tok && b->src_row && b->alive && b->kcur && b->fin_tokens && b->fin_asrc && b->fin_len &&
+                  b->fin_score && b->fin_ppl && b->fin_count,
+              "sat_decode: NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == SAT_F32) return d->exact ? decode_impl<float, true>(*d, *w, *b, st) : decode_impl<float, false>(*d, *w, *b, st);
+  return d->exact ? decode_impl<bf16, true>(*d, *w, *b, st) : decode_impl<bf16, false>(*d, *w, *b, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// Integer / indexing kernels of greedy (beamk = 1) and beam decoding (model.py:237-472), batched over
+// images with all beam state resident on the device:
+//   row_topk_kernel     : log-softmax(logit / T) + masks + parent score, per-row top-k candidates
+//   beam_update_kernel  : per image k^2 -> k merge, <END> handling, rescoring, order-preserving
+//                         compaction of live beams, history append, flush at max length
+//   gather_state_kernel : h, c reorder by source row (model.py:397)
+#pragma once
+#include "sat_common.cuh"
+
+constexpr int SAT_ALIVE = 1 << 30;
+enum { SAT_RESCORE_NONE = 0, SAT_RESCORE_LN = 1, SAT_RESCORE_WR = 2, SAT_RESCORE_BAR = 3 };
+
+// Per-image InitLSTM reinterpretation for a beam of k identical rows (model.py:265-269):
+//   h0[j] = o[(j % 2) * H : ...],  c0[j] = o[((k + j) % 2) * H : ...]   where o = init_out[img] ([2H]).
+template <typename T>
+__global__ void init_state_decode_kernel(const float* __restrict__ init_out, T* __restrict__ h0, float* __restrict__ c0,
+                                         int n_img, int k, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_img * k * H) return;
+  const int jj = (int)(idx % H);
+  const int64_t row = idx / H;
+  const int j = (int)(row % k);
+  const int64_t n = row / k;
+  const float* o = init_out + n * 2 * H;
+  h0[idx] = from_f<T>(o[(j % 2) * H + jj]);
+  c0[idx] = o[((k + j) % 2) * H + jj];
+}
+
+// scores = log_softmax(logit / temp) (model.py:330); <START>,<PAD> -> -inf (model.py:333); step 0 also
+// <END>,<UNK> (model.py:340); + parent score (model.py:351).  Emits the row's best `kk` candidates in
+// descending order (ties: lower vocabulary index first).
+__global__ void __launch_bounds__(256)
+row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur,
+                int k, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
+                float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  extern __shared__ __align__(16) float smem[];
+  float* x = smem;            // [V]
+  float* scratch = x + V;     // [33]
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const int r = blockIdx.x, n = r / k, j = r - n * k, tid = threadIdx.x;
+  const int kc = kcur[n];
+  if (j >= kc) return;
+  if (step == 0 && j != 0) return;                    // step 0 looks at beam 0 only (model.py:343)
+  const float* row = logits + (int64_t)r * V;
+  float mx = -INFINITY;
+  for (int v = tid; v < V; v += 256) {
+    const float xv = row[v] / temp;
+    x[v] = xv;
+    mx = fmaxf(mx, xv);
+  }
+  mx = block_max(mx, scratch);
+  float se = 0.0f;
+  for (int v = tid; v < V; v += 256) se += expf(x[v] - mx);
+  se = block_sum(se, scratch);
+  const float lse = logf(se);
+  const float base = step == 0 ? 0.0f : top_scores[r];
+  for (int v = tid; v < V; v += 256) {
+    float lp = (x[v] - mx) - lse;
+    if (v == tokSTART || v == tokPAD || (step == 0 && (v == tokEND || v == tokUNK))) lp = -INFINITY;
+    x[v] = step == 0 ? lp : lp + base;
+  }
+  __syncthreads();
+  const int kk = step == 0 ? k : kc;
+  float pv = INFINITY;
+  int pi = -1;
+  for (int i = 0; i < kk; ++i) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = tid; v < V; v += 256) {
+      const float xv = x[v];
+      const bool after = (xv < pv) || (xv == pv && v > pi);      // strictly after the previous pick in (val desc, idx asc)
+      if (after && (xv > bv || (xv == bv && v < bi))) { bv = xv; bi = v; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    bv = s_val[0]; bi = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+    if (tid == 0) { cand_val[(int64_t)r * k + i] = bv; cand_idx[(int64_t)r * k + i] = bi; }
+    pv = bv; pi = bi;
+  }
+}
+
+struct BeamParams {
+  int k, V, S;                 // beam width, vocab, max_gen_length
+  int tokEND;
+  int rescore;                 // SAT_RESCORE_*
+  float reward;
+  int hist_ld;                 // S + 1 entries per slot
+};
+
+// One warp per image.  Lane 0 performs the (tiny) merge; all lanes copy histories.
+__global__ void __launch_bounds__(32)
+beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+                   int32_t* __restrict__ kcur, float* __restrict__ top_scores, int32_t* __restrict__ cur_tok,
+                   int32_t* __restrict__ src_row, int32_t* __restrict__ alive, const int32_t* __restrict__ tok_in,
+                   const int32_t* __restrict__ asrc_in, int32_t* __restrict__ tok_out, int32_t* __restrict__ asrc_out,
+                   int32_t* __restrict__ fin_tokens, int32_t* __restrict__ fin_asrc, int32_t* __restrict__ fin_len,
+                   float* __restrict__ fin_score, float* __restrict__ fin_ppl, int32_t* __restrict__ fin_count) {
+  constexpr int KMAX = 32;
+  __shared__ float nval[KMAX];
+  __shared__ int nword[KMAX], nsrc[KMAX], dst[KMAX];
+  __shared__ int s_kc_new, s_nnew;
+  __shared__ float s_mean_all, s_mean_live;
+  const int n = blockIdx.x, lane = threadIdx.x, k = p.k;
+  const int kc = kcur[n];
+  if (kc == 0) return;
+  const int64_t r0 = (int64_t)n * k;
+  if (lane == 0) {
+    int nnew;
+    if (step == 0) {
+      nnew = k;
+      for (int i = 0; i < k; ++i) { nval[i] = cand_val[r0 * k + i]; nword[i] = cand_idx[r0 * k + i]; nsrc[i] = i; }
+    } else {
+      nnew = kc;
+      int ptr[KMAX];
+      for (int j = 0; j < kc; ++j) ptr[j] = 0;
+      for (int i = 0; i < kc; ++i) {                   // top-kc of the flattened [kc*V] scores (model.py:359)
+        int bj = -1;
+        float bv = 0.f;
+        int bw = 0;
+        for (int j = 0; j < kc; ++j) {
+          if (ptr[j] >= kc) continue;
+          const float v = cand_val[(r0 + j) * k + ptr[j]];
+          const int w = cand_idx[(r0 + j) * k + ptr[j]];
+          if (bj < 0 || v > bv) { bj = j; bv = v; bw = w; }   // j ascending => lower flat index wins ties
+        }
+        nval[i] = bv; nword[i] = bw; nsrc[i] = bj;
+        ++ptr[bj];
+      }
+    }
+    int live = 0;
+    for (int i = 0; i < nnew; ++i) dst[i] = (nword[i] == p.tokEND) ? -1 : live++;
+    // BAR rescoring uses mean(top_scores) as the variable stands when rescore() is called (model.py:414):
+    // the whole new beam for hypotheses that just ended, the survivors only for the max-length flush.
+    float mean_all = 0.0f, mean_live = 0.0f;
+    for (int i = 0; i < nnew; ++i) {
+      mean_all += nval[i];
+      if (dst[i] >= 0) mean_live += nval[i];
+    }
+    s_mean_all = mean_all / (float)nnew;
+    s_mean_live = live > 0 ? mean_live / (float)live : 0.0f;
+    s_kc_new = live;
+    s_nnew = nnew;
+  }
+  __syncwarp();
+  const int nnew = s_nnew;
+  const bool flush = step >= p.S;                       // model.py:441
+  const float fstep = (float)step;
+  for (int i = 0; i < nnew; ++i) {
+    const int64_t rs = r0 + nsrc[i];
+    const bool done = dst[i] < 0;
+    if (done || flush) {
+      // finished hypothesis: words / alphas of steps 0..step-1 along the ancestry ([1:-1], model.py:421,442)
+      int slot = 0;
+      if (lane == 0) slot = fin_count[n];
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      // completed ones of this step are appended first (in beam order), flushed survivors after them
+      if (!done) {
+        int ndone = 0;
+        for (int q = 0; q < nnew; ++q) ndone += dst[q] < 0;
+        slot += ndone + dst[i];
+      } else {
+        int before = 0;
+        for (int q = 0; q < i; ++q) before += dst[q] < 0;
+        slot += before;
+      }
+      const int64_t fo = ((int64_t)n * k + slot) * p.hist_ld;
+      for (int s = lane; s < step; s += 32) {
+        fin_tokens[fo + s] = tok_in[rs * p.hist_ld + s];
+        fin_asrc[fo + s] = asrc_in[rs * p.hist_ld + s];
+      }
+      if (lane == 0) {
+        const float v = nval[i];
+        float sc = v;
+        if (p.rescore == SAT_RESCORE_LN) sc = v / fstep;
+        else if (p.rescore == SAT_RESCORE_WR) sc = v + p.reward * fstep;
+        else if (p.rescore == SAT_RESCORE_BAR) sc = v + p.reward * (-(done ? s_mean_all : s_mean_live));
+        fin_len[(int64_t)n * k + slot] = step;
+        fin_score[(int64_t)n * k + slot] = sc;
+        fin_ppl[(int64_t)n * k + slot] = expf(-v / fstep);
+      }
+    }
+    if (!done && !flush) {
+      const int64_t rd = r0 + dst[i];
+      for (int s = lane; s < step; s += 32) {
+        tok_out[rd * p.hist_ld + s] = tok_in[rs * p.hist_ld + s];
+        asrc_out[rd * p.hist_ld + s] = asrc_in[rs * p.hist_ld + s];
+      }
+      if (lane == 0) {
+        tok_out[rd * p.hist_ld + step] = nword[i];
+        asrc_out[rd * p.hist_ld + step] = (int)rs;
+        top_scores[rd] = nval[i];
+        cur_tok[rd] = nword[i];
+        src_row[rd] = (int)rs;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    fin_count[n] += flush ? nnew : (nnew - s_kc_new);
+    kcur[n] = flush ? 0 : s_kc_new;
+  }
+  const int kc_after = flush ? 0 : s_kc_new;
+  for (int j = lane; j < k; j += 32) alive[r0 + j] = j < kc_after ? SAT_ALIVE : 0;
+}
+
+// h, c <- hn, cn gathered by source row (model.py:397); dead rows are left alone.
+template <typename T>
+__global__ void gather_state_kernel(const T* __restrict__ hn, const float* __restrict__ cn, const int32_t* __restrict__ src_row,
+                                    const int32_t* __restrict__ alive, T* __restrict__ h, float* __restrict__ c, int R, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)R * H) return;
+  const int64_t r = idx / H;
+  if (alive[r] == 0) return;
+  const int j = (int)(idx - r * H);
+  const int64_t s = src_row[r];
+  h[idx] = hn[s * H + j];
+  c[idx] = cn[s * H + j];
+}
+
+static __global__ void decode_init_kernel(int32_t* cur_tok, int32_t* alive, float* top_scores, int32_t* kcur, int32_t* fin_count,
+                                          int32_t* fin_len, int R, int n_img, int k, int tokSTART) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) {
+    cur_tok[i] = tokSTART;
+    alive[i] = SAT_ALIVE;
+    top_scores[i] = 0.0f;
+    fin_len[i] = 0;
+  }
+  if (i < n_img) {
+    kcur[i] = k;
+    fin_count[i] = 0;
+  }
+}

@@ -195,6 +195,7 @@ struct EpiLstm {
   int64_t ldst_h, ldst_c;
   TS* gates; int64_t ldgates;          // post-activation gates for backward (row m -> gates + m*ldgates)
   const int32_t* lens; int t;
+  const int32_t* gx_row;               // optional: Gx row index per m (decode: token id into the [V,4H] table)
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
     const int j = n >> 2;
     const bool active = t < lens[m];
@@ -205,7 +206,7 @@ struct EpiLstm {
       if (gates) st4(gates + (int64_t)m * ldgates + n, make_float4(0.f, 0.f, 0.f, 0.f));
       return;
     }
-    const float4 gx = ld4(Gx + (int64_t)m * ldgx + n);
+    const float4 gx = ld4(Gx + (int64_t)(gx_row ? gx_row[m] : m) * ldgx + n);
     const float4 gh = ld4(Gh + (int64_t)m * ldgh + n);
     const float gi = sat_sigmoid<kExact>(acc[0] + gx.x + gh.x);
     const float gf = sat_sigmoid<kExact>(acc[1] + gx.y + gh.y);
@@ -223,8 +224,9 @@ struct EpiLstm {
 template <typename TS, bool kExact>
 struct EpiTanhAdd {
   const TS* Xe; TS* Xo; int64_t ld;
+  const int32_t* xe_row;               // optional: Xe row index per m (decode: token id into the embedding table)
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
-    const float4 x = ld4(Xe + (int64_t)m * ld + n);
+    const float4 x = ld4(Xe + (int64_t)(xe_row ? xe_row[m] : m) * ld + n);
     st4(Xo + (int64_t)m * ld + n,
         make_float4(sat_tanh<kExact>(acc[0] + x.x), sat_tanh<kExact>(acc[1] + x.y), sat_tanh<kExact>(acc[2] + x.z),
                     sat_tanh<kExact>(acc[3] + x.w)));

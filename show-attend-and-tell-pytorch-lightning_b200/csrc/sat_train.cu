@@ -79,14 +79,14 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
     // gates = gz * Wihz^T + Gx[t] + hp[:, A+D:]  -> LSTM cell -> h_{t+1}, c_{t+1}
     EpiLstm<TS, kExact> epi{b.Gx + (int64_t)t * B * 4 * H, 4 * H, b.hp + A + D, NH3, h_t, c_t,
                             (TS*)b.Hs + (int64_t)(t + 1) * B * H, b.Cs + (int64_t)(t + 1) * B * H, H, H,
-                            (TS*)b.Gates + (int64_t)t * B * 4 * H, 4 * H, b.lens, t};
+                            (TS*)b.Gates + (int64_t)t * B * 4 * H, 4 * H, b.lens, t, nullptr};
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(gz_t, D, D), (const TS*)w.Wihz, D, B, 4 * H, epi, st)));
   }
 
   // ---- hoisted: deep output (model.py:127) and vocabulary projection (model.py:130) over all T*B rows
   const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
-                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E}, st)));
+                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr}, st)));
   SAT_PROF(3, st);
   if (b.logits_f32) {
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,

@@ -1,0 +1,169 @@
+"""Host side of batched greedy / beam decoding (SAT.forward / SAT.caption, model.py:214-472).
+
+All images of the batch are decoded together by sat_decode (device-side beam bookkeeping, no host
+sync per step); this module allocates the buffers and turns the finished-hypothesis arrays into the
+reference's return format: four Python lists (captions, scores, alphas [len,h,w] CPU tensors,
+perplexities), or lists of lists sorted by score when return_all=True (model.py:453-467).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, decoder
+from .packing import PackedWeights
+
+RESCORE = {None: 0, "LN": 1, "WR": 2, "BAR": 3}
+
+
+class DecodeWeights:
+    """Packed inference weights + the per-vocabulary gate table GxV, cached per parameter version."""
+
+    def __init__(self, W, dtype, device, exact, use_tc):
+        self.pw = PackedWeights(W, dtype=dtype, device=device, backward=False)
+        dm = self.pw.dims
+        self.exact, self.use_tc = exact, use_tc
+        d = decoder.make_dims(1, 1, 1, dm["D"], dm["A"], dm["E"], dm["H"], dm["V"], 1, dtype, exact, use_tc)
+        self.GxV = torch.empty(dm["V"], 4 * dm["H"], dtype=torch.float32, device=device)
+        _lib.check(_lib.lib().sat_decode_prepare_weights(C.byref(d), self.pw.ref(), _lib.ptr(self.GxV), _lib.stream_ptr()),
+                   "sat_decode_prepare_weights")
+
+
+def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_method=None, rescore_reward=0.5,
+                       vocab=None):
+    """ann_bld [n_img,L,D] (dw.pw.dtype, cuda).  Returns dict of device tensors (fin_* + alpha_all) after
+    enqueueing the whole decode; nothing is synchronised here."""
+    L_ = _lib.lib()
+    dev = ann_bld.device
+    n_img, L, D = ann_bld.shape
+    dm = dw.pw.dims
+    A, E, H, V = dm["A"], dm["E"], dm["H"], dm["V"]
+    S = int(max_gen_length)
+    R = n_img * k
+    dtype = dw.pw.dtype
+    d = decoder.make_dims(R, n_img, L, D, A, E, H, V, S + 1, dtype, dw.exact, dw.use_tc)
+    f, s, i32 = torch.float32, dtype, torch.int32
+    mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+    t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * H), f),
+             h=mk((R, H), s), c=mk((R, H), f), hn=mk((R, H), s), cn=mk((R, H), f), hp=mk((R, A + D + 4 * H), f),
+             z=mk((R, D), s), gz=mk((R, D), s), xo=mk((R, E), s), logits=mk((R, V), f), alpha_all=mk((S + 1, R, L), f),
+             cand_val=mk((R, k), f), cand_idx=mk((R, k), i32), tok_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev),
+             asrc_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev), top_scores=mk((R,), f), cur_tok=mk((R,), i32),
+             src_row=torch.zeros((R,), dtype=i32, device=dev), alive=mk((R,), i32), kcur=mk((n_img,), i32),
+             fin_tokens=torch.zeros((n_img, k, S + 1), dtype=i32, device=dev),
+             fin_asrc=torch.zeros((n_img, k, S + 1), dtype=i32, device=dev), fin_len=mk((n_img, k), i32),
+             fin_score=torch.full((n_img, k), float("-inf"), dtype=f, device=dev), fin_ppl=mk((n_img, k), f),
+             fin_count=mk((n_img,), i32))
+    temps = temperature if isinstance(temperature, (list, tuple)) else [temperature]
+    temps_arr = (C.c_float * (S + 1))(*[float(temps[i % len(temps)]) for i in range(S + 1)])
+    b = _lib.SatDecodeBuffers()
+    b.ann = _lib.ptr(ann_bld)
+    b.GxV = _lib.ptr(dw.GxV)
+    for name, tensor in t.items():
+        setattr(b, name, _lib.ptr(tensor))
+    b.temps = C.cast(temps_arr, C.c_void_p)
+    b.k, b.max_gen_length, b.rescore, b.reward = k, S, RESCORE[rescore_method], float(rescore_reward)
+    b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK = vocab["PAD"], vocab["START"], vocab["END"], vocab["UNK"]
+    _lib.check(L_.sat_decode(C.byref(d), dw.pw.ref(), C.byref(b), _lib.stream_ptr()), "sat_decode")
+    t["ann"] = ann_bld
+    t["_dims"] = (n_img, k, S, L)
+    return t
+
+
+def assemble(t, hw, return_all=False, want_alphas=True):
+    """fin_* device arrays -> the reference's four lists."""
+    n_img, k, S, L = t["_dims"]
+    cnt = t["fin_count"].cpu().numpy()
+    ln = t["fin_len"].cpu().numpy()
+    sc32 = t["fin_score"].cpu()
+    sc = sc32.numpy().astype(np.float64)
+    ppl = t["fin_ppl"].cpu().numpy().astype(np.float64)
+    toks = t["fin_tokens"].cpu().numpy()
+    # which hypotheses are returned, in which order
+    sel = []                                   # per image: list of finished-slot indices
+    for n in range(n_img):
+        c = int(cnt[n])
+        if return_all:                          # sort [score, index] pairs descending (model.py:455-457)
+            order = sorted(range(c), key=lambda i: (sc[n, i], i), reverse=True)
+        else:                                   # first index of the maximum (model.py:463)
+            order = [int(np.argmax(sc[n, :c]))]
+        sel.append(order)
+    alphas_out = None
+    if want_alphas:
+        # gather alpha rows of the selected hypotheses on the device, one D2H copy
+        asrc = t["fin_asrc"].cpu().numpy()
+        steps, rows, offs = [], [], []
+        for n in range(n_img):
+            for i in sel[n]:
+                l = int(ln[n, i])
+                offs.append((len(steps), l))
+                steps.extend(range(l))
+                rows.extend(asrc[n, i, :l].tolist())
+        if steps:
+            dev = t["alpha_all"].device
+            st = torch.tensor(steps, dtype=torch.long, device=dev)
+            rw = torch.tensor(rows, dtype=torch.long, device=dev)
+            flat = t["alpha_all"][st, rw].cpu()
+        else:
+            flat = torch.zeros(0, L)
+        alphas_out, it = [], iter(offs)
+        for n in range(n_img):
+            per = []
+            for _ in sel[n]:
+                o, l = next(it)
+                per.append(flat[o:o + l].reshape(l, *hw).clone())
+            alphas_out.append(per)
+    caps, scores, ppls = [], [], []
+    for n in range(n_img):
+        caps.append([toks[n, i, :int(ln[n, i])].tolist() for i in sel[n]])
+        scores.append([float(sc[n, i]) for i in sel[n]])
+        ppls.append([float(ppl[n, i]) for i in sel[n]])
+    if not return_all:
+        caps = [c[0] for c in caps]
+        scores = [s[0] for s in scores]
+        ppls = [p[0] for p in ppls]
+        if alphas_out is not None:
+            alphas_out = [a[0] for a in alphas_out]
+    return caps, scores, alphas_out, ppls
+
+
+def inference_weights(model):
+    """cached DecodeWeights for a SAT module, rebuilt when any decoder parameter changed."""
+    from .packing import PARAM_NAMES
+    params = model.decoder_weights()
+    cfg = model._cfg()
+    key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params) + (cfg["dtype"],)
+    cache = getattr(model, "_packed_infer", None)
+    if cache is None or cache[0] != key:
+        W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
+        dev = next(p for p in params if p is not None).device
+        model._packed_infer = (key, DecodeWeights(W, cfg["dtype"], dev, cfg["exact"], cfg["use_tc"]))
+    return model._packed_infer[1]
+
+
+def caption_from_annotations(model, ann, beamk, max_gen_length, temperature, rescore_method, rescore_reward, return_all):
+    dw = inference_weights(model)
+    hw = tuple(ann.shape[2:])
+    bld = decoder.annotations_as_bld(ann, dw.pw.dtype)
+    vocab = dict(PAD=model.stoi("<PAD>"), START=model.stoi("<START>"), END=model.stoi("<END>"), UNK=model.stoi("<UNK>"))
+    t = decode_annotations(dw, bld, int(beamk), max_gen_length, temperature, rescore_method, rescore_reward, vocab)
+    return assemble(t, hw, return_all=return_all)
+
+
+def smoke():
+    """tiny greedy + beam decode on cuda:0 checked against the CPU oracle (called by __graft_entry__.smoke)."""
+    from oracle import sat_oracle as O
+    D, A, E, H, V = 64, 32, 32, 64, 128
+    W = O.random_weights(D, A, E, H, V, seed=5, sharpen=True)
+    W["output.output.bias"][V - 1] = 3.0
+    g = torch.Generator().manual_seed(6)
+    ann = torch.randn(4, D, 4, 4, generator=g)
+    vocab = dict(PAD=0, UNK=V - 3, START=V - 2, END=V - 1)
+    dw = DecodeWeights(W, torch.float32, torch.device("cuda"), True, False)
+    for k in (1, 3):
+        ref = O.caption(W, ann, vocab, beamk=k, max_gen_length=10, rescore_method="LN")
+        t = decode_annotations(dw, decoder.annotations_as_bld(ann.cuda(), torch.float32), k, 10, 1.0, "LN", 0.5, vocab)
+        caps, scores, _, _ = assemble(t, (4, 4))
+        assert caps == ref[0], (k, caps, ref[0])
+        assert max(abs(a - b) for a, b in zip(scores, ref[1])) < 1e-4
+    print("decode smoke ok: greedy and beam token ids match the CPU oracle")
