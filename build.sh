@@ -14,5 +14,5 @@ for f in "$SRC"/*.cu; do
     $NVCC $FLAGS -c "$f" -o "$o" 2> "$o.log" || { cat "$o.log"; exit 1; }
   fi
 done
-$NVCC -shared -o "$OUT" "$HERE"/build/*.o -lcuda
+$NVCC -shared -o "$OUT" "$HERE"/build/*.o
 echo "built $OUT"

@@ -1,0 +1,262 @@
+// tcgen05 (5th-gen tensor core) GEMM core for sm_100a:  C[M,N] = epi( sum_seg A_seg[M,K_seg] * W[N,K]^T ),
+// bf16 operands (both K-major), fp32 accumulation in tensor memory.
+//
+//   warp 0    : TMA producer  (cp.async.bulk.tensor.2d, 128B-swizzled tiles, 4-stage mbarrier ring)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
+//   warps 2-5 : epilogue: tcgen05.ld (32 lanes x 16 columns per instruction) -> fused epilogue functor
+//
+// The epilogue functors are the same ones the SIMT core runs (LSTM cell, tanh+add, CE, plain store ...), so
+// every fused stage of the decoder exists on both cores.  Tiles: BM = 128, BN in {64,128}, BK = 64.
+// M / N / K tails are handled by TMA out-of-bounds zero fill plus predicated epilogue stores.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "sat_gemm_simt.cuh"
+
+namespace tc {
+
+constexpr int BM = 128, BK = 64, STAGES = 4, THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 format: version 1 at bit 46,
+// stride-byte-offset = 8 rows * 128 B, layout type 2 = SWIZZLE_128B at bits 61..63).
+__device__ __forceinline__ uint64_t make_smem_desc(const void* p) {
+  const uint32_t a = smem_u32(p);
+  return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Maps {
+  CUtensorMap a[2];   // A segments: dims {K_s, M}, box {64, 128}
+  CUtensorMap w;      // W: dims {Ktot, N}, box {64, BN}
+};
+
+template <int BN>
+struct Smem {
+  alignas(1024) bf16 a[STAGES][BM * BK];
+  alignas(1024) bf16 w[STAGES][BN * BK];
+  alignas(8) uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(THREADS)
+gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k1, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb0 = (k0 + BK - 1) / BK, nkb1 = (k1 + BK - 1) / BK;
+  const int nkb = nkb0 + nkb1;
+  constexpr uint32_t STAGE_BYTES = (BM * BK + BN * BK) * sizeof(bf16);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&s.empty[st], ph ^ 1);
+        mbar_expect_tx(&s.full[st], STAGE_BYTES);
+        const bool seg1 = kb >= nkb0;
+        const int ka = (seg1 ? kb - nkb0 : kb) * BK;            // k offset inside the A segment
+        const int kw = seg1 ? k0 + ka : ka;                      // k offset inside W
+        tma_load_2d(seg1 ? &maps.a[1] : &maps.a[0], &s.full[st], s.a[st], ka, m0);
+        tma_load_2d(&maps.w, &s.full[st], s.w[st], kw, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&s.full[st], ph);
+        tcgen05_fence_after();
+        const uint64_t ad = make_smem_desc(s.a[st]), bd = make_smem_desc(s.w[st]);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) umma(tmem, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+        umma_commit(&s.empty[st]);            // frees the smem stage when these MMAs retire
+      }
+      umma_commit(&s.tmem_full);              // accumulator complete
+    }
+  } else {
+    mbar_wait(&s.tmem_full, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (m < M) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + c + g * 4;
+          if (n < N) {
+            const float a4[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
+            epi(m, n, a4);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// 2D bf16 tensor map: inner dim = K (contiguous), outer = rows; box {64, box_rows}; 128B swizzle; OOB -> 0
+static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+  auto enc = get_encode();
+  SAT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SAT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld k=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)k, (long long)ld);
+  return 0;
+}
+
+static inline bool operands_ok(const GemmOperandA& A, const void* W, int64_t ldw) {
+  if (A.nseg < 1 || A.nseg > 2) return false;
+  for (int i = 0; i < A.nseg; ++i) {
+    if (A.k[i] % 8 != 0 || A.ld[i] % 8 != 0 || (reinterpret_cast<uintptr_t>(A.p[i]) & 15)) return false;
+  }
+  // every segment but the last must fill whole 64-wide k blocks (W is addressed with a running k offset)
+  if (A.nseg == 2 && A.k[0] % BK != 0) return false;
+  return ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+}
+
+template <int BN, typename Epi>
+static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream) {
+  Maps maps;
+  int ktot = 0;
+  for (int i = 0; i < A.nseg; ++i) {
+    SAT_TRY(make_map(&maps.a[i], A.p[i], M, A.k[i], A.ld[i], BM));
+    ktot += A.k[i];
+  }
+  if (A.nseg == 1) maps.a[1] = maps.a[0];
+  SAT_TRY(make_map(&maps.w, W, N, ktot, ldw, BN));
+  auto kern = gemm_tn_tc_kernel<BN, Epi>;
+  constexpr int smem = (int)sizeof(Smem<BN>) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  kern<<<grid, THREADS, smem, stream>>>(maps, M, N, A.k[0], A.nseg == 2 ? A.k[1] : 0, epi);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
+
+template <typename Epi>
+static int launch(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream) {
+  const long tiles128 = (long)((N + 127) / 128) * ((M + BM - 1) / BM);
+  if (tiles128 >= 148 && N >= 128) return launch_bn<128, Epi>(A, W, ldw, M, N, epi, stream);
+  return launch_bn<64, Epi>(A, W, ldw, M, N, epi, stream);
+}
+
+}  // namespace tc
