@@ -12,10 +12,11 @@ pytestmark = pytest.mark.gpu
 VOC = lambda V: dict(PAD=0, UNK=V - 3, START=V - 2, END=V - 1)
 
 
-def cuda_caption(W, ann, k, max_len, temperature=1.0, rescore=None, reward=0.5, return_all=False, dtype=torch.float32):
+def cuda_caption(W, ann, k, max_len, temperature=1.0, rescore=None, reward=0.5, return_all=False, dtype=torch.float32,
+                 use_tc=False):
     from sat_b200 import decode, decoder
     V = W["embedding.weight"].shape[0]
-    dw = decode.DecodeWeights(W, dtype, torch.device("cuda"), dtype == torch.float32, False)
+    dw = decode.DecodeWeights(W, dtype, torch.device("cuda"), dtype == torch.float32, use_tc)
     bld = decoder.annotations_as_bld(ann.cuda(), dtype)
     t = decode.decode_annotations(dw, bld, k, max_len, temperature, rescore, reward, VOC(V))
     return decode.assemble(t, tuple(ann.shape[2:]), return_all=return_all)
@@ -70,12 +71,13 @@ def test_decode_c1_dims_vs_oracle(k):
     print("caption lengths", lens)
 
 
-def test_greedy_bf16_runs_and_mostly_agrees():
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_greedy_bf16_runs_and_mostly_agrees(use_tc):
     D, A, E, H, V = 512, 128, 256, 512, 6400
     W = O.random_weights(D, A, E, H, V, seed=11, sharpen=True)
     g = torch.Generator().manual_seed(12)
     ann = torch.randn(6, D, 14, 14, generator=g)
     ref = O.caption(W, ann, VOC(V), beamk=1, max_gen_length=30)
-    got = cuda_caption(W, ann, 1, 30, dtype=torch.bfloat16)
+    got = cuda_caption(W, ann, 1, 30, dtype=torch.bfloat16, use_tc=use_tc)
     agree = sum(1 for a, b in zip(got[0], ref[0]) if a[:3] == b[:3])
     assert agree >= 3          # bf16 token ids are not expected to be bit-exact

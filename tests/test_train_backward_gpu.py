@@ -59,11 +59,12 @@ def test_backward_fp32_vs_oracle(cfg):
     assert relerr(d_ann, da_ref) < 5e-5
 
 
-def test_backward_bf16_vs_oracle():
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_backward_bf16_vs_oracle(use_tc):
     cfg = dict(Bi=8, ncap=1, hw=(14, 14), D=512, A=128, E=256, H=512, V=6400, T=10, ragged=True)
     W, ann, caps, lens = synth(**cfg)
     loss_ref, Gref, da_ref = oracle_grads(W, ann, caps, lens, 0.0, 1.0)
-    loss, G, d_ann = run_cuda_fwd_bwd(W, ann, caps, lens, 0.0, 1.0, dtype=torch.bfloat16, exact=False)
+    loss, G, d_ann = run_cuda_fwd_bwd(W, ann, caps, lens, 0.0, 1.0, dtype=torch.bfloat16, exact=False, use_tc=use_tc)
     assert abs(loss - loss_ref) < 2e-2 * abs(loss_ref)
     for k, g in Gref.items():
         assert relerr(G[k], g) < 6e-2, k

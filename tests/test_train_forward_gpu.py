@@ -69,11 +69,12 @@ def test_forward_fp32_vs_oracle(cfg):
     assert abs(r["acc"] - float(ref["acc"])) < 1e-6
 
 
-def test_forward_bf16_vs_oracle():
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_forward_bf16_vs_oracle(use_tc):
     cfg = dict(Bi=8, ncap=1, hw=(14, 14), D=512, A=128, E=256, H=512, V=6400, T=20, ragged=True)
     W, ann, caps, lens = synth(**cfg)
     ref = O.train_loss(W, ann, caps, lens, label_smoothing=0.0, att_gamma=1.0)
-    r = run_cuda_forward(W, ann, caps, lens, 0.0, 1.0, dtype=torch.bfloat16, exact=False, logits_f32=False)
+    r = run_cuda_forward(W, ann, caps, lens, 0.0, 1.0, dtype=torch.bfloat16, exact=False, use_tc=use_tc, logits_f32=False)
     assert relerr(r["logits"], ref["logits"]) < 2e-2
     assert abs(r["loss"] - float(ref["loss"])) < 2e-2 * abs(float(ref["loss"]))
     assert relerr(r["alphas"], ref["alphas"]) < 2e-2

@@ -1,0 +1,52 @@
+"""Decoder-only workload at BASELINE configs[1] dims (B=256, L=196, D=512, A=128, E=256, H=512, V=6400, T=20, bf16)
+for ncu captures: N iterations of fused forward + loss + BPTT (+ parameter-gradient GEMMs) on synthetic annotations.
+    python tools/decoder_step.py [--iters 3] [--fp32] [--decode K]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--fp32", action="store_true")
+ap.add_argument("--no-tc", action="store_true")
+ap.add_argument("--decode", type=int, default=0, help="run batched decode with this beam width instead of training")
+args = ap.parse_args()
+
+from oracle import sat_oracle as O  # noqa: E402  (weights generator only)
+from sat_b200 import decode, decoder  # noqa: E402
+from sat_b200.packing import PackedWeights  # noqa: E402
+
+D, A, E, H, V, T, L = 512, 128, 256, 512, 6400, 20, 196
+dtype = torch.float32 if args.fp32 else torch.bfloat16
+W = O.random_weights(D, A, E, H, V, seed=0)
+g = torch.Generator(device="cuda").manual_seed(0)
+B = args.batch
+ann = torch.randn(B, L, D, device="cuda", generator=g).to(dtype)
+caps = torch.randint(1, V - 3, (B, T + 1), device="cuda", generator=g)
+caps[:, 0] = V - 2
+lens = torch.full((B,), T, device="cuda")
+use_tc = (not args.fp32) and (not args.no_tc)
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if args.decode:
+    dw = decode.DecodeWeights(W, dtype, torch.device("cuda"), args.fp32, use_tc)
+    vocab = dict(PAD=0, UNK=V - 3, START=V - 2, END=V - 1)
+    for it in range(args.iters):
+        ev0.record()
+        t = decode.decode_annotations(dw, ann, args.decode, 30, 1.0, None, 0.5, vocab)
+        ev1.record()
+        torch.cuda.synchronize()
+        print("decode k=%d B=%d: %.3f ms" % (args.decode, B, ev0.elapsed_time(ev1)))
+else:
+    pw = PackedWeights(W, dtype=dtype, device="cuda", backward=True)
+    for it in range(args.iters):
+        ev0.record()
+        buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True)
+        G, d_ann = decoder.train_backward(pw, buf)
+        ev1.record()
+        torch.cuda.synchronize()
+        print("train fwd+bwd B=%d: %.3f ms  loss %.4f" % (B, ev0.elapsed_time(ev1), float(buf.t["out"][0])))
