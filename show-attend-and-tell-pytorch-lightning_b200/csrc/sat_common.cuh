@@ -81,6 +81,10 @@ template <> struct Vec16<float> {
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
   }
+  __device__ __forceinline__ static void load_shared(const float* p, float* o) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
   __device__ __forceinline__ static void store(float* p, const float* o) {
     *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -89,6 +93,15 @@ template <> struct Vec16<bf16> {
   static constexpr int N = 8;
   __device__ __forceinline__ static void load(const bf16* p, float* o) {
     uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ static void load_shared(const bf16* p, float* o) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

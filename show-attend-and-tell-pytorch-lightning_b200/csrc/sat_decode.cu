@@ -5,6 +5,7 @@
 // with no host synchronisation (the reference loops over images one at a time and syncs several times a step).
 #include "sat_decode_kernels.cuh"
 #include "sat_gemm.cuh"
+#include "sat_attention_pipe.cuh"
 #include "sat_kernels.cuh"
 
 namespace {
@@ -35,7 +36,6 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   SAT_LAUNCH_OK();
 
   const float scale = (float)(1.0 / sqrt((double)L));
-  const size_t att_smem = attention_fwd_smem(L, D, A, Vec16<TS>::N);
   const size_t topk_smem = sizeof(float) * (size_t)(V + 40);
   if (topk_smem > 48 * 1024)
     SAT_CUDA(cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
@@ -46,12 +46,10 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.h, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
                              st)));
     SAT_PROF(1, st);
-    attention_step_fwd_kernel<TS, kExact><<<R, ATT_THREADS, att_smem, st>>>(
-        ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, k, L, D, A, scale, b.alpha_all + (int64_t)step * R * L, L, nullptr,
-        (TS*)b.z, (TS*)b.gz, (TS*)nullptr, D);
+    SAT_TRY((launch_attention_fwd<TS, kExact>(ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, R, k, L, D, A, scale,
+                                              b.alpha_all + (int64_t)step * R * L, L, nullptr, (TS*)b.z, (TS*)b.gz,
+                                              (TS*)nullptr, D, st)));
     SAT_PROF(1, st);
-    SAT_COUNT_LAUNCH();
-    SAT_LAUNCH_OK();
     EpiLstm<TS, kExact> epi{b.GxV, 4 * H, b.hp + A + D, NH3, (const TS*)b.h, b.c, (TS*)b.hn, b.cn, H, H,
                             (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.gz, D, D), (const TS*)w.Wihz, D, R, 4 * H, epi, st)));

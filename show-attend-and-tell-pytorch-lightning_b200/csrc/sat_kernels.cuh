@@ -54,19 +54,32 @@ attention_step_fwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
   }
   __syncthreads();
 
-  // ---- phase 1: scores (one warp per location, lanes over attention_dim) --------------------
+  // ---- phase 1: scores (one warp per location, lanes over attention_dim; 4 rows in flight per warp) ---
   const T* Pb = P + (int64_t)img * L * A;
-  for (int l = warp; l < L; l += ATT_THREADS / 32) {
-    float s = 0.0f;
+  constexpr int NWARP = ATT_THREADS / 32;
+  for (int l0 = warp; l0 < L; l0 += 4 * NWARP) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int a = lane * 4; a < A; a += 128) {
-      const float4 p = ld4(Pb + (int64_t)l * A + a);
-      s = fmaf(ws[a + 0], sat_tanh<kExact>(p.x + qs[a + 0]), s);
-      s = fmaf(ws[a + 1], sat_tanh<kExact>(p.y + qs[a + 1]), s);
-      s = fmaf(ws[a + 2], sat_tanh<kExact>(p.z + qs[a + 2]), s);
-      s = fmaf(ws[a + 3], sat_tanh<kExact>(p.w + qs[a + 3]), s);
+      float4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + u * NWARP;
+        p[u] = l < L ? ld4(Pb + (int64_t)l * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] = fmaf(ws[a + 0], sat_tanh<kExact>(p[u].x + qs[a + 0]), s[u]);
+        s[u] = fmaf(ws[a + 1], sat_tanh<kExact>(p[u].y + qs[a + 1]), s[u]);
+        s[u] = fmaf(ws[a + 2], sat_tanh<kExact>(p[u].z + qs[a + 2]), s[u]);
+        s[u] = fmaf(ws[a + 3], sat_tanh<kExact>(p[u].w + qs[a + 3]), s[u]);
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) e[l] = s * scale;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * NWARP;
+      const float r = warp_sum(s[u]);
+      if (lane == 0 && l < L) e[l] = r * scale;
+    }
   }
   __syncthreads();
 

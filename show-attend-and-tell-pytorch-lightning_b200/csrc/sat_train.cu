@@ -11,6 +11,7 @@
 //  * finished captions are predicated (t < lens[b]) instead of compacted, so there is no host
 //    sync, no gather/scatter of state and no per-step reallocation.
 #include "sat_gemm.cuh"
+#include "sat_attention_pipe.cuh"
 #include "sat_kernels.cuh"
 
 namespace {
@@ -59,7 +60,6 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
 
   // ---- recurrence ------------------------------------------------------------------------------
   const float scale = (float)(1.0 / sqrt((double)L));
-  const size_t att_smem = attention_fwd_smem(L, D, A, Vec16<TS>::N);
   for (int t = 0; t < T; ++t) {
     const TS* h_t = (const TS*)b.Hs + (int64_t)t * B * H;
     const float* c_t = b.Cs + (int64_t)t * B * H;
@@ -70,12 +70,10 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
     TS* gz_t = (TS*)b.GZ + (int64_t)t * B * D;
     TS* beta_t = (TS*)b.Beta + (int64_t)t * B * D;
     SAT_PROF(1, st);
-    attention_step_fwd_kernel<TS, kExact><<<B, ATT_THREADS, att_smem, st>>>(
-        ann, (const TS*)b.P, w.wf, b.hp, NH3, b.lens, t, d.ncap, L, D, A, scale, b.alphas + (int64_t)t * L,
-        (int64_t)T * L, b.Q + (int64_t)t * B * A, z_t, gz_t, beta_t, D);
+    SAT_TRY((launch_attention_fwd<TS, kExact>(ann, (const TS*)b.P, w.wf, b.hp, NH3, b.lens, t, B, d.ncap, L, D, A, scale,
+                                              b.alphas + (int64_t)t * L, (int64_t)T * L, b.Q + (int64_t)t * B * A, z_t, gz_t,
+                                              beta_t, D, st)));
     SAT_PROF(1, st);
-    SAT_COUNT_LAUNCH();
-    SAT_LAUNCH_OK();
     // gates = gz * Wihz^T + Gx[t] + hp[:, A+D:]  -> LSTM cell -> h_{t+1}, c_{t+1}
     EpiLstm<TS, kExact> epi{b.Gx + (int64_t)t * B * 4 * H, 4 * H, b.hp + A + D, NH3, h_t, c_t,
                             (TS*)b.Hs + (int64_t)(t + 1) * B * H, b.Cs + (int64_t)(t + 1) * B * H, H, H,
@@ -176,20 +174,14 @@ int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, con
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = (float)(1.0 / sqrt((double)d->L));
 #define SAT_LAUNCH_ATT(TS, EX)                                                                                          \
-  do {                                                                                                                  \
-    const size_t smem = attention_fwd_smem(d->L, d->D, d->A, Vec16<TS>::N);                                             \
-    attention_step_fwd_kernel<TS, EX><<<d->B, ATT_THREADS, smem, st>>>((const TS*)ann, (const TS*)P, wf, hp, ldhp, lens, t, \
-                                                                       d->ncap, d->L, d->D, d->A, scale, alpha, ld_alpha, \
-                                                                       nullptr, (TS*)z, (TS*)gz, (TS*)beta, ld_z);       \
-  } while (0)
+  SAT_TRY((launch_attention_fwd<TS, EX>((const TS*)ann, (const TS*)P, wf, hp, ldhp, lens, t, d->B, d->ncap, d->L, d->D, d->A, \
+                                        scale, alpha, ld_alpha, nullptr, (TS*)z, (TS*)gz, (TS*)beta, ld_z, st)))
   if (d->dtype == SAT_F32) {
     if (d->exact) SAT_LAUNCH_ATT(float, true); else SAT_LAUNCH_ATT(float, false);
   } else {
     if (d->exact) SAT_LAUNCH_ATT(bf16, true); else SAT_LAUNCH_ATT(bf16, false);
   }
 #undef SAT_LAUNCH_ATT
-  SAT_COUNT_LAUNCH();
-  SAT_LAUNCH_OK();
   return 0;
 }
 
