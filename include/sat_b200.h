@@ -114,8 +114,8 @@ typedef struct SatTrainBuffers {
   void* dpre;            /* [T,B,E] s    grad wrt deep-output pre-activation                       */
   float* dHZ;            /* [T,B,H+D]    dpre * [W_ho|W_zo]                                        */
   void* DY;              /* [T,B,A+D+4H] s: dq | dbeta_pre | dG (gate-interleaved)                 */
-  float* dgz;            /* [B,D]        per-step scratch                                          */
-  float* dh;             /* [B,H]        running grad wrt h                                        */
+  float* dgz;            /* [16,B,D]     per-step scratch: split-K partials of dG * Wihz                   */
+  float* dh;             /* [16,B,H]     running grad wrt h: split-K partials of the h-chain GEMM          */
   float* dc;             /* [B,H]        running grad wrt c                                        */
   void* dZ;              /* [T,B,D] s    total grad wrt z_t (for d_ann)                            */
   float* dP;             /* [B,L,A]      accumulated grad wrt P                                    */

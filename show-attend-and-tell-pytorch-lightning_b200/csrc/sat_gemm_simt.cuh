@@ -141,6 +141,7 @@ struct EpiStore {
   const float* bias;        // [N] or nullptr
   const TR* res;            // residual [M, ldr] or nullptr
   int64_t ldr;
+  int64_t zstride;          // split-K: CTA z writes its partial at C + z*zstride (0 when unused)
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
     float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
     if (bias) { v.x += bias[n]; v.y += bias[n + 1]; v.z += bias[n + 2]; v.w += bias[n + 3]; }
@@ -148,7 +149,7 @@ struct EpiStore {
       const float4 r = ld4(res + (int64_t)m * ldr + n);
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
-    st4(C + (int64_t)m * ldc + n, v);
+    st4(C + (int64_t)blockIdx.z * zstride + (int64_t)m * ldc + n, v);
   }
 };
 

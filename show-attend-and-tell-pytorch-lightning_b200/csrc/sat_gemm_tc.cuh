@@ -104,12 +104,16 @@ struct Smem {
 template <int BN, typename Epi>
 __global__ void __launch_bounds__(THREADS)
 gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k1, Epi epi) {
+  // gridDim.z = split-K factor: CTA z accumulates k blocks [z*nkb/S, (z+1)*nkb/S) (partials are summed by the consumer)
   extern __shared__ uint8_t smem_raw[];
   Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb0 = (k0 + BK - 1) / BK, nkb1 = (k1 + BK - 1) / BK;
-  const int nkb = nkb0 + nkb1;
+  const int nkb_all = nkb0 + nkb1;
+  const int kb_begin = (int)(((long)nkb_all * blockIdx.z) / gridDim.z);
+  const int kb_end = (int)(((long)nkb_all * (blockIdx.z + 1)) / gridDim.z);
+  const int nkb = kb_end - kb_begin;
   constexpr uint32_t STAGE_BYTES = (BM * BK + BN * BK) * sizeof(bf16);
 
   if (threadIdx.x == 0) {
@@ -134,9 +138,10 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb_begin + i;
+        const int st = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&s.empty[st], ph ^ 1);
         mbar_expect_tx(&s.full[st], STAGE_BYTES);
         const bool seg1 = kb >= nkb0;
@@ -149,7 +154,7 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {      // local k-block index (split-K: this CTA's share)
         const int st = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&s.full[st], ph);
@@ -162,23 +167,42 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
       umma_commit(&s.tmem_full);              // accumulator complete
     }
   } else {
+    // ===== epilogue: TMEM -> registers -> shared (transpose) -> coalesced fused epilogue =====
+    // A thread owns one accumulator ROW after tcgen05.ld; global accesses of the epilogue functors want a warp
+    // on consecutive COLUMNS of one row.  The operand ring is idle once tmem_full fires, so it is reused as a
+    // [128][BN+4] fp32 staging tile (conflict-free: row stride = 4 mod 32 banks).
     mbar_wait(&s.tmem_full, 0);
     tcgen05_fence_after();
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
+    constexpr int LDT = BN + 4;
+    float* tile = reinterpret_cast<float*>(&s.a[0][0]);
+    static_assert((size_t)BM * LDT * sizeof(float) <= sizeof(s.a) + sizeof(s.w), "staging tile must fit the ring");
+    const int row = q * 32 + lane;
+    if (nkb > 0) {
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (m < M) {
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c + g * 4;
-          if (n < N) {
-            const float a4[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
-            epi(m, n, a4);
-          }
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<float4*>(&tile[row * LDT + c + g * 4]) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+    } else {
+      for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4*>(&tile[row * LDT + c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    constexpr int LPR = BN / 4;                // lanes per row
+    constexpr int RPW = 32 / LPR;              // rows per warp pass
+    const int ew = warp - 2;                   // 0..3
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    const int n = n0 + lc;
+#pragma unroll 1
+    for (int r = ew * RPW + lr; r < BM; r += 4 * RPW) {
+      const int m = m0 + r;
+      if (m < M && n < N) {
+        const float4 a = *reinterpret_cast<const float4*>(&tile[r * LDT + lc]);
+        const float a4[4] = {a.x, a.y, a.z, a.w};
+        epi(m, n, a4);
       }
     }
   }
@@ -229,7 +253,8 @@ static inline bool operands_ok(const GemmOperandA& A, const void* W, int64_t ldw
 }
 
 template <int BN, typename Epi>
-static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream) {
+static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream,
+                     int splitk = 1) {
   Maps maps;
   int ktot = 0;
   for (int i = 0; i < A.nseg; ++i) {
@@ -245,7 +270,7 @@ static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, i
     SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
   kern<<<grid, THREADS, smem, stream>>>(maps, M, N, A.k[0], A.nseg == 2 ? A.k[1] : 0, epi);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
@@ -253,10 +278,20 @@ static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, i
 }
 
 template <typename Epi>
-static int launch(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream) {
+static int launch(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream,
+                  int splitk = 1) {
   const long tiles128 = (long)((N + 127) / 128) * ((M + BM - 1) / BM);
-  if (tiles128 >= 148 && N >= 128) return launch_bn<128, Epi>(A, W, ldw, M, N, epi, stream);
-  return launch_bn<64, Epi>(A, W, ldw, M, N, epi, stream);
+  if (tiles128 >= 148 && N >= 128 && splitk == 1) return launch_bn<128, Epi>(A, W, ldw, M, N, epi, stream);
+  return launch_bn<64, Epi>(A, W, ldw, M, N, epi, stream, splitk);
+}
+
+// split-K factor for skinny GEMMs (few output tiles, long K): enough CTAs to cover the SMs, >= 4 k blocks each
+static inline int pick_splitk(int M, int N, int ktot) {
+  const long tiles = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
+  const int nkb = (ktot + BK - 1) / BK;
+  int s = 1;
+  while (s < 16 && tiles * (s * 2) <= 160 && nkb / (s * 2) >= 4) s *= 2;
+  return s;
 }
 
 }  // namespace tc

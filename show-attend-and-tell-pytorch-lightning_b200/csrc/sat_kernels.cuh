@@ -228,8 +228,9 @@ __global__ void init_state_kernel(const float* __restrict__ init_out, T* __restr
 }
 
 // inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i
-static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ dc0,
-                                      float* __restrict__ d_init_out, int B, int H, int ncap) {
+static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int ns_dh, int64_t dh_stride,
+                                             const float* __restrict__ dc0, float* __restrict__ d_init_out, int B, int H,
+                                             int ncap) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, 2H]
   const int Bi = B / ncap;
   if (idx >= (int64_t)Bi * 2 * H) return;
@@ -240,7 +241,11 @@ static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, cons
   for (int c = 0; c < ncap; ++c) {
     const int64_t r = i * ncap + c;
     const int64_t f = r * 2 * H + col;
-    s += f < BH ? dh0[f] : dc0[f - BH];
+    if (f < BH) {
+      for (int sp = 0; sp < ns_dh; ++sp) s += dh0[(int64_t)sp * dh_stride + f];
+    } else {
+      s += dc0[f - BH];
+    }
   }
   d_init_out[idx] = s;
 }
@@ -397,8 +402,8 @@ loss_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restri
 // =============================================================================================
 template <typename TS, bool kExact>
 __global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* __restrict__ c_prev,
-                                     const float* __restrict__ c_next, const float* __restrict__ dh,
-                                     const float* __restrict__ dHo, int64_t ld_dho, float* __restrict__ dc,
+                                     const float* __restrict__ c_next, const float* __restrict__ dh, int ns_dh,
+                                     int64_t dh_stride, const float* __restrict__ dHo, int64_t ld_dho, float* __restrict__ dc,
                                      TS* __restrict__ dG, int64_t ld_dg, const int32_t* __restrict__ lens, int t, int B,
                                      int H) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,7 +418,9 @@ __global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* 
   const float gi = g4.x, gf = g4.y, gg = g4.z, go = g4.w;
   const float cp = c_prev[idx], cn = c_next[idx];
   const float tc = sat_tanh<kExact>(cn);
-  const float dht = dh[idx] + dHo[(int64_t)b * ld_dho + j];
+  float dhs = 0.0f;
+  for (int sp = 0; sp < ns_dh; ++sp) dhs += dh[(int64_t)sp * dh_stride + idx];     // split-K partials of the h-chain GEMM
+  const float dht = dhs + dHo[(int64_t)b * ld_dho + j];
   const float dct = dc[idx] + dht * go * (1.0f - tc * tc);
   st4(dg, make_float4(dct * gg * gi * (1.0f - gi), dct * cp * gf * (1.0f - gf), dct * gi * (1.0f - gg * gg),
                       dht * tc * go * (1.0f - go)));
@@ -436,7 +443,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, const float* __restrict__ wf,
                           const float* __restrict__ q_t, const float* __restrict__ alpha, int64_t ld_alpha,
                           const float* __restrict__ S, const T* __restrict__ z_t, const T* __restrict__ beta_t,
-                          const float* __restrict__ dgz, const float* __restrict__ dZout, int64_t ld_dzout,
+                          const float* __restrict__ dgz, int ns_dgz, int64_t dgz_stride,
+                          const float* __restrict__ dZout, int64_t ld_dzout,
                           const int32_t* __restrict__ lens, int t, int ncap, int B, int L, int D, int A, float scale,
                           float gamma, const float* __restrict__ gscale, const float* __restrict__ dalpha_ext,
                           float* __restrict__ dP, T* __restrict__ dZ_t,
@@ -463,7 +471,8 @@ attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
   const float g = gscale ? *gscale : 1.0f;
   // phase A
   for (int d = tid; d < D; d += ATT_THREADS) {
-    const float dg = dgz[(int64_t)b * D + d];
+    float dg = 0.0f;
+    for (int sp = 0; sp < ns_dgz; ++sp) dg += dgz[(int64_t)sp * dgz_stride + (int64_t)b * D + d];
     const float bt = to_f(beta_t[(int64_t)b * D + d]);
     const float zz = to_f(z_t[(int64_t)b * D + d]);
     const float dzv = dZout[(int64_t)b * ld_dzout + d] + dg * bt;

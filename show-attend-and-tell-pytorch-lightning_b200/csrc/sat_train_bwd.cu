@@ -26,7 +26,13 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dpre, E, E), (const TS*)w.WhozoT, E, M, H + D,
                            EpiStore<float>{b.dHZ, H + D, nullptr, nullptr, 0}, st)));
 
-  SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)B * H, st));
+  // split-K factors of the two skinny per-step GEMMs (tensor-core core only; partials are summed by their consumers)
+  const int NH3_ = A + D + 4 * H;
+  const bool tc_dgz = gemm_tn_uses_tc<TS, TS>(tc, gemm_a1((const TS*)b.DY + A + D, NH3_, 4 * H), (const TS*)w.WihzT, 4 * H, B, D);
+  const bool tc_dh = gemm_tn_uses_tc<TS, TS>(tc, gemm_a1(b.DY, NH3_, NH3_), (const TS*)w.WhcatT, NH3_, B, H);
+  const int sk_dgz = tc_dgz ? tc::pick_splitk(B, D, 4 * H) : 1;
+  const int sk_dh = tc_dh ? tc::pick_splitk(B, H, NH3_) : 1;
+  SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)sk_dh * B * H, st));
   SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)B * H, st));
   SAT_CUDA(cudaMemsetAsync(b.dP, 0, sizeof(float) * (size_t)B * L * A, st));
 
@@ -39,17 +45,18 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     TS* DY_t = (TS*)b.DY + (int64_t)t * B * NH3;
     const float* dHZ_t = b.dHZ + (int64_t)t * B * (H + D);
     lstm_bwd_step_kernel<TS, kExact><<<(B * H + 255) / 256, 256, 0, st>>>(
-        (const TS*)b.Gates + (int64_t)t * B * 4 * H, b.Cs + (int64_t)t * B * H, b.Cs + (int64_t)(t + 1) * B * H, b.dh, dHZ_t,
-        H + D, b.dc, DY_t + A + D, NH3, b.lens, t, B, H);
+        (const TS*)b.Gates + (int64_t)t * B * 4 * H, b.Cs + (int64_t)t * B * H, b.Cs + (int64_t)(t + 1) * B * H, b.dh, sk_dh,
+        (int64_t)B * H, dHZ_t, H + D, b.dc, DY_t + A + D, NH3, b.lens, t, B, H);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     // dgz = dG * Wihz     (A operand: DY_t[:, A+D:], K = 4H)
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + A + D, NH3, 4 * H), (const TS*)w.WihzT, 4 * H, B, D,
-                             EpiStore<float>{b.dgz, D, nullptr, nullptr, 0}, st)));
+                             EpiStore<float>{b.dgz, D, nullptr, nullptr, 0, (int64_t)B * D}, st, sk_dgz)));
     SAT_PROF(2, st);
     att_k<<<B, ATT_THREADS, att_smem, st>>>(ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
                                             (int64_t)T * L, b.S, (const TS*)b.Z + (int64_t)t * B * D,
-                                            (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, dHZ_t + H, H + D, b.lens, t, d.ncap,
+                                            (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, sk_dgz, (int64_t)B * D, dHZ_t + H, H + D, b.lens,
+                                            t, d.ncap,
                                             B, L, D, A, scale, b.att_gamma, b.gscale,
                                             b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, (TS*)b.dZ + (int64_t)t * B * D,
                                             DY_t, NH3, b.dwf_part + (int64_t)t * B * A);
@@ -57,7 +64,9 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     // dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (rows inactive at t keep their dh)
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t, NH3, NH3), (const TS*)w.WhcatT, NH3, B, H, EpiDh{b.dh, H, b.lens, t}, st)));
+    // (rows not active at t have an all-zero DY row, and their dh is still zero in backward order, so a plain store is exact)
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t, NH3, NH3), (const TS*)w.WhcatT, NH3, B, H,
+                             EpiStore<float>{b.dh, H, nullptr, nullptr, 0, (int64_t)B * H}, st, sk_dh)));
   }
 
   // dXe = dG * Wihe + dpre                               [M,E]
@@ -65,7 +74,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
                            EpiStore<float, TS>{b.dXe, E, nullptr, (const TS*)b.dpre, E}, st)));
 
   // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
-  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, b.dc, b.d_init_out, B, H, d.ncap);
+  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, b.d_init_out, B, H, d.ncap);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.d_init_out, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,

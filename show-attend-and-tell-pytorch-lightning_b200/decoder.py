@@ -58,8 +58,8 @@ class TrainBuffers:
             t["dpre"] = mk((T, B, E), s)
             t["dHZ"] = mk((T, B, H + D), f)
             t["DY"] = mk((T, B, NH3), s)
-            t["dgz"] = mk((B, D), f)
-            t["dh"] = mk((B, H), f)
+            t["dgz"] = mk((16, B, D), f)        # split-K partials (SAT_MAX_SPLITK)
+            t["dh"] = mk((16, B, H), f)
             t["dc"] = mk((B, H), f)
             t["dZ"] = mk((T, B, D), s)
             t["dP"] = mk((B, L, A), f)
