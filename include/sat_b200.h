@@ -119,6 +119,10 @@ typedef struct SatTrainBuffers {
   float* dc;             /* [B,H]        running grad wrt c                                        */
   void* dZ;              /* [T,B,D] s    total grad wrt z_t (for d_ann)                            */
   float* dP;             /* [B,L,A]      accumulated grad wrt P                                    */
+  void* dP16;            /* [B,L,A] s    copy of dP in the operand dtype, written at the last backward step (t = 0);
+                                         feeds the tensor-core d_ann GEMM (may be NULL in fp32 mode)          */
+  float* dann_tmp;       /* [B,L,D]      fp32 scratch of the tensor-core d_ann path (alpha (x) dz + mean term); may be
+                                         NULL in fp32 mode                                                    */
   float* dwf_part;       /* [T,B,A]      per-(b,t) partial of d f_att.weight                       */
   float* dXe;            /* [T,B,E]      grad wrt embedded words                                   */
   float* d_init_out;     /* [Bi,2H]                                                               */

@@ -28,7 +28,7 @@ class SatTrainBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "caps", "lens", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
                  "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
-                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dwf_part", "dXe", "d_init_out",
+                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dann_tmp", "dwf_part", "dXe", "d_init_out",
                  "df1", "dmean", "d_ann")] + \
                [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("logits_f32", C.c_int32),
                 ("reserved", C.c_int32)]

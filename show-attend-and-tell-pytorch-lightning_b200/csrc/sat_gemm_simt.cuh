@@ -133,6 +133,12 @@ static int launch_gemm_tn_simt(const GemmOperandA& A, const TW* W, int64_t ldw, 
 
 // ---- epilogues -----------------------------------------------------------------------------
 
+// Epilogue concept (two-phase so that the tensor-core core can issue the global loads of several rows before
+// any dependent math -- the epilogue is latency-bound otherwise):
+//   Ctx  load(int m, int n) const                      -- global reads for (row m, columns n..n+3)
+//   void apply(int m, int n, const float (&acc)[4], const Ctx&) const
+//   void operator()(m, n, acc)                         -- load + apply (SIMT core)
+
 // C = acc + bias (+ residual of type TR)
 template <typename TO, typename TR = float>
 struct EpiStore {
@@ -142,23 +148,18 @@ struct EpiStore {
   const TR* res;            // residual [M, ldr] or nullptr
   int64_t ldr;
   int64_t zstride;          // split-K: CTA z writes its partial at C + z*zstride (0 when unused)
-  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
-    float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    if (bias) { v.x += bias[n]; v.y += bias[n + 1]; v.z += bias[n + 2]; v.w += bias[n + 3]; }
-    if (res) {
-      const float4 r = ld4(res + (int64_t)m * ldr + n);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-    }
-    st4(C + (int64_t)blockIdx.z * zstride + (int64_t)m * ldc + n, v);
+  struct Ctx { float4 b, r; };
+  __device__ __forceinline__ Ctx load(int m, int n) const {
+    Ctx c;
+    c.b = bias ? ld4(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    c.r = res ? ld4(res + (int64_t)m * ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return c;
   }
-};
-
-// h-chain of the backward pass: dh[b,:] = acc for rows active at step t, unchanged otherwise
-struct EpiDh {
-  float* dh; int64_t ld; const int32_t* lens; int t;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
-    if (t < lens[m]) st4(dh + (int64_t)m * ld + n, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
+    st4(C + (int64_t)blockIdx.z * zstride + (int64_t)m * ldc + n,
+        make_float4(acc[0] + c.b.x + c.r.x, acc[1] + c.b.y + c.r.y, acc[2] + c.b.z + c.r.z, acc[3] + c.b.w + c.r.w));
   }
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
 };
 
 // d_ann[b,l,:] = acc (= dP[b,l,:] * Wa) + sum_t alpha[b,t,l] * dZ[t,b,:] + dmean[img,:] * mean_scale
@@ -167,9 +168,16 @@ template <typename TS>
 struct EpiDAnn {
   TS* d_ann; const float* alphas; const TS* dZ; const float* dmean;
   int B, T, L, D, ncap; float mean_scale;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+  struct Ctx { float4 dm; };
+  __device__ __forceinline__ Ctx load(int m, int n) const {
+    Ctx c;
+    c.dm = ld4(dmean + (int64_t)((m / L) / ncap) * D + n);
+    return c;
+  }
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
+  __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
     const int b = m / L, l = m - b * L;
-    const float4 dm = ld4(dmean + (int64_t)(b / ncap) * D + n);
+    const float4 dm = c.dm;
     float4 v = make_float4(acc[0] + dm.x * mean_scale, acc[1] + dm.y * mean_scale, acc[2] + dm.z * mean_scale,
                            acc[3] + dm.w * mean_scale);
     const float* al = alphas + ((int64_t)b * T) * L + l;
@@ -197,18 +205,30 @@ struct EpiLstm {
   TS* gates; int64_t ldgates;          // post-activation gates for backward (row m -> gates + m*ldgates)
   const int32_t* lens; int t;
   const int32_t* gx_row;               // optional: Gx row index per m (decode: token id into the [V,4H] table)
-  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
+  struct Ctx { float4 gx, gh; float cp; bool active; };
+  __device__ __forceinline__ Ctx load(int m, int n) const {
+    Ctx c;
+    c.active = t < lens[m];
+    c.cp = c_prev[(int64_t)m * ldst_c + (n >> 2)];
+    if (c.active) {
+      c.gx = ld4(Gx + (int64_t)(gx_row ? gx_row[m] : m) * ldgx + n);
+      c.gh = ld4(Gh + (int64_t)m * ldgh + n);
+    } else {
+      c.gx = c.gh = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return c;
+  }
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
+  __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
     const int j = n >> 2;
-    const bool active = t < lens[m];
-    const float cp = c_prev[(int64_t)m * ldst_c + j];
-    if (!active) {
+    const float cp = c.cp;
+    if (!c.active) {
       h_next[(int64_t)m * ldst_h + j] = h_prev[(int64_t)m * ldst_h + j];
       c_next[(int64_t)m * ldst_c + j] = cp;
       if (gates) st4(gates + (int64_t)m * ldgates + n, make_float4(0.f, 0.f, 0.f, 0.f));
       return;
     }
-    const float4 gx = ld4(Gx + (int64_t)(gx_row ? gx_row[m] : m) * ldgx + n);
-    const float4 gh = ld4(Gh + (int64_t)m * ldgh + n);
+    const float4 gx = c.gx, gh = c.gh;
     const float gi = sat_sigmoid<kExact>(acc[0] + gx.x + gh.x);
     const float gf = sat_sigmoid<kExact>(acc[1] + gx.y + gh.y);
     const float gg = sat_tanh<kExact>(acc[2] + gx.z + gh.z);
@@ -226,8 +246,15 @@ template <typename TS, bool kExact>
 struct EpiTanhAdd {
   const TS* Xe; TS* Xo; int64_t ld;
   const int32_t* xe_row;               // optional: Xe row index per m (decode: token id into the embedding table)
-  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
-    const float4 x = ld4(Xe + (int64_t)(xe_row ? xe_row[m] : m) * ld + n);
+  struct Ctx { float4 x; };
+  __device__ __forceinline__ Ctx load(int m, int n) const {
+    Ctx c;
+    c.x = ld4(Xe + (int64_t)(xe_row ? xe_row[m] : m) * ld + n);
+    return c;
+  }
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
+  __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
+    const float4 x = c.x;
     st4(Xo + (int64_t)m * ld + n,
         make_float4(sat_tanh<kExact>(acc[0] + x.x), sat_tanh<kExact>(acc[1] + x.y), sat_tanh<kExact>(acc[2] + x.z),
                     sat_tanh<kExact>(acc[3] + x.w)));
@@ -238,9 +265,17 @@ struct EpiTanhAdd {
 template <typename TS>
 struct EpiDpre {
   const TS* Xo; TS* dpre; int64_t ld; const float* gscale;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const {
-    const float g = gscale ? *gscale : 1.0f;
-    const float4 x = ld4(Xo + (int64_t)m * ld + n);
+  struct Ctx { float4 x; float g; };
+  __device__ __forceinline__ Ctx load(int m, int n) const {
+    Ctx c;
+    c.g = gscale ? *gscale : 1.0f;
+    c.x = ld4(Xo + (int64_t)m * ld + n);
+    return c;
+  }
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
+  __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
+    const float g = c.g;
+    const float4 x = c.x;
     st4(dpre + (int64_t)m * ld + n, make_float4(g * acc[0] * (1.f - x.x * x.x), g * acc[1] * (1.f - x.y * x.y),
                                                  g * acc[2] * (1.f - x.z * x.z), g * acc[3] * (1.f - x.w * x.w)));
   }

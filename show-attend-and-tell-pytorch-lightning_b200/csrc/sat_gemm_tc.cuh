@@ -196,13 +196,27 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
     const int ew = warp - 2;                   // 0..3
     const int lr = lane / LPR, lc = (lane % LPR) * 4;
     const int n = n0 + lc;
+    constexpr int NIT = BM / (4 * RPW);       // rows per thread
+    constexpr int UN = 4;                      // rows whose epilogue operands are loaded before any dependent math
+    static_assert(NIT % UN == 0, "row loop must divide");
 #pragma unroll 1
-    for (int r = ew * RPW + lr; r < BM; r += 4 * RPW) {
-      const int m = m0 + r;
-      if (m < M && n < N) {
-        const float4 a = *reinterpret_cast<const float4*>(&tile[r * LDT + lc]);
-        const float a4[4] = {a.x, a.y, a.z, a.w};
-        epi(m, n, a4);
+    for (int i0 = 0; i0 < NIT; i0 += UN) {
+      typename Epi::Ctx ctx[UN];
+      bool ok[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int m = m0 + ew * RPW + lr + (i0 + u) * 4 * RPW;
+        ok[u] = m < M && n < N;
+        if (ok[u]) ctx[u] = epi.load(m, n);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int r = ew * RPW + lr + (i0 + u) * 4 * RPW;
+        if (ok[u]) {
+          const float4 a = *reinterpret_cast<const float4*>(&tile[r * LDT + lc]);
+          const float a4[4] = {a.x, a.y, a.z, a.w};
+          epi.apply(m0 + r, n, a4, ctx[u]);
+        }
       }
     }
   }

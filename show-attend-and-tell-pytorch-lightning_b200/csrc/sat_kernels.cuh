@@ -447,7 +447,7 @@ attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
                           const float* __restrict__ dZout, int64_t ld_dzout,
                           const int32_t* __restrict__ lens, int t, int ncap, int B, int L, int D, int A, float scale,
                           float gamma, const float* __restrict__ gscale, const float* __restrict__ dalpha_ext,
-                          float* __restrict__ dP, T* __restrict__ dZ_t,
+                          float* __restrict__ dP, T* __restrict__ dP16, T* __restrict__ dZ_t,
                           T* __restrict__ DY_t, int64_t ld_dy, float* __restrict__ dwf_t) {
   extern __shared__ __align__(16) float smem[];
   constexpr int VN = Vec16<T>::N;
@@ -540,6 +540,7 @@ attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
         }
         acc.x += o[0]; acc.y += o[1]; acc.z += o[2]; acc.w += o[3];
         *reinterpret_cast<float4*>(dPb + (int64_t)l * A + a) = acc;
+        if (dP16 != nullptr && t == 0) st4(dP16 + ((int64_t)b * L + l) * A + a, acc);   // final value, operand dtype
       }
     }
   }
@@ -566,4 +567,43 @@ attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
 
 static inline size_t attention_bwd_smem(int L, int D, int A) {
   return sizeof(float) * (size_t)(D + ((L + 3) & ~3) + 2 * A + (ATT_THREADS / 32) * 2 * A + 40);
+}
+
+
+// =============================================================================================
+// d_ann, attention part:  tmp[b,l,d] = sum_t alpha[b,t,l] * dZ[t,b,d] + dmean[img,d] * mean_scale   (fp32)
+// The tensor-core GEMM dP * Wa then adds tmp as a coalesced residual and writes d_ann in the operand dtype
+// (d_a += alpha (x) dz, deferred to one pass after the time loop).
+// One CTA per (caption, 512-column chunk): dZ[:,b,chunk] and alpha[b,:,:] are staged in shared memory.
+// =============================================================================================
+constexpr int DANN_DC = 512;
+template <typename T>
+__global__ void __launch_bounds__(256)
+dann_alpha_kernel(const float* __restrict__ alphas, const T* __restrict__ dZ, const float* __restrict__ dmean,
+                  float* __restrict__ tmp, int B, int T_, int L, int D, int ncap, float mean_scale) {
+  extern __shared__ __align__(16) float smem[];
+  float* dzs = smem;                       // [T][DANN_DC]
+  float* als = dzs + (size_t)T_ * DANN_DC; // [T][L]
+  const int b = blockIdx.x, d0 = blockIdx.y * DANN_DC, tid = threadIdx.x;
+  const int dc = min(DANN_DC, D - d0);
+  for (int i = tid * 4; i < T_ * DANN_DC; i += 256 * 4) {
+    const int t = i / DANN_DC, c = i - t * DANN_DC;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < dc) v = ld4(dZ + ((int64_t)t * B + b) * D + d0 + c);
+    *reinterpret_cast<float4*>(dzs + i) = v;
+  }
+  for (int i = tid; i < T_ * L; i += 256) als[i] = alphas[(int64_t)b * T_ * L + i];
+  __syncthreads();
+  const int cq = (tid & 127) * 4, lg = tid >> 7;
+  if (cq >= dc) return;
+  const float4 dm = ld4(dmean + (int64_t)(b / ncap) * D + d0 + cq);
+  for (int l = lg; l < L; l += 2) {
+    float4 acc = make_float4(dm.x * mean_scale, dm.y * mean_scale, dm.z * mean_scale, dm.w * mean_scale);
+    for (int t = 0; t < T_; ++t) {
+      const float a = als[t * L + l];
+      const float4 z = *reinterpret_cast<const float4*>(dzs + (size_t)t * DANN_DC + cq);
+      acc.x = fmaf(a, z.x, acc.x); acc.y = fmaf(a, z.y, acc.y); acc.z = fmaf(a, z.z, acc.z); acc.w = fmaf(a, z.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(tmp + ((int64_t)b * L + l) * D + d0 + cq) = acc;
+  }
 }

@@ -35,6 +35,8 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)sk_dh * B * H, st));
   SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)B * H, st));
   SAT_CUDA(cudaMemsetAsync(b.dP, 0, sizeof(float) * (size_t)B * L * A, st));
+  const bool dann_tc = tc && b.dP16 != nullptr && b.dann_tmp != nullptr && !std::is_same<TS, float>::value;
+  if (dann_tc) SAT_CUDA(cudaMemsetAsync(b.dP16, 0, sizeof(TS) * (size_t)B * L * A, st));
 
   const float scale = (float)(1.0 / sqrt((double)L));
   const size_t att_smem = attention_bwd_smem(L, D, A);
@@ -58,7 +60,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
                                             (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, sk_dgz, (int64_t)B * D, dHZ_t + H, H + D, b.lens,
                                             t, d.ncap,
                                             B, L, D, A, scale, b.att_gamma, b.gscale,
-                                            b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, (TS*)b.dZ + (int64_t)t * B * D,
+                                            b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, dann_tc ? (TS*)b.dP16 : (TS*)nullptr, (TS*)b.dZ + (int64_t)t * B * D,
                                             DY_t, NH3, b.dwf_part + (int64_t)t * B * A);
     SAT_PROF(2, st);
     SAT_COUNT_LAUNCH();
@@ -84,10 +86,21 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
 
   // d_ann[b,l,:] = dP[b,l,:] * Wa + sum_t alpha[b,t,l] dZ[t,b,:] + dmean[img]/(L*ncap)
   // (for ncap > 1 the buffer holds per-caption rows [B,L,D]; the host sums the ncap rows of an image)
-  SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.dP, A, A), (const TS*)w.WaT, A, B * L, D,
-                              EpiDAnn<TS>{(TS*)b.d_ann, b.alphas, (const TS*)b.dZ, b.dmean, B, T, L, D, d.ncap,
-                                          1.0f / ((float)L * (float)d.ncap)},
-                              st)));
+  EpiDAnn<TS> epi_dann{(TS*)b.d_ann, b.alphas, (const TS*)b.dZ, b.dmean, B, T, L, D, d.ncap, 1.0f / ((float)L * (float)d.ncap)};
+  if (dann_tc) {
+    // tensor-core path: attention part + mean term in fp32 scratch, then dP16 * Wa with that scratch as a residual
+    const size_t sm = sizeof(float) * ((size_t)T * DANN_DC + (size_t)T * L);
+    auto kd = dann_alpha_kernel<TS>;
+    if (sm > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kd<<<dim3(B, (D + DANN_DC - 1) / DANN_DC), 256, sm, st>>>(b.alphas, (const TS*)b.dZ, b.dmean, b.dann_tmp, B, T, L, D, d.ncap,
+                                                              1.0f / ((float)L * (float)d.ncap));
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+    SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.dP16, A, A), (const TS*)w.WaT, A, B * L, D,
+                             EpiStore<TS, float>{(TS*)b.d_ann, D, nullptr, b.dann_tmp, D, 0}, st)));
+  } else {
+    SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.dP, A, A), (const TS*)w.WaT, A, B * L, D, epi_dann, st)));
+  }
   return 0;
 }
 

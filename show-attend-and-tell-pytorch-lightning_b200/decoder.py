@@ -63,6 +63,9 @@ class TrainBuffers:
             t["dc"] = mk((B, H), f)
             t["dZ"] = mk((T, B, D), s)
             t["dP"] = mk((B, L, A), f)
+            if dtype != torch.float32:
+                t["dP16"] = mk((B, L, A), s)
+                t["dann_tmp"] = mk((B, L, D), f)
             t["dwf_part"] = mk((T, B, A), f)
             t["dXe"] = mk((T, B, E), f)
             t["d_init_out"] = mk((Bi, 2 * H), f)
