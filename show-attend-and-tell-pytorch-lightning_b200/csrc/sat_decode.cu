@@ -24,9 +24,9 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   const int NV = D / Vec16<TS>::N;
   mean_L_kernel<TS><<<dim3((NV + 127) / 128, n_img), 128, 0, st>>>(ann, (TS*)b.meanv, L, D);
   SAT_COUNT_LAUNCH();
-  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(b.meanv, D, D), (const TS*)w.Wfact, D, n_img, E,
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.meanv, D, D), (const TS*)w.Wfact, D, n_img, E,
                            EpiStore<TS>{(TS*)b.f1, E, w.bfact, nullptr, 0}, st)));
-  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(b.f1, E, E), (const TS*)w.Winit, E, n_img, 2 * H,
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.f1, E, E), (const TS*)w.Winit, E, n_img, 2 * H,
                            EpiStore<float>{b.init_out, 2 * H, w.binit, nullptr, 0}, st)));
   init_state_decode_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>(b.init_out, (TS*)b.h, b.c, n_img, k, H);
   SAT_COUNT_LAUNCH();

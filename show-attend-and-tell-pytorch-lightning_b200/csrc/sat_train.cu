@@ -29,9 +29,9 @@ static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void
   mean_L_kernel<TS><<<dim3((NV + 127) / 128, Bi), 128, 0, st>>>((const TS*)ann, (TS*)meanv, L, D);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
-  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(meanv, D, D), (const TS*)w.Wfact, D, Bi, E,
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(meanv, D, D), (const TS*)w.Wfact, D, Bi, E,
                            EpiStore<TS>{(TS*)f1, E, w.bfact, nullptr, 0}, st)));
-  SAT_TRY((gemm_tn<TS, TS>(false, gemm_a1(f1, E, E), (const TS*)w.Winit, E, Bi, 2 * H,
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(f1, E, E), (const TS*)w.Winit, E, Bi, 2 * H,
                            EpiStore<float>{init_out, 2 * H, w.binit, nullptr, 0}, st)));
   const int64_t n = 2 * (int64_t)B * H;
   init_state_kernel<TS><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(init_out, (TS*)h0, c0, H, H, B, H, d.ncap);

@@ -6,6 +6,7 @@
 //   GEMM dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (one GEMM, K = A+D+4H)
 // Everything else is hoisted to whole-sequence GEMMs over T*B rows (dpre, dHZ, dXe, d_ann), and
 // the parameter gradients are plain reductions over (t,b) of the buffers written here.
+#include "sat_attention_pipe.cuh"
 #include "sat_gemm.cuh"
 #include "sat_kernels.cuh"
 
@@ -39,8 +40,10 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   if (dann_tc) SAT_CUDA(cudaMemsetAsync(b.dP16, 0, sizeof(TS) * (size_t)B * L * A, st));
 
   const float scale = (float)(1.0 / sqrt((double)L));
-  const size_t att_smem = attention_bwd_smem(L, D, A);
-  auto att_k = attention_step_bwd_kernel<TS, kExact>;
+  const bool att_pipe = attention_bwd_pipe_ok<TS>(D, A);
+  const size_t att_smem = att_pipe ? attention_bwd_pipe_smem(L, D, A) : attention_bwd_smem(L, D, A);
+  auto att_k = att_pipe ? attention_step_bwd_pipe_kernel<TS, kExact, ATTP_BWD_CW> : attention_step_bwd_kernel<TS, kExact>;
+  const int att_threads = att_pipe ? ATTP_BWD_CW * 32 + 32 : ATT_THREADS;
   if (att_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(att_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
 
   for (int t = T - 1; t >= 0; --t) {
@@ -55,7 +58,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + A + D, NH3, 4 * H), (const TS*)w.WihzT, 4 * H, B, D,
                              EpiStore<float>{b.dgz, D, nullptr, nullptr, 0, (int64_t)B * D}, st, sk_dgz)));
     SAT_PROF(2, st);
-    att_k<<<B, ATT_THREADS, att_smem, st>>>(ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
+    att_k<<<B, att_threads, att_smem, st>>>(ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
                                             (int64_t)T * L, b.S, (const TS*)b.Z + (int64_t)t * B * D,
                                             (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, sk_dgz, (int64_t)B * D, dHZ_t + H, H + D, b.lens,
                                             t, d.ncap,
