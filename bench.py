@@ -298,7 +298,7 @@ def run_train(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "attention_fwd_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roof = {"kernel": "attention_step_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"kernel": "attention_step_fwd_pipe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "launches_timed": att_n,
             "avg_launch_us": 1e3 * att_ms / max(att_n, 1), "algorithmic_bytes_per_launch": att_bytes,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}

@@ -30,9 +30,20 @@ class FlatGradBuckets:
             flat = torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=dev)
             off = 0
             for p in b:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                p.grad = self._view(flat, off, p)
                 off += p.numel()
             self.flat.append(flat)
+
+    @staticmethod
+    def _view(flat, off, p):
+        """bucket slice with the parameter's own strides (channels_last conv weights keep their layout, so autograd's
+        gradient-layout contract holds and no per-step transposes are inserted)."""
+        try:
+            if p.is_contiguous() or not p.is_non_overlapping_and_dense():
+                return flat[off:off + p.numel()].view_as(p)
+            return flat[off:off + p.numel()].as_strided(p.size(), p.stride())
+        except Exception:
+            return flat[off:off + p.numel()].view_as(p)
 
     def zero(self):
         for f in self.flat:
@@ -43,7 +54,7 @@ class FlatGradBuckets:
         for b, flat in zip(self.buckets, self.flat):
             off = 0
             for p in b:
-                v = flat[off:off + p.numel()].view_as(p)
+                v = self._view(flat, off, p)
                 if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                     if p.grad is not None:
                         v.copy_(p.grad)
