@@ -80,7 +80,10 @@ typedef struct SatTrainBuffers {
   const void* ann;       /* [Bi,L,D] s   annotations: channels-last view of get_encoder's [Bi,D,h,w] (model.py:483) */
   const int32_t* caps;   /* [B,T+1]      encoded captions, column 0 = <START>                     */
   const int32_t* lens;   /* [B]          number of targets per caption (model.py:492)             */
+  const int32_t* sampled; /* HOST pointer, [T] flags or NULL: step t feeds back argmax_v logits[t-1] instead of the ground-truth
+                            word (scheduled sampling, model.py:518-523; the host draws torch.rand(1) per step > 2)      */
   /* fwd */
+  int32_t* tok;          /* [T,B]        previous-word ids actually fed at each step (ground truth or sampled)      */
   void* P;               /* [Bi,L,A] s   W_a * a, once per image (reference recomputes per step, model.py:100) */
   void* meanv;           /* [Bi,D] s     mean over locations (model.py:78)                        */
   void* f1;              /* [Bi,E] s     init_lstm.factorize output                               */

@@ -79,7 +79,7 @@ def deep_output(W, x_e, h, z, deep=True):
     else:
         x = h @ W["output.hidden.weight"].t()
     logit = x @ W["output.output.weight"].t()
-    if "output.output.bias" in W and W["output.output.bias"] is not None:
+    if W.get("output.output.bias", None) is not None:
         logit = logit + W["output.output.bias"]
     return logit
 
@@ -155,9 +155,9 @@ def label_smoothing_loss(x, target, smoothing=0.0):
 
 
 def train_loss(W, ann_img, encoded_captions, lengths, label_smoothing=0.0, att_gamma=1.0,
-               epsilon=1.0, deep=True):
+               epsilon=1.0, deep=True, rand=None):
     """model.py:588-597: returns dict(loss, acc, ce, reg, logits, alphas)."""
-    logits, alphas, caps, lens = train_batch(W, ann_img, encoded_captions, lengths, epsilon, deep)
+    logits, alphas, caps, lens = train_batch(W, ann_img, encoded_captions, lengths, epsilon, deep, rand)
     lp, tp = pack(logits, caps, lens)
     ce = label_smoothing_loss(lp.data, tp.data, label_smoothing)
     reg = ((1 - alphas.sum(dim=1)) ** 2).mean()                     # model.py:594

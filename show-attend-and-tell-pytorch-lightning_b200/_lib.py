@@ -26,7 +26,7 @@ class SatWeights(C.Structure):
 
 class SatTrainBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
-                ("ann", "caps", "lens", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
+                ("ann", "caps", "lens", "sampled", "tok", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
                  "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
                  "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dann_tmp", "dwf_part", "dXe", "d_init_out",
                  "df1", "dmean", "d_ann")] + \

@@ -16,7 +16,10 @@
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, THREADS = 192;
+constexpr int BM = 128, BK = 64, THREADS = 192;
+// operand ring depth: 4 x 24 KB at BN = 64 and 3 x 32 KB at BN = 128 -> 96 KB per CTA, two CTAs per SM, so one CTA's
+// epilogue overlaps the other's TMA/MMA main loop (the kernels are not persistent)
+template <int BN> struct Stages { static constexpr int value = BN >= 128 ? 3 : 4; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,6 +96,7 @@ struct Maps {
 
 template <int BN>
 struct Smem {
+  static constexpr int STAGES = Stages<BN>::value;
   alignas(1024) bf16 a[STAGES][BM * BK];
   alignas(1024) bf16 w[STAGES][BN * BK];
   alignas(8) uint64_t full[STAGES];
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(THREADS)
 gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k1, Epi epi) {
   // gridDim.z = split-K factor: CTA z accumulates k blocks [z*nkb/S, (z+1)*nkb/S) (partials are summed by the consumer)
   extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGES = Stages<BN>::value;
   Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;

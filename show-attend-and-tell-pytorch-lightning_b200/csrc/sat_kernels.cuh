@@ -251,18 +251,56 @@ static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int 
 }
 
 // =============================================================================================
-// embedding gather, time-major:  Xe[t,b,:] = Emb[caps[b,t],:]                         model.py:526
+// previous-word ids, time-major: tok[t,b] = caps[b,t]   (teacher forcing, model.py:520)
+// =============================================================================================
+static __global__ void tok_init_kernel(const int32_t* __restrict__ caps, int32_t* __restrict__ tok, int B, int T_, int caplen) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= T_ * B) return;
+  const int t = m / B, b = m - t * B;
+  tok[m] = caps[(int64_t)b * caplen + t];
+}
+
+// =============================================================================================
+// embedding gather over `rows` time-major rows:  Xe[m,:] = Emb[tok[m],:]                 model.py:526
 // =============================================================================================
 template <typename T>
-__global__ void embed_gather_kernel(const T* __restrict__ Emb, const int32_t* __restrict__ caps, T* __restrict__ Xe,
-                                    int B, int T_, int E, int caplen) {
-  const int m = blockIdx.x;            // m = t*B + b
-  const int t = m / B, b = m - t * B;
-  const int w = caps[(int64_t)b * caplen + t];
+__global__ void embed_gather_kernel(const T* __restrict__ Emb, const int32_t* __restrict__ tok, T* __restrict__ Xe, int E) {
+  const int m = blockIdx.x;
+  const int w = tok[m];
   constexpr int VN = Vec16<T>::N;
   for (int c = threadIdx.x; c < E / VN; c += blockDim.x) {
     const uint4 v = *reinterpret_cast<const uint4*>(Emb + (int64_t)w * E + c * VN);
     *reinterpret_cast<uint4*>(Xe + (int64_t)m * E + c * VN) = v;
+  }
+}
+
+// =============================================================================================
+// scheduled sampling feedback: tok[b] = argmax_v logits[b,:] (first maximal index, like torch.argmax, model.py:523)
+// =============================================================================================
+template <typename TL>
+__global__ void __launch_bounds__(256) row_argmax_kernel(const TL* __restrict__ logits, int32_t* __restrict__ tok, int V) {
+  __shared__ float s_val[8];
+  __shared__ int s_arg[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const TL* row = logits + (int64_t)b * V;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int v = tid; v < V; v += 256) {
+    const float xv = to_f(row[v]);
+    if (xv > mx) { mx = xv; arg = v; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = mx; s_arg[tid >> 5] = arg; }
+  __syncthreads();
+  if (tid == 0) {
+    mx = s_val[0]; arg = s_arg[0];
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > mx || (s_val[w] == mx && s_arg[w] < arg)) { mx = s_val[w]; arg = s_arg[w]; }
+    tok[b] = arg == 0x7fffffff ? 0 : arg;
   }
 }
 

@@ -52,7 +52,9 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   SAT_TRY(sat_prepare_images(&d, &w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st));
 
   // ---- hoisted: embeddings of the (teacher-forced) previous words and their gate projection ---
-  embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.caps, (TS*)b.Xe, B, T, E, caplen);
+  tok_init_kernel<<<(T * B + 255) / 256, 256, 0, st>>>(b.caps, b.tok, B, T, caplen);
+  SAT_COUNT_LAUNCH();
+  embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.tok, (TS*)b.Xe, E);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xe, E, E), (const TS*)w.Wihe, E, T * B, 4 * H,
@@ -61,6 +63,28 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   // ---- recurrence ------------------------------------------------------------------------------
   const float scale = (float)(1.0 / sqrt((double)L));
   for (int t = 0; t < T; ++t) {
+    if (b.sampled != nullptr && t > 0 && b.sampled[t]) {
+      // scheduled sampling (model.py:518-523): this step's input word is argmax_v logits[t-1]; compute the output of
+      // step t-1 now (the hoisted whole-sequence GEMMs below recompute the same values), then re-embed and re-project.
+      const int64_t o1 = (int64_t)(t - 1) * B;
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)b.Hs + (int64_t)t * B * H, H, H, (const TS*)b.Z + o1 * D, D, D), (const TS*)w.Whozo,
+                               H + D, B, E, EpiTanhAdd<TS, kExact>{(const TS*)b.Xe + o1 * E, (TS*)b.Xo + o1 * E, E, nullptr}, st)));
+      if (b.logits_f32) {
+        SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xo + o1 * E, E, E), (const TS*)w.Wo, E, B, V,
+                                 EpiStore<float>{(float*)b.logits + o1 * V, V, w.bo, nullptr, 0}, st)));
+        row_argmax_kernel<float><<<B, 256, 0, st>>>((const float*)b.logits + o1 * V, b.tok + (int64_t)t * B, V);
+      } else {
+        SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xo + o1 * E, E, E), (const TS*)w.Wo, E, B, V,
+                                 EpiStore<TS>{(TS*)b.logits + o1 * V, V, w.bo, nullptr, 0}, st)));
+        row_argmax_kernel<TS><<<B, 256, 0, st>>>((const TS*)b.logits + o1 * V, b.tok + (int64_t)t * B, V);
+      }
+      SAT_COUNT_LAUNCH();
+      embed_gather_kernel<TS><<<B, 64, 0, st>>>((const TS*)w.Emb, b.tok + (int64_t)t * B, (TS*)b.Xe + (int64_t)t * B * E, E);
+      SAT_COUNT_LAUNCH();
+      SAT_LAUNCH_OK();
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xe + (int64_t)t * B * E, E, E), (const TS*)w.Wihe, E, B, 4 * H,
+                               EpiStore<float>{b.Gx + (int64_t)t * B * 4 * H, 4 * H, w.bg, nullptr, 0}, st)));
+    }
     const TS* h_t = (const TS*)b.Hs + (int64_t)t * B * H;
     const float* c_t = b.Cs + (int64_t)t * B * H;
     // hp = h_t * [W_h | W_beta | W_hh]^T + [0 | b_beta | 0]
@@ -189,7 +213,7 @@ int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b,
   SAT_TRY(check_dims(d));
   SAT_REQUIRE(w && b, "sat_train_forward: NULL struct");
   SAT_REQUIRE(d->T > 0, "sat_train_forward: T must be > 0");
-  SAT_REQUIRE(b->ann && b->caps && b->lens && b->P && b->meanv && b->f1 && b->init_out && b->Xe && b->Gx && b->Hs && b->Cs &&
+  SAT_REQUIRE(b->ann && b->caps && b->lens && b->tok && b->P && b->meanv && b->f1 && b->init_out && b->Xe && b->Gx && b->Hs && b->Cs &&
                   b->hp && b->Q && b->alphas && b->Z && b->GZ && b->Beta && b->Gates && b->Xo && b->logits && b->row_loss &&
                   b->row_argmax && b->S && b->out,
               "sat_train_forward: NULL forward buffer");

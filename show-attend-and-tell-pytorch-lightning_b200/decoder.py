@@ -30,6 +30,7 @@ class TrainBuffers:
         s, f = dtype, torch.float32
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
         t = self.t = {}
+        t["tok"] = mk((T, B), torch.int32)
         t["P"] = mk((Bi, L, A), s)
         t["meanv"] = mk((Bi, D), s)
         t["f1"] = mk((Bi, E), s)
@@ -79,9 +80,15 @@ class TrainBuffers:
         self.c.logits_f32 = 1 if logits_f32 else 0
         self.dims = d
 
-    def bind_inputs(self, ann, caps, lens, label_smoothing, att_gamma):
+    def bind_inputs(self, ann, caps, lens, label_smoothing, att_gamma, sampled=None):
         self.t["ann"], self.t["caps"], self.t["lens"] = ann, caps, lens   # keep alive
         self.c.ann, self.c.caps, self.c.lens = _lib.ptr(ann), _lib.ptr(caps), _lib.ptr(lens)
+        if sampled is not None and any(sampled):
+            self._sampled = (C.c_int32 * len(sampled))(*[1 if x else 0 for x in sampled])     # host array, kept alive
+            self.c.sampled = C.cast(self._sampled, C.c_void_p)
+        else:
+            self._sampled = None
+            self.c.sampled = None
         self.c.label_smoothing = float(label_smoothing)
         self.c.att_gamma = float(att_gamma)
 
@@ -97,7 +104,7 @@ def annotations_as_bld(ann, dtype):
 
 
 def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, exact=True, use_tc=False,
-                  logits_f32=False, backward=True, keep_logits=False, buffers=None):
+                  logits_f32=False, backward=True, keep_logits=False, buffers=None, sampled=None):
     """ann_bld [Bi,L,D] (pw.dtype, cuda); caps [Bi,ncap,T+1] or [B,T+1] int; lens [Bi,ncap] or [B].
     Runs sat_train_forward; returns the TrainBuffers (loss etc. in .t['out'])."""
     L_ = _lib.lib()
@@ -112,7 +119,7 @@ def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, e
     d = make_dims(B, Bi, L, D, dm["A"], dm["E"], dm["H"], dm["V"], caplen - 1, pw.dtype, exact, use_tc)
     if buffers is None:
         buffers = TrainBuffers(d, pw.dtype, dev, logits_f32=logits_f32, backward=backward, keep_logits=keep_logits)
-    buffers.bind_inputs(ann_bld, caps2, lens2, label_smoothing, att_gamma)
+    buffers.bind_inputs(ann_bld, caps2, lens2, label_smoothing, att_gamma, sampled)
     buffers.dims = d
     _lib.check(L_.sat_train_forward(C.byref(d), pw.ref(), C.byref(buffers.c), _lib.stream_ptr()), "sat_train_forward")
     return buffers
@@ -184,7 +191,7 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
     G["init_lstm.init.bias"] = dio.sum(0)
     G["init_lstm.factorize.weight"] = _mm_tn(t["df1"], t["meanv"].float())
     G["init_lstm.factorize.bias"] = t["df1"].sum(0)
-    tok = t["caps"][:, :T].t().reshape(M).long()
+    tok = t["tok"].reshape(M).long()            # words actually fed (ground truth or scheduled-sampling feedback)
     dEmb = torch.zeros(V, E, dtype=torch.float32, device=dlog.device)
     dEmb.index_add_(0, tok, t["dXe"].reshape(M, E))
     if pad_idx is not None:

@@ -260,7 +260,8 @@ class _FusedTrainLoss(torch.autograd.Function):
         pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, cfg["label_smoothing"], cfg["att_gamma"], exact=cfg["exact"],
-                                    use_tc=cfg["use_tc"], logits_f32=False, backward=True, keep_logits=False)
+                                    use_tc=cfg["use_tc"], logits_f32=False, backward=True, keep_logits=False,
+                                    sampled=cfg.get("sampled"))
         ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
         ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
         ctx.have = [p is not None for p in params]
@@ -290,7 +291,7 @@ class _TrainLogits(torch.autograd.Function):
         pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, 0.0, 0.0, exact=cfg["exact"], use_tc=cfg["use_tc"],
-                                    logits_f32=True, backward=True, keep_logits=True)
+                                    logits_f32=True, backward=True, keep_logits=True, sampled=cfg.get("sampled"))
         ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
         ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
         ctx.have = [p is not None for p in params]
@@ -397,30 +398,47 @@ class SAT(_Base):
         return self.encoder(img)
 
     # ---- training (model.py:474-628) ----------------------------------------------------------
+    @staticmethod
+    def _sampling_plan(lengths, T, epsilon):
+        """Host-side schedule of model.py:518: steps 0..2 are teacher-forced; for every later step that still has an
+        active caption one torch.rand(1) is drawn and the step feeds back argmax(logits[t-1]) when it exceeds epsilon."""
+        eps = float(epsilon)
+        if eps >= 1.0:
+            return None
+        max_len = int(lengths.max())
+        plan = [0] * T
+        for step in range(min(T, max_len)):
+            if step <= 2:
+                continue
+            if not bool(torch.rand(1) <= eps):
+                plan[step] = 1
+        return plan
+
     def train_batch(self, batch, epsilon=0):
         """-> (PackedSequence logits fp32, PackedSequence targets, alphas [B,T,L])  (model.py:557)."""
-        if float(epsilon) < 1.0:
-            raise NotImplementedError("scheduled sampling (epsilon < 1, model.py:518-523) is not on the accelerated "
-                                      "path yet; use epsilon=1 / decoder_tf='always'")
         if self.training and (self.hparams.dropout > 0 or self.hparams.embedding_dropout > 0):
             raise NotImplementedError("dropout > 0 is not on the accelerated path yet")
         img, encoded_captions, lengths = batch
         ann = self.encode(img)
-        logits, alphas = _TrainLogits.apply(ann, encoded_captions, lengths, self._cfg(), *self.decoder_weights())
+        cfg = self._cfg()
+        cfg["sampled"] = self._sampling_plan(lengths, encoded_captions.size(2) - 1, epsilon)
+        logits, alphas = _TrainLogits.apply(ann, encoded_captions, lengths, cfg, *self.decoder_weights())
         caps = encoded_captions.reshape(-1, encoded_captions.size(2))
         lens = lengths.reshape(-1).tolist()
         logits_packed = pack_padded_sequence(logits, lens, batch_first=True, enforce_sorted=False)
         targets_packed = pack_padded_sequence(caps[:, 1:], lens, batch_first=True, enforce_sorted=False)
         return logits_packed, targets_packed, alphas
 
-    def fused_loss(self, batch):
-        """Fused forward + loss of one teacher-forced step: (loss with grad, aux[8] = loss, ce, reg,
-        accuracy, 1/ntok, ntok).  This is what training_step runs."""
+    def fused_loss(self, batch, epsilon=1.0):
+        """Fused forward + loss of one training step: (loss with grad, aux[8] = loss, ce, reg,
+        accuracy, 1/ntok, ntok).  This is what training_step runs; epsilon < 1 enables scheduled sampling."""
         if self.training and (self.hparams.dropout > 0 or self.hparams.embedding_dropout > 0):
             raise NotImplementedError("dropout > 0 is not on the accelerated path yet")
         img, encoded_captions, lengths = batch
         ann = self.encode(img)
-        return _FusedTrainLoss.apply(ann, encoded_captions, lengths, self._cfg(), *self.decoder_weights())
+        cfg = self._cfg()
+        cfg["sampled"] = self._sampling_plan(lengths, encoded_captions.size(2) - 1, epsilon)
+        return _FusedTrainLoss.apply(ann, encoded_captions, lengths, cfg, *self.decoder_weights())
 
     def _epsilon(self):
         hp = self.hparams
@@ -443,12 +461,10 @@ class SAT(_Base):
     def training_step(self, batch, batch_idx):
         hp = self.hparams
         epsilon = self._epsilon()
-        if epsilon < 1.0:
-            raise NotImplementedError("decoder_tf != 'always' (scheduled sampling) is not on the accelerated path yet")
         if self.global_step == hp.encoder_finetune_after and hp.encoder_finetune_after >= 0:
             for p in self.encoder.parameters():
                 p.requires_grad = True
-        loss, aux = self.fused_loss(batch)
+        loss, aux = self.fused_loss(batch, epsilon)
         metrics = {"loss": loss, "accuracy": aux[3], "epsilon_tf": float(epsilon)}   # device scalars: no sync here
         logger = getattr(self, "logger", None)
         if logger is not None and getattr(logger, "experiment", None) is not None:

@@ -96,8 +96,59 @@ def test_module_forwards_match_oracle():
     assert relerr(lo, lo_ref) < 1e-5
 
 
-def test_scheduled_sampling_not_silently_wrong():
-    m = build()
-    ann, caps, lens = batch(1)
-    with pytest.raises(NotImplementedError):
-        m.train_batch((ann.cuda(), caps.cuda(), lens.cuda()), epsilon=0)
+@pytest.mark.parametrize("epsilon", [0.0, 0.5])
+def test_scheduled_sampling_matches_oracle(epsilon):
+    """epsilon < 1 (model.py:518-523): steps > 2 feed back argmax(logits[t-1]) when the host draw exceeds epsilon.  Same CPU RNG
+    stream for the oracle and the module (one torch.rand(1) per step > 2 that still has an active caption)."""
+    m = build(seed=3, label_smoothing=0.1)
+    with torch.no_grad():
+        m.output.output.weight *= 6          # decisive argmax so the fed-back tokens are stable across rounding
+    ann, caps, lens = batch(4, ncap=2, T=9)
+    W = {k: v.requires_grad_(True) for k, v in weights_cpu(m).items()}
+    a_ref = ann.clone().requires_grad_(True)
+    torch.manual_seed(123)
+    ref = O.train_loss(W, a_ref, caps, lens, 0.1, 1.0, epsilon=epsilon)
+    ref["loss"].backward()
+    m.train()
+    torch.manual_seed(123)
+    a = ann.cuda().requires_grad_(True)
+    lp, tp, alphas = m.train_batch((a, caps.cuda(), lens.cuda()), epsilon=epsilon)
+    assert relerr(lp.data, ref["logits_packed"].data) < 1e-5
+    assert relerr(alphas, ref["alphas"]) < 1e-5
+    loss = m.criterion(lp.data, tp.data) + ((1 - alphas.sum(dim=1)) ** 2).mean()
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, W[k].grad) < 5e-5, k
+    # fused path with the same draws
+    m.zero_grad()
+    torch.manual_seed(123)
+    loss2, aux = m.fused_loss((ann.cuda(), caps.cuda(), lens.cuda()), epsilon=epsilon)
+    assert abs(float(loss2) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    loss2.backward()
+    assert relerr(m.embedding.weight.grad, W["embedding.weight"].grad) < 5e-5
+
+
+def test_weight_tying_shares_embedding_and_grads_match():
+    """weight_tying (model.py:198-199): output.output.weight IS embedding.weight, no output bias."""
+    from sat_b200.model import SAT
+    torch.manual_seed(5)
+    hp = rh.default_hparams(encoder_dim=64, attention_dim=32, embed_dim=32, decoder_dim=64, vocab_size=128, input_size=64,
+                            weight_tying=True, label_smoothing=0.1)
+    m = SAT(**hp)
+    m.encoder = nn.Identity()
+    m = m.cuda()
+    assert m.output.output.weight is m.embedding.weight and m.output.output.bias is None
+    ann, caps, lens = batch(7, ncap=1)
+    W = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items() if not k.startswith("encoder")}
+    emb = W["embedding.weight"]
+    Wt = dict(W)
+    Wt["output.output.weight"] = emb                      # tied: same leaf
+    Wt["output.output.bias"] = None
+    ref = O.train_loss(Wt, ann, caps, lens, 0.1, 1.0)
+    ref["loss"].backward()
+    m.train()
+    out = m.training_step((ann.cuda(), caps.cuda(), lens.cuda()), 0)
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    out["loss"].backward()
+    assert relerr(m.embedding.weight.grad, emb.grad) < 5e-5
+    assert relerr(m.lstm.weight_ih_l0.grad, W["lstm.weight_ih_l0"].grad) < 5e-5
