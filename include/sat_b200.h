@@ -41,7 +41,7 @@ typedef struct SatDims {
   int32_t dtype;      /* SAT_F32 | SAT_BF16 */
   int32_t exact;      /* 1: libm-accurate tanh/exp (fp32 parity mode); 0: MUFU approximations */
   int32_t use_tc;     /* 1: tcgen05 tensor-core GEMMs where the shape allows (bf16 only); 0: SIMT FFMA GEMMs */
-  int32_t reserved;
+  int32_t plain_output; /* 1: DeepOutput with deep=False (model.py:128-129: x = W_ho h', no tanh / embedding / context); 0: deep */
 } SatDims;
 
 /* Packed decoder weights (device).  "s" = storage dtype of SatDims.dtype. */

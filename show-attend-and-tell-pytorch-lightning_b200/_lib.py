@@ -15,7 +15,7 @@ vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # all device pointers travel a
 
 class SatDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("B", "Bi", "ncap", "L", "D", "A", "E", "H", "V", "T", "dtype", "exact", "use_tc", "reserved")]
+                ("B", "Bi", "ncap", "L", "D", "A", "E", "H", "V", "T", "dtype", "exact", "use_tc", "plain_output")]
 
 
 class SatWeights(C.Structure):

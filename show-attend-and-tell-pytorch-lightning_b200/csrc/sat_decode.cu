@@ -54,7 +54,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
                             (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.gz, D, D), (const TS*)w.Wihz, D, R, 4 * H, epi, st)));
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(b.hn, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
-                             EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok}, st)));
+                             EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok, d.plain_output}, st)));
     SAT_PROF(3, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
     SAT_PROF(3, st);

@@ -246,15 +246,20 @@ template <typename TS, bool kExact>
 struct EpiTanhAdd {
   const TS* Xe; TS* Xo; int64_t ld;
   const int32_t* xe_row;               // optional: Xe row index per m (decode: token id into the embedding table)
+  int plain;                           // DeepOutput(deep=False): Xo = acc (model.py:129)
   struct Ctx { float4 x; };
   __device__ __forceinline__ Ctx load(int m, int n) const {
     Ctx c;
-    c.x = ld4(Xe + (int64_t)(xe_row ? xe_row[m] : m) * ld + n);
+    c.x = plain ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(Xe + (int64_t)(xe_row ? xe_row[m] : m) * ld + n);
     return c;
   }
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
   __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
     const float4 x = c.x;
+    if (plain) {
+      st4(Xo + (int64_t)m * ld + n, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      return;
+    }
     st4(Xo + (int64_t)m * ld + n,
         make_float4(sat_tanh<kExact>(acc[0] + x.x), sat_tanh<kExact>(acc[1] + x.y), sat_tanh<kExact>(acc[2] + x.z),
                     sat_tanh<kExact>(acc[3] + x.w)));
@@ -265,6 +270,7 @@ struct EpiTanhAdd {
 template <typename TS>
 struct EpiDpre {
   const TS* Xo; TS* dpre; int64_t ld; const float* gscale;
+  int plain;                           // DeepOutput(deep=False): no tanh derivative
   struct Ctx { float4 x; float g; };
   __device__ __forceinline__ Ctx load(int m, int n) const {
     Ctx c;
@@ -275,7 +281,7 @@ struct EpiDpre {
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
   __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
     const float g = c.g;
-    const float4 x = c.x;
+    const float4 x = plain ? make_float4(0.f, 0.f, 0.f, 0.f) : c.x;
     st4(dpre + (int64_t)m * ld + n, make_float4(g * acc[0] * (1.f - x.x * x.x), g * acc[1] * (1.f - x.y * x.y),
                                                  g * acc[2] * (1.f - x.z * x.z), g * acc[3] * (1.f - x.w * x.w)));
   }

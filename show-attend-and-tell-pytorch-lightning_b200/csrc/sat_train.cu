@@ -68,7 +68,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
       // step t-1 now (the hoisted whole-sequence GEMMs below recompute the same values), then re-embed and re-project.
       const int64_t o1 = (int64_t)(t - 1) * B;
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)b.Hs + (int64_t)t * B * H, H, H, (const TS*)b.Z + o1 * D, D, D), (const TS*)w.Whozo,
-                               H + D, B, E, EpiTanhAdd<TS, kExact>{(const TS*)b.Xe + o1 * E, (TS*)b.Xo + o1 * E, E, nullptr}, st)));
+                               H + D, B, E, EpiTanhAdd<TS, kExact>{(const TS*)b.Xe + o1 * E, (TS*)b.Xo + o1 * E, E, nullptr, d.plain_output}, st)));
       if (b.logits_f32) {
         SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xo + o1 * E, E, E), (const TS*)w.Wo, E, B, V,
                                  EpiStore<float>{(float*)b.logits + o1 * V, V, w.bo, nullptr, 0}, st)));
@@ -108,7 +108,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   // ---- hoisted: deep output (model.py:127) and vocabulary projection (model.py:130) over all T*B rows
   const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
-                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr}, st)));
+                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr, d.plain_output}, st)));
   SAT_PROF(3, st);
   if (b.logits_f32) {
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,

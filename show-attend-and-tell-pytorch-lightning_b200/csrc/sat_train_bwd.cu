@@ -22,7 +22,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
 
   // dpre = g * (dlogits * Wo) * (1 - Xo^2)            [M,E]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dlogits, V, V), (const TS*)w.WoT, V, M, E,
-                           EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale}, st)));
+                           EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale, d.plain_output}, st)));
   // dHZ = dpre * [W_ho | W_zo]                         [M,H+D]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dpre, E, E), (const TS*)w.WhozoT, E, M, H + D,
                            EpiStore<float>{b.dHZ, H + D, nullptr, nullptr, 0}, st)));
@@ -76,7 +76,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
 
   // dXe = dG * Wihe + dpre                               [M,E]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.DY + A + D, NH3, 4 * H), (const TS*)w.WiheT, 4 * H, M, E,
-                           EpiStore<float, TS>{b.dXe, E, nullptr, (const TS*)b.dpre, E}, st)));
+                           EpiStore<float, TS>{b.dXe, E, nullptr, d.plain_output ? (const TS*)nullptr : (const TS*)b.dpre, E}, st)));
 
   // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
   init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, b.d_init_out, B, H, d.ncap);

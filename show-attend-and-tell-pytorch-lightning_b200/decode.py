@@ -23,7 +23,7 @@ class DecodeWeights:
         self.pw = PackedWeights(W, dtype=dtype, device=device, backward=False)
         dm = self.pw.dims
         self.exact, self.use_tc = exact, use_tc
-        d = decoder.make_dims(1, 1, 1, dm["D"], dm["A"], dm["E"], dm["H"], dm["V"], 1, dtype, exact, use_tc)
+        d = decoder.make_dims(1, 1, 1, dm["D"], dm["A"], dm["E"], dm["H"], dm["V"], 1, dtype, exact, use_tc, self.pw.plain_output)
         self.GxV = torch.empty(dm["V"], 4 * dm["H"], dtype=torch.float32, device=device)
         _lib.check(_lib.lib().sat_decode_prepare_weights(C.byref(d), self.pw.ref(), _lib.ptr(self.GxV), _lib.stream_ptr()),
                    "sat_decode_prepare_weights")
@@ -41,7 +41,7 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     S = int(max_gen_length)
     R = n_img * k
     dtype = dw.pw.dtype
-    d = decoder.make_dims(R, n_img, L, D, A, E, H, V, S + 1, dtype, dw.exact, dw.use_tc)
+    d = decoder.make_dims(R, n_img, L, D, A, E, H, V, S + 1, dtype, dw.exact, dw.use_tc, dw.pw.plain_output)
     f, s, i32 = torch.float32, dtype, torch.int32
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
     t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * H), f),

@@ -11,8 +11,9 @@ from . import _lib
 from .packing import PackedWeights, deinterleave_gates
 
 
-def make_dims(B, Bi, L, D, A, E, H, V, T, dtype, exact, use_tc):
+def make_dims(B, Bi, L, D, A, E, H, V, T, dtype, exact, use_tc, plain_output=False):
     d = _lib.SatDims()
+    d.plain_output = 1 if plain_output else 0
     d.B, d.Bi, d.ncap = B, Bi, B // Bi
     d.L, d.D, d.A, d.E, d.H, d.V, d.T = L, D, A, E, H, V, T
     d.dtype = _lib.dtype_code(dtype)
@@ -116,7 +117,7 @@ def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, e
     dm = pw.dims
     assert D == dm["D"], "annotation width %d != encoder_dim %d" % (D, dm["D"])
     assert ann_bld.dtype == pw.dtype and ann_bld.is_contiguous()
-    d = make_dims(B, Bi, L, D, dm["A"], dm["E"], dm["H"], dm["V"], caplen - 1, pw.dtype, exact, use_tc)
+    d = make_dims(B, Bi, L, D, dm["A"], dm["E"], dm["H"], dm["V"], caplen - 1, pw.dtype, exact, use_tc, pw.plain_output)
     if buffers is None:
         buffers = TrainBuffers(d, pw.dtype, dev, logits_f32=logits_f32, backward=backward, keep_logits=keep_logits)
     buffers.bind_inputs(ann_bld, caps2, lens2, label_smoothing, att_gamma, sampled)
@@ -165,7 +166,8 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
     dpre = t["dpre"].reshape(M, E)
     Hn = t["Hs"][1:].reshape(M, H)
     G["output.hidden.weight"] = _mm_tn(dpre, Hn)
-    G["output.context.weight"] = _mm_tn(dpre, t["Z"].reshape(M, D))
+    if not pw.plain_output:
+        G["output.context.weight"] = _mm_tn(dpre, t["Z"].reshape(M, D))
     DY = t["DY"].reshape(M, NH3)
     dWh3 = _mm_tn(DY, t["Hs"][:T].reshape(M, H))
     G["attention.decoder_att.weight"] = dWh3[:A]

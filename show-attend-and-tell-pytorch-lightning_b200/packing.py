@@ -41,9 +41,9 @@ class PackedWeights:
         wa, wh = f32(W["attention.encoder_att.weight"]), f32(W["attention.decoder_att.weight"])
         wb, bb = f32(W["beta.0.weight"]), f32(W["beta.0.bias"])
         who = f32(W["output.hidden.weight"])
-        if "output.context.weight" not in W or W["output.context.weight"] is None:
-            raise NotImplementedError("deep_output=False is not on the accelerated path yet (BASELINE configs use deep_output=True)")
-        wzo = f32(W["output.context.weight"])
+        # DeepOutput(deep=False) has no context projection (model.py:120-121): pack zeros and flag the plain epilogues
+        self.plain_output = W.get("output.context.weight", None) is None
+        wzo = torch.zeros(who.shape[0], wa.shape[1], device=dev) if self.plain_output else f32(W["output.context.weight"])
         wo = f32(W["output.output.weight"])
         bo = W.get("output.output.bias", None)
         V, E = emb.shape

@@ -152,3 +152,43 @@ def test_weight_tying_shares_embedding_and_grads_match():
     out["loss"].backward()
     assert relerr(m.embedding.weight.grad, emb.grad) < 5e-5
     assert relerr(m.lstm.weight_ih_l0.grad, W["lstm.weight_ih_l0"].grad) < 5e-5
+
+
+def test_plain_output_layer_deep_output_false():
+    """deep_output=False (train.py default; model.py:128-129): x = W_ho h', no tanh / embedding / context term."""
+    m = build(seed=6, deep_output=False, label_smoothing=0.1)
+    assert not hasattr(m.output, "context")
+    ann, caps, lens = batch(8, ncap=1)
+    W = {k: v.requires_grad_(True) for k, v in weights_cpu(m).items()}
+    a_ref = ann.clone().requires_grad_(True)
+    ref = O.train_loss(W, a_ref, caps, lens, 0.1, 1.0, deep=False)
+    ref["loss"].backward()
+    m.train()
+    a = ann.cuda().requires_grad_(True)
+    out = m.training_step((a, caps.cuda(), lens.cuda()), 0)
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    out["loss"].backward()
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, W[k].grad) < 5e-5, k
+    assert relerr(a.grad, a_ref.grad) < 5e-5
+    # decode through the module API
+    Wd = {k: v.detach() for k, v in W.items()}
+    Wd["output.output.weight"] = Wd["output.output.weight"] * 8
+    with torch.no_grad():
+        m.output.output.weight *= 8
+    vocab = dict(PAD=0, UNK=125, START=126, END=127)
+    ref_c = O.caption(Wd, ann, vocab, beamk=3, max_gen_length=8, rescore_method="LN", deep=False)
+    got = m.caption(ann.cuda(), beamk=3, max_gen_length=8, rescore_method="LN")
+    assert got[0] == ref_c[0]
+    assert max(abs(x - y) for x, y in zip(got[1], ref_c[1])) < 1e-4
+
+
+def test_caption_api_returns_reference_format():
+    m = build(seed=7)
+    ann, _, _ = batch(9, ncap=1)
+    caps, scores, alphas, ppl = m.caption(ann.cuda(), beamk=2, max_gen_length=5, return_all=True)
+    assert not m.training                                        # caption() leaves the module in eval() (model.py:231)
+    assert len(caps) == ann.shape[0] and all(isinstance(c, list) and isinstance(c[0], list) for c in caps)
+    assert all(a[0].device.type == "cpu" and a[0].shape[1:] == (4, 3) for a in alphas)
+    assert all(len(c[0]) == a[0].shape[0] for c, a in zip(caps, alphas))
+    assert all(s == sorted(s, reverse=True) for s in scores)
