@@ -152,6 +152,13 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   }
 
   // ===== consumers (256 threads, named barrier 1) =====
+  // beta_pre of the columns this thread finalises is fetched now, long before it is needed
+  float bpre[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int d = tid + i * ATTP_CONSUMERS;
+    bpre[i] = d < D ? hp_b[A + d] : 0.0f;
+  }
   // lane-resident slices of q and w_f: lane owns attention columns lane*4 + 128*k .. +3  (A <= 128 * ATTP_KA)
   float qreg[ATTP_KA][4], wreg[ATTP_KA][4];
 #pragma unroll
@@ -169,21 +176,34 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
     const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
     const int r0 = i * RCP, rows = min(RCP, L - r0);
-    for (int l = warp; l < rows; l += ATTP_CWARPS) {
-      float s = 0.0f;
+    for (int l0 = warp * 4; l0 < rows; l0 += ATTP_CWARPS * 4) {     // 4 rows in flight per warp: independent chains
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int k = 0; k < ATTP_KA; ++k) {
         const int a = lane * 4 + 128 * k;
         if (a < A) {
-          const float4 p = ld4(Ps + (size_t)l * A + a);
-          s = fmaf(wreg[k][0], sat_tanh<kExact>(p.x + qreg[k][0]), s);
-          s = fmaf(wreg[k][1], sat_tanh<kExact>(p.y + qreg[k][1]), s);
-          s = fmaf(wreg[k][2], sat_tanh<kExact>(p.z + qreg[k][2]), s);
-          s = fmaf(wreg[k][3], sat_tanh<kExact>(p.w + qreg[k][3]), s);
+          float4 p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            p[u] = (l0 + u) < rows ? ld4(Ps + (size_t)(l0 + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            s4[u] = fmaf(wreg[k][0], sat_tanh<kExact>(p[u].x + qreg[k][0]), s4[u]);
+            s4[u] = fmaf(wreg[k][1], sat_tanh<kExact>(p[u].y + qreg[k][1]), s4[u]);
+            s4[u] = fmaf(wreg[k][2], sat_tanh<kExact>(p[u].z + qreg[k][2]), s4[u]);
+            s4[u] = fmaf(wreg[k][3], sat_tanh<kExact>(p[u].w + qreg[k][3]), s4[u]);
+          }
         }
       }
-      s = warp_sum(s);
-      if (lane == 0) e[r0 + l] = s * scale;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s4[u] += __shfl_xor_sync(0xffffffffu, s4[u], o);
+      }
+      if (lane < 4 && (l0 + lane) < rows) {
+        const float sv = lane == 0 ? s4[0] : (lane == 1 ? s4[1] : (lane == 2 ? s4[2] : s4[3]));
+        e[r0 + l0 + lane] = sv * scale;
+      }
     }
     __syncwarp();
     if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
@@ -263,7 +283,19 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     for (int i = 0; i < VN; ++i) red[rg * D + cv0 * VN + i] = acc[i];
   }
   sat_named_bar(1, ATTP_CONSUMERS);
-  for (int d = tid; d < D; d += ATTP_CONSUMERS) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int d = tid + i * ATTP_CONSUMERS;
+    if (d < D) {
+      float zs = 0.0f;
+      for (int r = 0; r < RG; ++r) zs += red[r * D + d];
+      const float bt = sat_sigmoid<kExact>(bpre[i]);
+      z[(int64_t)b * ld_z + d] = from_f<T>(zs);
+      gz[(int64_t)b * ld_z + d] = from_f<T>(bt * zs);
+      if (beta) beta[(int64_t)b * ld_z + d] = from_f<T>(bt);
+    }
+  }
+  for (int d = tid + 8 * ATTP_CONSUMERS; d < D; d += ATTP_CONSUMERS) {     // D > 8 * consumers: plain path
     float zs = 0.0f;
     for (int r = 0; r < RG; ++r) zs += red[r * D + d];
     const float bt = sat_sigmoid<kExact>(hp_b[A + d]);
@@ -272,7 +304,6 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     if (beta) beta[(int64_t)b * ld_z + d] = from_f<T>(bt);
   }
 }
-
 
 static inline size_t attention_fwd_pipe_smem(int L, int D, int A, int vn) {
   constexpr int ATTP_CONSUMERS = ATTP_FWD_CW * 32;
