@@ -8,6 +8,9 @@
 //   annotation stages (16-byte shared-memory loads), beta gate, stores.
 //   Every byte of P / annotations is read from global memory exactly once per step; 2 CTAs per SM keep
 //   ~190 KB of loads in flight per SM, which is what an HBM-bound kernel needs on B200.
+//   Tried and dropped (measured slower on B200): an 8-CTA cluster/DSMEM split of each caption, a
+//   context phase on mma.sync + ldmatrix (also with a pre-swizzled annotation copy), one CTA per image for beam
+//   groups, 16 consumer warps, and single-lane mbarrier polling.
 #pragma once
 #include <stdlib.h>
 

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--iters", type=int, default=12)
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--no-tc", action="store_true")
@@ -32,6 +32,7 @@ caps[:, 0] = V - 2
 lens = torch.full((B,), T, device="cuda")
 use_tc = (not args.fp32) and (not args.no_tc)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+times = []
 if args.decode:
     dw = decode.DecodeWeights(W, dtype, torch.device("cuda"), args.fp32, use_tc)
     vocab = dict(PAD=0, UNK=V - 3, START=V - 2, END=V - 1)
@@ -40,7 +41,9 @@ if args.decode:
         t = decode.decode_annotations(dw, ann, args.decode, 30, 1.0, None, 0.5, vocab)
         ev1.record()
         torch.cuda.synchronize()
-        print("decode k=%d B=%d: %.3f ms" % (args.decode, B, ev0.elapsed_time(ev1)))
+        times.append(ev0.elapsed_time(ev1))
+    times = sorted(times[2:] or times)
+    print("decode k=%d B=%d: median %.3f ms (min %.3f) over %d iters" % (args.decode, B, times[len(times) // 2], times[0], len(times)))
 else:
     pw = PackedWeights(W, dtype=dtype, device="cuda", backward=True)
     for it in range(args.iters):
@@ -49,4 +52,6 @@ else:
         G, d_ann = decoder.train_backward(pw, buf)
         ev1.record()
         torch.cuda.synchronize()
-        print("train fwd+bwd B=%d: %.3f ms  loss %.4f" % (B, ev0.elapsed_time(ev1), float(buf.t["out"][0])))
+        times.append(ev0.elapsed_time(ev1))
+    times = sorted(times[2:] or times)
+    print("train fwd+bwd B=%d: median %.3f ms (min %.3f) over %d iters  loss %.4f" % (B, times[len(times) // 2], times[0], len(times), float(buf.t["out"][0])))
