@@ -29,12 +29,15 @@ __global__ void init_state_decode_kernel(const float* __restrict__ init_out, T* 
 // scores = log_softmax(logit / temp) (model.py:330); <START>,<PAD> -> -inf (model.py:333); step 0 also
 // <END>,<UNK> (model.py:340); + parent score (model.py:351).  Emits the row's best `kk` candidates in
 // descending order (ties: lower vocabulary index first).
+// log-softmax and "+ parent score" are monotone per row, so the candidates are selected on the scaled logits
+// x = logit / temp (one pass from global memory fused with the running max / argmax, one pass over shared memory
+// for the sum of exponentials) and only the winners are converted: score = (x - max) - log(sum exp(x - max)) + parent.
 __global__ void __launch_bounds__(256)
 row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur,
                 int k, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
                 float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
   extern __shared__ __align__(16) float smem[];
-  float* x = smem;            // [V]
+  float* x = smem;            // [V]  scaled logits, masked entries set to -inf after the softmax statistics
   float* scratch = x + V;     // [33]
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
@@ -43,25 +46,27 @@ row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_
   if (j >= kc) return;
   if (step == 0 && j != 0) return;                    // step 0 looks at beam 0 only (model.py:343)
   const float* row = logits + (int64_t)r * V;
+  const bool s0 = step == 0;
+  // pass 1 (global -> shared): x = logit / temp, row max over ALL entries (softmax statistics ignore the masks)
   float mx = -INFINITY;
-  for (int v = tid; v < V; v += 256) {
-    const float xv = row[v] / temp;
-    x[v] = xv;
-    mx = fmaxf(mx, xv);
+  for (int v = tid * 4; v < V; v += 256 * 4) {
+    float4 q = *reinterpret_cast<const float4*>(row + v);
+    q.x = q.x / temp; q.y = q.y / temp; q.z = q.z / temp; q.w = q.w / temp;
+    *reinterpret_cast<float4*>(x + v) = q;
+    mx = fmaxf(fmaxf(mx, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
   }
   mx = block_max(mx, scratch);
+  // pass 2 (shared): sum of exponentials; masked tokens are then removed from the candidate set
   float se = 0.0f;
-  for (int v = tid; v < V; v += 256) se += expf(x[v] - mx);
+  for (int v = tid; v < V; v += 256) {
+    const float xv = x[v];
+    se += expf(xv - mx);
+    if (v == tokSTART || v == tokPAD || (s0 && (v == tokEND || v == tokUNK))) x[v] = -INFINITY;
+  }
   se = block_sum(se, scratch);
   const float lse = logf(se);
-  const float base = step == 0 ? 0.0f : top_scores[r];
-  for (int v = tid; v < V; v += 256) {
-    float lp = (x[v] - mx) - lse;
-    if (v == tokSTART || v == tokPAD || (step == 0 && (v == tokEND || v == tokUNK))) lp = -INFINITY;
-    x[v] = step == 0 ? lp : lp + base;
-  }
-  __syncthreads();
-  const int kk = step == 0 ? k : kc;
+  const float base = s0 ? 0.0f : top_scores[r];
+  const int kk = s0 ? k : kc;
   float pv = INFINITY;
   int pi = -1;
   for (int i = 0; i < kk; ++i) {
@@ -83,7 +88,11 @@ row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_
     bv = s_val[0]; bi = s_idx[0];
     for (int w = 1; w < 8; ++w)
       if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
-    if (tid == 0) { cand_val[(int64_t)r * k + i] = bv; cand_idx[(int64_t)r * k + i] = bi; }
+    if (tid == 0) {
+      const float lp = (bv - mx) - lse;                            // -inf stays -inf
+      cand_val[(int64_t)r * k + i] = s0 ? lp : lp + base;
+      cand_idx[(int64_t)r * k + i] = bi;
+    }
     pv = bv; pi = bi;
   }
 }

@@ -299,8 +299,13 @@ static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, i
 template <typename Epi>
 static int launch(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream,
                   int splitk = 1) {
-  const long tiles128 = (long)((N + 127) / 128) * ((M + BM - 1) / BM);
+  const long mt = (M + BM - 1) / BM;
+  const long tiles128 = (long)((N + 127) / 128) * mt;
   if (tiles128 >= 148 && N >= 128 && splitk == 1) return launch_bn<128, Epi>(A, W, ldw, M, N, epi, stream);
+  // skinny GEMMs (the per-step M = B projections): narrower N tiles put more CTAs to work and halve the serial
+  // epilogue work per thread (the fused LSTM / store epilogues are latency-bound, not throughput-bound)
+  const long tiles64 = (long)((N + 63) / 64) * mt * splitk;
+  if (tiles64 < 120 && N >= 64) return launch_bn<32, Epi>(A, W, ldw, M, N, epi, stream, splitk);
   return launch_bn<64, Epi>(A, W, ldw, M, N, epi, stream, splitk);
 }
 
