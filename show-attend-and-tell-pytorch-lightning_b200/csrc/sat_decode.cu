@@ -22,7 +22,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, n_img * L, A,
                            EpiStore<TS>{(TS*)b.P, A, nullptr, nullptr, 0}, st)));
   const int NV = D / Vec16<TS>::N;
-  mean_L_kernel<TS><<<dim3((NV + 127) / 128, n_img), 128, 0, st>>>(ann, (TS*)b.meanv, L, D);
+  mean_L_kernel<TS><<<dim3((NV + 31) / 32, n_img), 256, 0, st>>>(ann, (TS*)b.meanv, L, D);
   SAT_COUNT_LAUNCH();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.meanv, D, D), (const TS*)w.Wfact, D, n_img, E,
                            EpiStore<TS>{(TS*)b.f1, E, w.bfact, nullptr, 0}, st)));

@@ -180,26 +180,40 @@ static inline size_t attention_fwd_smem(int L, int D, int A, int vn) {
 // mean over locations: meanv[i,d] = (1/L) sum_l ann[i,l,d]                        model.py:78
 // =============================================================================================
 template <typename T>
-__global__ void mean_L_kernel(const T* __restrict__ ann, T* __restrict__ meanv, int L, int D) {
+__global__ void __launch_bounds__(256) mean_L_kernel(const T* __restrict__ ann, T* __restrict__ meanv, int L, int D) {
+  // CTA = (32 column vectors) x (8 row groups); partial sums of the row groups are combined through shared memory
   constexpr int VN = Vec16<T>::N;
+  __shared__ float part[8][32][VN + 1];
   const int NV = D / VN;
-  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int cv = blockIdx.x * 32 + cl;
   const int i = blockIdx.y;
-  if (cv >= NV) return;
-  const T* a = ann + (int64_t)i * L * D + cv * VN;
   float acc[VN];
 #pragma unroll
   for (int k = 0; k < VN; ++k) acc[k] = 0.0f;
-  for (int l = 0; l < L; ++l) {
-    float v[VN];
-    Vec16<T>::load(a + (int64_t)l * D, v);
+  if (cv < NV) {
+    const T* a = ann + (int64_t)i * L * D + cv * VN;
+    for (int l = rg; l < L; l += 8) {
+      float v[VN];
+      Vec16<T>::load(a + (int64_t)l * D, v);
 #pragma unroll
-    for (int k = 0; k < VN; ++k) acc[k] += v[k];
+      for (int k = 0; k < VN; ++k) acc[k] += v[k];
+    }
   }
-  const float inv = 1.0f / (float)L;
 #pragma unroll
-  for (int k = 0; k < VN; ++k) acc[k] *= inv;
-  Vec16<T>::store(meanv + (int64_t)i * D + cv * VN, acc);
+  for (int k = 0; k < VN; ++k) part[rg][cl][k] = acc[k];
+  __syncthreads();
+  if (rg == 0 && cv < NV) {
+    const float inv = 1.0f / (float)L;
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sum += part[r][cl][k];
+      acc[k] = sum * inv;
+    }
+    Vec16<T>::store(meanv + (int64_t)i * D + cv * VN, acc);
+  }
 }
 
 // =============================================================================================
@@ -635,13 +649,20 @@ dann_alpha_kernel(const float* __restrict__ alphas, const T* __restrict__ dZ, co
   const int cq = (tid & 127) * 4, lg = tid >> 7;
   if (cq >= dc) return;
   const float4 dm = ld4(dmean + (int64_t)(b / ncap) * D + d0 + cq);
-  for (int l = lg; l < L; l += 2) {
-    float4 acc = make_float4(dm.x * mean_scale, dm.y * mean_scale, dm.z * mean_scale, dm.w * mean_scale);
+  const float4 m4 = make_float4(dm.x * mean_scale, dm.y * mean_scale, dm.z * mean_scale, dm.w * mean_scale);
+  for (int l0 = lg * 4; l0 < L; l0 += 8) {           // 4 consecutive rows per thread share every dz vector load
+    float4 acc[4] = {m4, m4, m4, m4};
     for (int t = 0; t < T_; ++t) {
-      const float a = als[t * L + l];
       const float4 z = *reinterpret_cast<const float4*>(dzs + (size_t)t * DANN_DC + cq);
-      acc.x = fmaf(a, z.x, acc.x); acc.y = fmaf(a, z.y, acc.y); acc.z = fmaf(a, z.z, acc.z); acc.w = fmaf(a, z.w, acc.w);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float a = (l0 + u) < L ? als[t * L + l0 + u] : 0.0f;
+        acc[u].x = fmaf(a, z.x, acc[u].x); acc[u].y = fmaf(a, z.y, acc[u].y);
+        acc[u].z = fmaf(a, z.z, acc[u].z); acc[u].w = fmaf(a, z.w, acc[u].w);
+      }
     }
-    *reinterpret_cast<float4*>(tmp + ((int64_t)b * L + l) * D + d0 + cq) = acc;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if ((l0 + u) < L) *reinterpret_cast<float4*>(tmp + ((int64_t)b * L + l0 + u) * D + d0 + cq) = acc[u];
   }
 }

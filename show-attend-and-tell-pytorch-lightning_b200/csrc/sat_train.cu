@@ -26,7 +26,7 @@ static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void
                            st)));
   // mean over locations, then the two Linear layers of InitLSTM (no nonlinearity between, model.py:79)
   const int NV = D / Vec16<TS>::N;
-  mean_L_kernel<TS><<<dim3((NV + 127) / 128, Bi), 128, 0, st>>>((const TS*)ann, (TS*)meanv, L, D);
+  mean_L_kernel<TS><<<dim3((NV + 31) / 32, Bi), 256, 0, st>>>((const TS*)ann, (TS*)meanv, L, D);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(meanv, D, D), (const TS*)w.Wfact, D, Bi, E,
