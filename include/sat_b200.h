@@ -135,6 +135,9 @@ typedef struct SatTrainBuffers {
   /* scalars */
   float label_smoothing;
   float att_gamma;
+  float dropout_p;       /* nn.Dropout p of InitLSTM (model.py:74,78) and DeepOutput (model.py:117,130); 0 in eval mode */
+  float emb_dropout_p;   /* embedding_dropout p (model.py:164,526)                                                     */
+  uint64_t dropout_seed; /* masks are a pure function of (seed, stream, element index); draw a new seed every step      */
   int32_t logits_f32;    /* logits buffer is fp32 (API path: train_batch returns fp32 logits, model.py:504) */
   int32_t reserved;
 } SatTrainBuffers;
@@ -215,6 +218,10 @@ int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, con
 
 /* Whole teacher-forced forward + loss: SAT.train_batch (model.py:474-557) with epsilon = 1,
  * LabelSmoothing (util.py:105-112), doubly-stochastic term and accuracy (model.py:592-597). */
+/* The dropout multiplier (0 or 1/(1-p)) the kernels apply to element `idx` of stream 1 (InitLSTM mean, idx = img*D+d),
+ * 2 (embedded words, idx = (t*B+b)*E+e) or 3 (deep-output activations, idx = (t*B+b)*E+e).  Host-side mirror for tests. */
+float sat_dropout_multiplier(float p, uint64_t seed, uint32_t stream, uint64_t idx);
+
 int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
 
 /* Hand-written BPTT of sat_train_forward (what autograd derives from model.py:510-548): fills

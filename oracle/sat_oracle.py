@@ -72,32 +72,36 @@ def lstm_cell(W, x, h, c):
     return h2, c2
 
 
-def deep_output(W, x_e, h, z, deep=True):
-    """model.py:125-131 (dropout p=0)."""
+def deep_output(W, x_e, h, z, deep=True, drop=None):
+    """model.py:125-131; `drop` = explicit dropout multipliers (0 or 1/(1-p)) for the activations before the output layer."""
     if deep:
         x = torch.tanh(x_e + h @ W["output.hidden.weight"].t() + z @ W["output.context.weight"].t())
     else:
         x = h @ W["output.hidden.weight"].t()
+    if drop is not None:
+        x = x * drop
     logit = x @ W["output.output.weight"].t()
     if W.get("output.output.bias", None) is not None:
         logit = logit + W["output.output.bias"]
     return logit
 
 
-def decoder_step(W, ann, words, h, c, deep=True):
+def decoder_step(W, ann, words, h, c, deep=True, emb_drop=None, out_drop=None):
     """One pass of the per-timestep hot path: model.py:298-327 (decode) == 526-547 (train)."""
     x_e = W["embedding.weight"][words]
+    if emb_drop is not None:
+        x_e = x_e * emb_drop                      # embedding_dropout (model.py:526)
     z, alpha = attention(W, ann, h)
     beta = beta_gate(W, h)
     h2, c2 = lstm_cell(W, torch.cat([x_e, beta * z], dim=1), h, c)
-    logit = deep_output(W, x_e, h2, z, deep)      # ungated z, new h
+    logit = deep_output(W, x_e, h2, z, deep, out_drop)      # ungated z, new h
     return logit, alpha, h2, c2
 
 
 # --------------------------------------------------------------------------------------
 # teacher-forced forward (model.py:474-557) + loss (model.py:592-597, util.py:105-112)
 # --------------------------------------------------------------------------------------
-def train_batch(W, ann_img, encoded_captions, lengths, epsilon=1.0, deep=True, rand=None):
+def train_batch(W, ann_img, encoded_captions, lengths, epsilon=1.0, deep=True, rand=None, masks=None):
     """ann_img [B_img,D,h,w]; encoded_captions [B_img,ncap,T+1] int64; lengths [B_img,ncap].
 
     Returns padded logits [B,T,V], alphas [B,T,L], flat captions [B,T+1], flat lengths [B].
@@ -113,7 +117,16 @@ def train_batch(W, ann_img, encoded_captions, lengths, epsilon=1.0, deep=True, r
     T = caplen - 1
     L = ann.shape[2] * ann.shape[3]
     V = W["embedding.weight"].shape[0]
-    h, c = init_lstm(W, ann)
+    # masks: optional explicit dropout multipliers dict(mean [B,D], emb [B,T,E], out [B,T,E]) so that the train-mode
+    # path (model.py:78,526,130) can be checked with the masks the CUDA kernels generate
+    if masks is not None and masks.get("mean") is not None:
+        mean = ann.mean((2, 3)) * masks["mean"]
+        f1 = mean @ W["init_lstm.factorize.weight"].t() + W["init_lstm.factorize.bias"]
+        out0 = f1 @ W["init_lstm.init.weight"].t() + W["init_lstm.init.bias"]
+        st0 = out0.reshape(2, mean.shape[0], out0.shape[1] // 2)
+        h, c = st0[0], st0[1]
+    else:
+        h, c = init_lstm(W, ann)
     h, c = h.clone(), c.clone()
     dt = ann.dtype
     logits = torch.zeros(B, T, V, dtype=dt)
@@ -131,7 +144,9 @@ def train_batch(W, ann_img, encoded_captions, lengths, epsilon=1.0, deep=True, r
             words = caps[idx, step]
         else:
             words = torch.argmax(logits[idx, step - 1, :], dim=1)   # model.py:523 (no grad path)
-        logit, alpha, h2, c2 = decoder_step(W, ann[idx], words, h[idx], c[idx], deep)
+        ed = masks["emb"][idx, step] if masks is not None and masks.get("emb") is not None else None
+        od = masks["out"][idx, step] if masks is not None and masks.get("out") is not None else None
+        logit, alpha, h2, c2 = decoder_step(W, ann[idx], words, h[idx], c[idx], deep, ed, od)
         alphas = alphas.index_put((idx, torch.tensor(step)), alpha)
         logits = logits.index_put((idx, torch.tensor(step)), logit)
         h = h.index_put((idx,), h2)
@@ -155,9 +170,9 @@ def label_smoothing_loss(x, target, smoothing=0.0):
 
 
 def train_loss(W, ann_img, encoded_captions, lengths, label_smoothing=0.0, att_gamma=1.0,
-               epsilon=1.0, deep=True, rand=None):
+               epsilon=1.0, deep=True, rand=None, masks=None):
     """model.py:588-597: returns dict(loss, acc, ce, reg, logits, alphas)."""
-    logits, alphas, caps, lens = train_batch(W, ann_img, encoded_captions, lengths, epsilon, deep, rand)
+    logits, alphas, caps, lens = train_batch(W, ann_img, encoded_captions, lengths, epsilon, deep, rand, masks)
     lp, tp = pack(logits, caps, lens)
     ce = label_smoothing_loss(lp.data, tp.data, label_smoothing)
     reg = ((1 - alphas.sum(dim=1)) ** 2).mean()                     # model.py:594

@@ -30,7 +30,8 @@ class SatTrainBuffers(C.Structure):
                  "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
                  "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dann_tmp", "dwf_part", "dXe", "d_init_out",
                  "df1", "dmean", "d_ann")] + \
-               [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("logits_f32", C.c_int32),
+               [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("dropout_p", C.c_float),
+                ("emb_dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("logits_f32", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -43,7 +44,7 @@ class SatDecodeBuffers(C.Structure):
                 ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32)]
 
 
-EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end",
+EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end", "sat_dropout_multiplier",
            "sat_linear", "sat_prepare_images",
            "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward", "sat_decode_prepare_weights", "sat_decode"]
 
@@ -79,6 +80,8 @@ def lib():
     for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers, SatDecodeBuffers)):
         if L.sat_abi_sizeof(i) != C.sizeof(st):
             raise SatError("ABI mismatch for %s: lib %d vs ctypes %d" % (st.__name__, L.sat_abi_sizeof(i), C.sizeof(st)))
+    L.sat_dropout_multiplier.argtypes = [C.c_float, C.c_uint64, C.c_uint32, C.c_uint64]
+    L.sat_dropout_multiplier.restype = C.c_float
     L.sat_profile_begin.argtypes = [C.c_int]
     L.sat_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.sat_linear.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

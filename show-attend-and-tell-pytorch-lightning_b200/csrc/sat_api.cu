@@ -54,6 +54,8 @@ int sat_profile_end(float* total_ms, int* count) {
 
 int sat_version(void) { return SAT_ABI_VERSION; }
 
+float sat_dropout_multiplier(float p, uint64_t seed, uint32_t stream, uint64_t idx) { return sat_dropout_scale(p, seed, stream, idx); }
+
 const char* sat_last_error(void) { return g_err; }
 
 unsigned long long sat_launch_count(void) { return g_sat_launches; }

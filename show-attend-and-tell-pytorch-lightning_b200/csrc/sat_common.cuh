@@ -136,6 +136,23 @@ template <bool kExact> __device__ __forceinline__ float sat_sigmoid(float x) {
   return __fdividef(1.0f, 1.0f + __expf(-x));
 }
 
+// ---- dropout: stateless counter-based masks ------------------------------------------------------
+// keep(seed, stream, idx) is a pure function, so the backward pass regenerates the forward masks instead of storing them.
+// streams: 1 = InitLSTM mean (model.py:78), 2 = embedding_dropout (model.py:526), 3 = DeepOutput dropout (model.py:130)
+__host__ __device__ __forceinline__ uint32_t sat_hash32(uint64_t seed, uint32_t stream, uint64_t idx) {
+  uint64_t x = idx * 0x9E3779B97F4A7C15ull + seed + ((uint64_t)stream << 56);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+// multiplier of an element under inverted dropout with drop probability p: 0 or 1/(1-p)
+__host__ __device__ __forceinline__ float sat_dropout_scale(float p, uint64_t seed, uint32_t stream, uint64_t idx) {
+  if (p <= 0.0f) return 1.0f;
+  const float u = (float)(sat_hash32(seed, stream, idx) >> 8) * (1.0f / 16777216.0f);
+  return u < p ? 0.0f : 1.0f / (1.0f - p);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

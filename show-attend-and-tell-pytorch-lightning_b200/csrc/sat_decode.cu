@@ -22,7 +22,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, n_img * L, A,
                            EpiStore<TS>{(TS*)b.P, A, nullptr, nullptr, 0}, st)));
   const int NV = D / Vec16<TS>::N;
-  mean_L_kernel<TS><<<dim3((NV + 31) / 32, n_img), 256, 0, st>>>(ann, (TS*)b.meanv, L, D);
+  mean_L_kernel<TS><<<dim3((NV + 31) / 32, n_img), 256, 0, st>>>(ann, (TS*)b.meanv, L, D, 0.0f, 0ull);
   SAT_COUNT_LAUNCH();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.meanv, D, D), (const TS*)w.Wfact, D, n_img, E,
                            EpiStore<TS>{(TS*)b.f1, E, w.bfact, nullptr, 0}, st)));
@@ -54,7 +54,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
                             (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.gz, D, D), (const TS*)w.Wihz, D, R, 4 * H, epi, st)));
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(b.hn, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
-                             EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok, d.plain_output}, st)));
+                             EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok, d.plain_output, 0.0f, 0ull, 0}, st)));
     SAT_PROF(3, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
     SAT_PROF(3, st);

@@ -247,6 +247,7 @@ struct EpiTanhAdd {
   const TS* Xe; TS* Xo; int64_t ld;
   const int32_t* xe_row;               // optional: Xe row index per m (decode: token id into the embedding table)
   int plain;                           // DeepOutput(deep=False): Xo = acc (model.py:129)
+  float drop_p; uint64_t seed; int64_t m_base;   // dropout on the activations before the vocabulary layer (model.py:130)
   struct Ctx { float4 x; };
   __device__ __forceinline__ Ctx load(int m, int n) const {
     Ctx c;
@@ -256,13 +257,17 @@ struct EpiTanhAdd {
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
   __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
     const float4 x = c.x;
-    if (plain) {
-      st4(Xo + (int64_t)m * ld + n, make_float4(acc[0], acc[1], acc[2], acc[3]));
-      return;
+    float4 o;
+    if (plain) o = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else
+      o = make_float4(sat_tanh<kExact>(acc[0] + x.x), sat_tanh<kExact>(acc[1] + x.y), sat_tanh<kExact>(acc[2] + x.z),
+                      sat_tanh<kExact>(acc[3] + x.w));
+    if (drop_p > 0.0f) {
+      const uint64_t i0 = (uint64_t)(m_base + m) * ld + n;
+      o.x *= sat_dropout_scale(drop_p, seed, 3u, i0);     o.y *= sat_dropout_scale(drop_p, seed, 3u, i0 + 1);
+      o.z *= sat_dropout_scale(drop_p, seed, 3u, i0 + 2); o.w *= sat_dropout_scale(drop_p, seed, 3u, i0 + 3);
     }
-    st4(Xo + (int64_t)m * ld + n,
-        make_float4(sat_tanh<kExact>(acc[0] + x.x), sat_tanh<kExact>(acc[1] + x.y), sat_tanh<kExact>(acc[2] + x.z),
-                    sat_tanh<kExact>(acc[3] + x.w)));
+    st4(Xo + (int64_t)m * ld + n, o);
   }
 };
 
@@ -271,6 +276,7 @@ template <typename TS>
 struct EpiDpre {
   const TS* Xo; TS* dpre; int64_t ld; const float* gscale;
   int plain;                           // DeepOutput(deep=False): no tanh derivative
+  float drop_p; uint64_t seed;         // Xo holds the DROPPED activations: x = Xo * (1-p) where kept; grad gets the mask
   struct Ctx { float4 x; float g; };
   __device__ __forceinline__ Ctx load(int m, int n) const {
     Ctx c;
@@ -281,8 +287,16 @@ struct EpiDpre {
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
   __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx& c) const {
     const float g = c.g;
-    const float4 x = plain ? make_float4(0.f, 0.f, 0.f, 0.f) : c.x;
-    st4(dpre + (int64_t)m * ld + n, make_float4(g * acc[0] * (1.f - x.x * x.x), g * acc[1] * (1.f - x.y * x.y),
-                                                 g * acc[2] * (1.f - x.z * x.z), g * acc[3] * (1.f - x.w * x.w)));
+    float4 x = plain ? make_float4(0.f, 0.f, 0.f, 0.f) : c.x;
+    float4 k4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (drop_p > 0.0f) {
+      const uint64_t i0 = (uint64_t)m * ld + n;
+      k4 = make_float4(sat_dropout_scale(drop_p, seed, 3u, i0), sat_dropout_scale(drop_p, seed, 3u, i0 + 1),
+                       sat_dropout_scale(drop_p, seed, 3u, i0 + 2), sat_dropout_scale(drop_p, seed, 3u, i0 + 3));
+      const float keep = 1.0f - drop_p;
+      x.x *= keep; x.y *= keep; x.z *= keep; x.w *= keep;      // undo the forward scaling where kept (irrelevant where dropped)
+    }
+    st4(dpre + (int64_t)m * ld + n, make_float4(g * k4.x * acc[0] * (1.f - x.x * x.x), g * k4.y * acc[1] * (1.f - x.y * x.y),
+                                                 g * k4.z * acc[2] * (1.f - x.z * x.z), g * k4.w * acc[3] * (1.f - x.w * x.w)));
   }
 };

@@ -180,7 +180,8 @@ static inline size_t attention_fwd_smem(int L, int D, int A, int vn) {
 // mean over locations: meanv[i,d] = (1/L) sum_l ann[i,l,d]                        model.py:78
 // =============================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) mean_L_kernel(const T* __restrict__ ann, T* __restrict__ meanv, int L, int D) {
+__global__ void __launch_bounds__(256) mean_L_kernel(const T* __restrict__ ann, T* __restrict__ meanv, int L, int D, float drop_p,
+                                                      uint64_t seed) {
   // CTA = (32 column vectors) x (8 row groups); partial sums of the row groups are combined through shared memory
   constexpr int VN = Vec16<T>::N;
   __shared__ float part[8][32][VN + 1];
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) mean_L_kernel(const T* __restrict__ ann, 
       float sum = 0.0f;
 #pragma unroll
       for (int r = 0; r < 8; ++r) sum += part[r][cl][k];
-      acc[k] = sum * inv;
+      acc[k] = sum * inv * sat_dropout_scale(drop_p, seed, 1u, (uint64_t)i * D + cv * VN + k);    // model.py:78
     }
     Vec16<T>::store(meanv + (int64_t)i * D + cv * VN, acc);
   }
@@ -278,14 +279,29 @@ static __global__ void tok_init_kernel(const int32_t* __restrict__ caps, int32_t
 // embedding gather over `rows` time-major rows:  Xe[m,:] = Emb[tok[m],:]                 model.py:526
 // =============================================================================================
 template <typename T>
-__global__ void embed_gather_kernel(const T* __restrict__ Emb, const int32_t* __restrict__ tok, T* __restrict__ Xe, int E) {
-  const int m = blockIdx.x;
+__global__ void embed_gather_kernel(const T* __restrict__ Emb, const int32_t* __restrict__ tok, T* __restrict__ Xe, int E,
+                                    int64_t m_base, float drop_p, uint64_t seed) {
+  const int m = blockIdx.x;            // row of this launch; m_base + m is the global time-major row (dropout index)
   const int w = tok[m];
   constexpr int VN = Vec16<T>::N;
   for (int c = threadIdx.x; c < E / VN; c += blockDim.x) {
-    const uint4 v = *reinterpret_cast<const uint4*>(Emb + (int64_t)w * E + c * VN);
-    *reinterpret_cast<uint4*>(Xe + (int64_t)m * E + c * VN) = v;
+    if (drop_p <= 0.0f) {
+      const uint4 v = *reinterpret_cast<const uint4*>(Emb + (int64_t)w * E + c * VN);
+      *reinterpret_cast<uint4*>(Xe + (int64_t)m * E + c * VN) = v;
+    } else {                          // embedding_dropout (model.py:526)
+      float v[VN];
+      Vec16<T>::load(Emb + (int64_t)w * E + c * VN, v);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) v[k] *= sat_dropout_scale(drop_p, seed, 2u, (uint64_t)(m_base + m) * E + c * VN + k);
+      Vec16<T>::store(Xe + (int64_t)m * E + c * VN, v);
+    }
   }
+}
+
+// x[i] *= dropout multiplier of (stream, i): backward of the InitLSTM-mean and embedding dropouts
+static __global__ void dropout_bwd_kernel(float* __restrict__ x, int64_t n, float drop_p, uint64_t seed, uint32_t stream) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= sat_dropout_scale(drop_p, seed, stream, (uint64_t)i);
 }
 
 // =============================================================================================

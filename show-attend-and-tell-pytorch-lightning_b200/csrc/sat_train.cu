@@ -18,7 +18,7 @@ namespace {
 
 template <typename TS>
 static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void* ann, void* P, void* meanv, void* f1,
-                               float* init_out, void* h0, float* c0, cudaStream_t st) {
+                               float* init_out, void* h0, float* c0, cudaStream_t st, float drop_p = 0.0f, uint64_t seed = 0) {
   const int B = d.B, Bi = d.Bi, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H;
   const bool tc = d.use_tc != 0;
   // P = ann * Wa^T  ([Bi*L, D] x [A, D]^T)
@@ -26,7 +26,7 @@ static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void
                            st)));
   // mean over locations, then the two Linear layers of InitLSTM (no nonlinearity between, model.py:79)
   const int NV = D / Vec16<TS>::N;
-  mean_L_kernel<TS><<<dim3((NV + 31) / 32, Bi), 256, 0, st>>>((const TS*)ann, (TS*)meanv, L, D);
+  mean_L_kernel<TS><<<dim3((NV + 31) / 32, Bi), 256, 0, st>>>((const TS*)ann, (TS*)meanv, L, D, drop_p, seed);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(meanv, D, D), (const TS*)w.Wfact, D, Bi, E,
@@ -49,12 +49,12 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   const TS* ann = (const TS*)b.ann;
 
   // ---- once per image ------------------------------------------------------------------------
-  SAT_TRY(sat_prepare_images(&d, &w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st));
+  SAT_TRY((prepare_images_impl<TS>(d, w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st, b.dropout_p, b.dropout_seed)));
 
   // ---- hoisted: embeddings of the (teacher-forced) previous words and their gate projection ---
   tok_init_kernel<<<(T * B + 255) / 256, 256, 0, st>>>(b.caps, b.tok, B, T, caplen);
   SAT_COUNT_LAUNCH();
-  embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.tok, (TS*)b.Xe, E);
+  embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.tok, (TS*)b.Xe, E, 0, b.emb_dropout_p, b.dropout_seed);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xe, E, E), (const TS*)w.Wihe, E, T * B, 4 * H,
@@ -68,7 +68,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
       // step t-1 now (the hoisted whole-sequence GEMMs below recompute the same values), then re-embed and re-project.
       const int64_t o1 = (int64_t)(t - 1) * B;
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)b.Hs + (int64_t)t * B * H, H, H, (const TS*)b.Z + o1 * D, D, D), (const TS*)w.Whozo,
-                               H + D, B, E, EpiTanhAdd<TS, kExact>{(const TS*)b.Xe + o1 * E, (TS*)b.Xo + o1 * E, E, nullptr, d.plain_output}, st)));
+                               H + D, B, E, EpiTanhAdd<TS, kExact>{(const TS*)b.Xe + o1 * E, (TS*)b.Xo + o1 * E, E, nullptr, d.plain_output, b.dropout_p, b.dropout_seed, o1}, st)));
       if (b.logits_f32) {
         SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xo + o1 * E, E, E), (const TS*)w.Wo, E, B, V,
                                  EpiStore<float>{(float*)b.logits + o1 * V, V, w.bo, nullptr, 0}, st)));
@@ -79,7 +79,8 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
         row_argmax_kernel<TS><<<B, 256, 0, st>>>((const TS*)b.logits + o1 * V, b.tok + (int64_t)t * B, V);
       }
       SAT_COUNT_LAUNCH();
-      embed_gather_kernel<TS><<<B, 64, 0, st>>>((const TS*)w.Emb, b.tok + (int64_t)t * B, (TS*)b.Xe + (int64_t)t * B * E, E);
+      embed_gather_kernel<TS><<<B, 64, 0, st>>>((const TS*)w.Emb, b.tok + (int64_t)t * B, (TS*)b.Xe + (int64_t)t * B * E, E, (int64_t)t * B,
+                                                b.emb_dropout_p, b.dropout_seed);
       SAT_COUNT_LAUNCH();
       SAT_LAUNCH_OK();
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xe + (int64_t)t * B * E, E, E), (const TS*)w.Wihe, E, B, 4 * H,
@@ -108,7 +109,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   // ---- hoisted: deep output (model.py:127) and vocabulary projection (model.py:130) over all T*B rows
   const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
-                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr, d.plain_output}, st)));
+                           EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr, d.plain_output, b.dropout_p, b.dropout_seed, 0}, st)));
   SAT_PROF(3, st);
   if (b.logits_f32) {
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,

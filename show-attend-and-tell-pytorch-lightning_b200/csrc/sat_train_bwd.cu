@@ -22,7 +22,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
 
   // dpre = g * (dlogits * Wo) * (1 - Xo^2)            [M,E]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dlogits, V, V), (const TS*)w.WoT, V, M, E,
-                           EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale, d.plain_output}, st)));
+                           EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale, d.plain_output, b.dropout_p, b.dropout_seed}, st)));
   // dHZ = dpre * [W_ho | W_zo]                         [M,H+D]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dpre, E, E), (const TS*)w.WhozoT, E, M, H + D,
                            EpiStore<float>{b.dHZ, H + D, nullptr, nullptr, 0}, st)));
@@ -78,6 +78,10 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.DY + A + D, NH3, 4 * H), (const TS*)w.WiheT, 4 * H, M, E,
                            EpiStore<float, TS>{b.dXe, E, nullptr, d.plain_output ? (const TS*)nullptr : (const TS*)b.dpre, E}, st)));
 
+  if (b.emb_dropout_p > 0.0f) {   // embedding_dropout backward: dXe is the grad wrt the dropped embeddings
+    dropout_bwd_kernel<<<(unsigned)(((int64_t)M * E + 255) / 256), 256, 0, st>>>(b.dXe, (int64_t)M * E, b.emb_dropout_p, b.dropout_seed, 2u);
+    SAT_COUNT_LAUNCH();
+  }
   // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
   init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, b.d_init_out, B, H, d.ncap);
   SAT_COUNT_LAUNCH();
@@ -87,6 +91,10 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.df1, E, E), (const TS*)w.WfactT, E, Bi, D,
                               EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));
 
+  if (b.dropout_p > 0.0f) {       // InitLSTM dropout on the mean (model.py:78)
+    dropout_bwd_kernel<<<(unsigned)(((int64_t)Bi * D + 255) / 256), 256, 0, st>>>(b.dmean, (int64_t)Bi * D, b.dropout_p, b.dropout_seed, 1u);
+    SAT_COUNT_LAUNCH();
+  }
   // d_ann[b,l,:] = dP[b,l,:] * Wa + sum_t alpha[b,t,l] dZ[t,b,:] + dmean[img]/(L*ncap)
   // (for ncap > 1 the buffer holds per-caption rows [B,L,D]; the host sums the ncap rows of an image)
   EpiDAnn<TS> epi_dann{(TS*)b.d_ann, b.alphas, (const TS*)b.dZ, b.dmean, B, T, L, D, d.ncap, 1.0f / ((float)L * (float)d.ncap)};

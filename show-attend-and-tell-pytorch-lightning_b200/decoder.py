@@ -81,7 +81,7 @@ class TrainBuffers:
         self.c.logits_f32 = 1 if logits_f32 else 0
         self.dims = d
 
-    def bind_inputs(self, ann, caps, lens, label_smoothing, att_gamma, sampled=None):
+    def bind_inputs(self, ann, caps, lens, label_smoothing, att_gamma, sampled=None, dropout=(0.0, 0.0, 0)):
         self.t["ann"], self.t["caps"], self.t["lens"] = ann, caps, lens   # keep alive
         self.c.ann, self.c.caps, self.c.lens = _lib.ptr(ann), _lib.ptr(caps), _lib.ptr(lens)
         if sampled is not None and any(sampled):
@@ -92,6 +92,7 @@ class TrainBuffers:
             self.c.sampled = None
         self.c.label_smoothing = float(label_smoothing)
         self.c.att_gamma = float(att_gamma)
+        self.c.dropout_p, self.c.emb_dropout_p, self.c.dropout_seed = float(dropout[0]), float(dropout[1]), int(dropout[2])
 
 
 def annotations_as_bld(ann, dtype):
@@ -105,7 +106,7 @@ def annotations_as_bld(ann, dtype):
 
 
 def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, exact=True, use_tc=False,
-                  logits_f32=False, backward=True, keep_logits=False, buffers=None, sampled=None):
+                  logits_f32=False, backward=True, keep_logits=False, buffers=None, sampled=None, dropout=(0.0, 0.0, 0)):
     """ann_bld [Bi,L,D] (pw.dtype, cuda); caps [Bi,ncap,T+1] or [B,T+1] int; lens [Bi,ncap] or [B].
     Runs sat_train_forward; returns the TrainBuffers (loss etc. in .t['out'])."""
     L_ = _lib.lib()
@@ -120,7 +121,7 @@ def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, e
     d = make_dims(B, Bi, L, D, dm["A"], dm["E"], dm["H"], dm["V"], caplen - 1, pw.dtype, exact, use_tc, pw.plain_output)
     if buffers is None:
         buffers = TrainBuffers(d, pw.dtype, dev, logits_f32=logits_f32, backward=backward, keep_logits=keep_logits)
-    buffers.bind_inputs(ann_bld, caps2, lens2, label_smoothing, att_gamma, sampled)
+    buffers.bind_inputs(ann_bld, caps2, lens2, label_smoothing, att_gamma, sampled, dropout)
     buffers.dims = d
     _lib.check(L_.sat_train_forward(C.byref(d), pw.ref(), C.byref(buffers.c), _lib.stream_ptr()), "sat_train_forward")
     return buffers

@@ -261,7 +261,7 @@ class _FusedTrainLoss(torch.autograd.Function):
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, cfg["label_smoothing"], cfg["att_gamma"], exact=cfg["exact"],
                                     use_tc=cfg["use_tc"], logits_f32=False, backward=True, keep_logits=False,
-                                    sampled=cfg.get("sampled"))
+                                    sampled=cfg.get("sampled"), dropout=cfg.get("dropout", (0.0, 0.0, 0)))
         ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
         ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
         ctx.have = [p is not None for p in params]
@@ -291,7 +291,8 @@ class _TrainLogits(torch.autograd.Function):
         pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, 0.0, 0.0, exact=cfg["exact"], use_tc=cfg["use_tc"],
-                                    logits_f32=True, backward=True, keep_logits=True, sampled=cfg.get("sampled"))
+                                    logits_f32=True, backward=True, keep_logits=True, sampled=cfg.get("sampled"),
+                                    dropout=cfg.get("dropout", (0.0, 0.0, 0)))
         ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
         ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
         ctx.have = [p is not None for p in params]
@@ -381,6 +382,16 @@ class SAT(_Base):
                     label_smoothing=float(self.hparams.label_smoothing), att_gamma=float(self.hparams.att_gamma),
                     pad_idx=self.stoi("<PAD>"), weight_tying=bool(self.hparams.weight_tying and self.hparams.deep_output))
 
+    def _dropout_cfg(self):
+        """(dropout p, embedding_dropout p, seed): active in train() mode only, like nn.Dropout.  The masks are a pure function
+        of (seed, element index) inside the kernels (sat_b200.h); a fresh seed is drawn from torch's CPU generator per step."""
+        if not self.training:
+            return (0.0, 0.0, 0)
+        p, pe = float(self.hparams.dropout), float(self.hparams.embedding_dropout)
+        if p <= 0.0 and pe <= 0.0:
+            return (0.0, 0.0, 0)
+        return (p, pe, int(torch.randint(0, 2 ** 62, (1,)).item()))
+
     def decoder_weights(self):
         """reference-named decoder parameters in PARAM_NAMES order (None where absent)."""
         sd = dict(self.named_parameters())
@@ -416,12 +427,11 @@ class SAT(_Base):
 
     def train_batch(self, batch, epsilon=0):
         """-> (PackedSequence logits fp32, PackedSequence targets, alphas [B,T,L])  (model.py:557)."""
-        if self.training and (self.hparams.dropout > 0 or self.hparams.embedding_dropout > 0):
-            raise NotImplementedError("dropout > 0 is not on the accelerated path yet")
         img, encoded_captions, lengths = batch
         ann = self.encode(img)
         cfg = self._cfg()
         cfg["sampled"] = self._sampling_plan(lengths, encoded_captions.size(2) - 1, epsilon)
+        cfg["dropout"] = self._dropout_cfg()
         logits, alphas = _TrainLogits.apply(ann, encoded_captions, lengths, cfg, *self.decoder_weights())
         caps = encoded_captions.reshape(-1, encoded_captions.size(2))
         lens = lengths.reshape(-1).tolist()
@@ -432,12 +442,11 @@ class SAT(_Base):
     def fused_loss(self, batch, epsilon=1.0):
         """Fused forward + loss of one training step: (loss with grad, aux[8] = loss, ce, reg,
         accuracy, 1/ntok, ntok).  This is what training_step runs; epsilon < 1 enables scheduled sampling."""
-        if self.training and (self.hparams.dropout > 0 or self.hparams.embedding_dropout > 0):
-            raise NotImplementedError("dropout > 0 is not on the accelerated path yet")
         img, encoded_captions, lengths = batch
         ann = self.encode(img)
         cfg = self._cfg()
         cfg["sampled"] = self._sampling_plan(lengths, encoded_captions.size(2) - 1, epsilon)
+        cfg["dropout"] = self._dropout_cfg()
         return _FusedTrainLoss.apply(ann, encoded_captions, lengths, cfg, *self.decoder_weights())
 
     def _epsilon(self):

@@ -192,3 +192,38 @@ def test_caption_api_returns_reference_format():
     assert all(a[0].device.type == "cpu" and a[0].shape[1:] == (4, 3) for a in alphas)
     assert all(len(c[0]) == a[0].shape[0] for c, a in zip(caps, alphas))
     assert all(s == sorted(s, reverse=True) for s in scores)
+
+
+def test_dropout_train_mode_matches_oracle_with_the_same_masks():
+    """dropout / embedding_dropout > 0 in train() mode (model.py:78,526,130; the reference's recommended recipes use 0.2):
+    the kernels' masks are a pure function of (seed, index), so the oracle is run with exactly those masks."""
+    import ctypes as C
+    from sat_b200 import _lib
+    m = build(seed=9, label_smoothing=0.1, dropout=0.3, embedding_dropout=0.2)
+    ann, caps, lens = batch(11, ncap=1, T=6)
+    Bi, D, E, T = ann.shape[0], 64, 32, 6
+    W = {k: v.requires_grad_(True) for k, v in weights_cpu(m).items()}
+    m.train()
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # the draw fused_loss will make
+    mul = lambda p, stream, idx: _lib.lib().sat_dropout_multiplier(C.c_float(p), C.c_uint64(seed), C.c_uint32(stream), C.c_uint64(idx))
+    mean_mask = torch.tensor([[mul(0.3, 1, i * D + d) for d in range(D)] for i in range(Bi)])
+    emb_mask = torch.tensor([[[mul(0.2, 2, (t * Bi + b) * E + e) for e in range(E)] for t in range(T)] for b in range(Bi)])
+    out_mask = torch.tensor([[[mul(0.3, 3, (t * Bi + b) * E + e) for e in range(E)] for t in range(T)] for b in range(Bi)])
+    assert 0.15 < float((emb_mask == 0).float().mean()) < 0.25 and 0.22 < float((out_mask == 0).float().mean()) < 0.38
+    a_ref = ann.clone().requires_grad_(True)
+    ref = O.train_loss(W, a_ref, caps, lens, 0.1, 1.0, masks=dict(mean=mean_mask, emb=emb_mask, out=out_mask))
+    ref["loss"].backward()
+    torch.manual_seed(77)
+    a = ann.cuda().requires_grad_(True)
+    loss, aux = m.fused_loss((a, caps.cuda(), lens.cuda()))
+    assert abs(float(loss) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, W[k].grad) < 5e-5, k
+    assert relerr(a.grad, a_ref.grad) < 5e-5
+    # eval mode ignores dropout
+    m.eval()
+    l_eval, _ = m.fused_loss((ann.cuda(), caps.cuda(), lens.cuda()))
+    ref0 = O.train_loss({k: v.detach() for k, v in W.items()}, ann, caps, lens, 0.1, 1.0)
+    assert abs(float(l_eval) - float(ref0["loss"])) < 1e-5 * abs(float(ref0["loss"]))
