@@ -136,6 +136,14 @@ def inference_weights(model):
     cache = getattr(model, "_packed_infer", None)
     if cache is None or cache[0] != key:
         W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
+        mn = model.hparams.get("embed_norm", None) if hasattr(model.hparams, "get") else None
+        if mn is not None:
+            # max_norm renormalisation (model.py:161): every row a decode can look up, applied to the packed copy only
+            e = W["embedding.weight"].detach().clone()
+            torch.embedding_renorm_(e, torch.arange(e.shape[0], device=e.device), float(mn), 2.0)
+            W["embedding.weight"] = e
+            if model.hparams.weight_tying and model.hparams.deep_output:
+                W["output.output.weight"] = e
         dev = next(p for p in params if p is not None).device
         model._packed_infer = (key, DecodeWeights(W, cfg["dtype"], dev, cfg["exact"], cfg["use_tc"]))
     return model._packed_infer[1]

@@ -392,6 +392,18 @@ class SAT(_Base):
             return (0.0, 0.0, 0)
         return (p, pe, int(torch.randint(0, 2 ** 62, (1,)).item()))
 
+    def _renorm_embedding(self, token_ids=None):
+        """nn.Embedding(max_norm=embed_norm) renormalises the looked-up rows IN PLACE at every forward (model.py:158-163).
+        The kernels gather from a packed copy, so the same side effect is applied here before packing: to the rows of
+        `token_ids`, or to every row when the ids are produced on the device (scheduled sampling)."""
+        mn = self.hparams.embed_norm
+        if mn is None:
+            return
+        w = self.embedding.weight
+        with torch.no_grad():
+            ids = torch.arange(w.shape[0], device=w.device) if token_ids is None else token_ids.reshape(-1).to(w.device).unique()
+            torch.embedding_renorm_(w, ids, float(mn), 2.0)
+
     def decoder_weights(self):
         """reference-named decoder parameters in PARAM_NAMES order (None where absent)."""
         sd = dict(self.named_parameters())
@@ -432,6 +444,7 @@ class SAT(_Base):
         cfg = self._cfg()
         cfg["sampled"] = self._sampling_plan(lengths, encoded_captions.size(2) - 1, epsilon)
         cfg["dropout"] = self._dropout_cfg()
+        self._renorm_embedding(None if cfg["sampled"] else encoded_captions[..., :-1])
         logits, alphas = _TrainLogits.apply(ann, encoded_captions, lengths, cfg, *self.decoder_weights())
         caps = encoded_captions.reshape(-1, encoded_captions.size(2))
         lens = lengths.reshape(-1).tolist()
@@ -447,6 +460,7 @@ class SAT(_Base):
         cfg = self._cfg()
         cfg["sampled"] = self._sampling_plan(lengths, encoded_captions.size(2) - 1, epsilon)
         cfg["dropout"] = self._dropout_cfg()
+        self._renorm_embedding(None if cfg["sampled"] else encoded_captions[..., :-1])
         return _FusedTrainLoss.apply(ann, encoded_captions, lengths, cfg, *self.decoder_weights())
 
     def _epsilon(self):

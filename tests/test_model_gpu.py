@@ -227,3 +227,23 @@ def test_dropout_train_mode_matches_oracle_with_the_same_masks():
     l_eval, _ = m.fused_loss((ann.cuda(), caps.cuda(), lens.cuda()))
     ref0 = O.train_loss({k: v.detach() for k, v in W.items()}, ann, caps, lens, 0.1, 1.0)
     assert abs(float(l_eval) - float(ref0["loss"])) < 1e-5 * abs(float(ref0["loss"]))
+
+
+def test_embed_norm_renormalises_like_nn_embedding():
+    """embed_norm (nn.Embedding(max_norm=...), model.py:161): looked-up rows are clipped in place before use."""
+    m = build(seed=10, embed_norm=1.0)
+    ann, caps, lens = batch(12, ncap=1)
+    W = weights_cpu(m)
+    ref_emb = torch.nn.Embedding(128, 32, max_norm=1.0, padding_idx=0)
+    with torch.no_grad():
+        ref_emb.weight.copy_(W["embedding.weight"])
+    ref_emb(caps[..., :-1].reshape(-1))                       # in-place renorm of the used rows, as the reference's forward does
+    Wr = dict(W)
+    Wr["embedding.weight"] = ref_emb.weight.detach().clone()
+    ref = O.train_loss(Wr, ann, caps, lens, 0.0, 1.0)
+    m.train()
+    loss, _ = m.fused_loss((ann.cuda(), caps.cuda(), lens.cuda()))
+    assert abs(float(loss) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    assert relerr(m.embedding.weight, ref_emb.weight) < 1e-6      # same side effect on the parameter
+    used = caps[..., :-1].reshape(-1).unique()
+    assert float(m.embedding.weight[used.cuda()].norm(dim=1).max()) <= 1.0 + 1e-5
