@@ -73,6 +73,28 @@ typedef struct SatWeights {
   const void* WfactT;  /* [D,E] s */
 } SatWeights;
 
+/* fp32 master parameters under the reference's names (device pointers, contiguous). */
+typedef struct SatMasterWeights {
+  const float* embedding;    /* embedding.weight [V,E]                       */
+  const float* fact_w;       /* init_lstm.factorize.weight [E,D]             */
+  const float* fact_b;       /* init_lstm.factorize.bias [E]                 */
+  const float* init_w;       /* init_lstm.init.weight [2H,E]                 */
+  const float* init_b;       /* init_lstm.init.bias [2H]                     */
+  const float* w_ih;         /* lstm.weight_ih_l0 [4H,E+D]                   */
+  const float* w_hh;         /* lstm.weight_hh_l0 [4H,H]                     */
+  const float* b_ih;         /* lstm.bias_ih_l0 [4H]                         */
+  const float* b_hh;         /* lstm.bias_hh_l0 [4H]                         */
+  const float* enc_att;      /* attention.encoder_att.weight [A,D]           */
+  const float* dec_att;      /* attention.decoder_att.weight [A,H]           */
+  const float* f_att;        /* attention.f_att.weight [1,A]                 */
+  const float* beta_w;       /* beta.0.weight [D,H]                          */
+  const float* beta_b;       /* beta.0.bias [D]                              */
+  const float* out_hidden;   /* output.hidden.weight [E,H]                   */
+  const float* out_context;  /* output.context.weight [E,D] or NULL (deep_output=False: destination stays zero) */
+  const float* out_w;        /* output.output.weight [V,E]                   */
+  const float* out_b;        /* output.output.bias [V] or NULL (weight tying) */
+} SatMasterWeights;
+
 /* Buffers of one teacher-forced training step.  fwd = written by sat_train_forward and read by
  * sat_train_backward; bwd = written by sat_train_backward. */
 typedef struct SatTrainBuffers {
@@ -185,10 +207,15 @@ typedef struct SatDecodeBuffers {
 
 int sat_version(void);
 const char* sat_last_error(void);
-/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers, 3 SatDecodeBuffers */
+/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers, 3 SatDecodeBuffers, 4 SatMasterWeights */
 int sat_abi_sizeof(int which);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 unsigned long long sat_launch_count(void);
+
+/* Converts the master parameters into every packed layout of `w` (whose pointers name caller-allocated buffers; NULL
+ * destinations are skipped) with one kernel.  Replaces the implicit per-op layouts of the reference's nn.Modules
+ * (model.py:158-199); run after every optimizer step. */
+int sat_pack_weights(const SatDims* d, const SatMasterWeights* m, const SatWeights* w, void* stream);
 
 /* Kernel timing for bench.py's roofline entry: while enabled, every launch of the selected kernel kind
  * (1 = attention step forward, 2 = attention step backward, 3 = vocabulary GEMM) is bracketed by CUDA

@@ -24,6 +24,12 @@ class SatWeights(C.Structure):
                  "Winit", "binit", "WoT", "WhozoT", "WihzT", "WiheT", "WhcatT", "WaT", "WinitT", "WfactT")]
 
 
+class SatMasterWeights(C.Structure):
+    _fields_ = [(n, vp) for n in
+                ("embedding", "fact_w", "fact_b", "init_w", "init_b", "w_ih", "w_hh", "b_ih", "b_hh", "enc_att", "dec_att",
+                 "f_att", "beta_w", "beta_b", "out_hidden", "out_context", "out_w", "out_b")]
+
+
 class SatTrainBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "caps", "lens", "sampled", "tok", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
@@ -44,7 +50,7 @@ class SatDecodeBuffers(C.Structure):
                 ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32)]
 
 
-EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end", "sat_dropout_multiplier",
+EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end", "sat_dropout_multiplier", "sat_pack_weights",
            "sat_linear", "sat_prepare_images",
            "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward", "sat_decode_prepare_weights", "sat_decode"]
 
@@ -77,11 +83,12 @@ def lib():
     L.sat_last_error.restype = C.c_char_p
     L.sat_launch_count.restype = C.c_ulonglong
     L.sat_abi_sizeof.argtypes = [C.c_int]
-    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers, SatDecodeBuffers)):
+    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers, SatDecodeBuffers, SatMasterWeights)):
         if L.sat_abi_sizeof(i) != C.sizeof(st):
             raise SatError("ABI mismatch for %s: lib %d vs ctypes %d" % (st.__name__, L.sat_abi_sizeof(i), C.sizeof(st)))
     L.sat_dropout_multiplier.argtypes = [C.c_float, C.c_uint64, C.c_uint32, C.c_uint64]
     L.sat_dropout_multiplier.restype = C.c_float
+    L.sat_pack_weights.argtypes = [C.POINTER(SatDims), C.POINTER(SatMasterWeights), C.POINTER(SatWeights), vp]
     L.sat_profile_begin.argtypes = [C.c_int]
     L.sat_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.sat_linear.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

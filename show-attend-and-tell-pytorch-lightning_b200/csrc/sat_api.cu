@@ -66,6 +66,7 @@ int sat_abi_sizeof(int which) {
     case 1: return (int)sizeof(SatWeights);
     case 2: return (int)sizeof(SatTrainBuffers);
     case 3: return (int)sizeof(SatDecodeBuffers);
+    case 4: return (int)sizeof(SatMasterWeights);
     default: return -1;
   }
 }

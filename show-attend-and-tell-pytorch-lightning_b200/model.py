@@ -251,13 +251,28 @@ class LabelSmoothing(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # autograd bridges
 # ------------------------------------------------------------------------------------------------
+def _packed_for(cfg, W, device):
+    """Persistent PackedWeights of the owning module (cfg["owner"]), repacked from the current parameters with one kernel;
+    a throw-away object when there is no owner or the parameter set changed shape."""
+    owner = cfg.get("owner")
+    key = (cfg["dtype"], str(device), tuple((n, tuple(p.shape)) for n, p in sorted(W.items())))
+    if owner is not None:
+        cached = getattr(owner, "_packed_train", None)
+        if cached is not None and cached[0] == key:
+            return cached[1].repack(W)
+    pw = PackedWeights(W, dtype=cfg["dtype"], device=device, backward=True)
+    if owner is not None:
+        object.__setattr__(owner, "_packed_train", (key, pw))
+    return pw
+
+
 class _FusedTrainLoss(torch.autograd.Function):
     """loss (+ aux) of one teacher-forced step; backward = hand-written BPTT (sat_train_backward)."""
 
     @staticmethod
     def forward(ctx, ann, caps, lens, cfg, *params):
         W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
-        pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
+        pw = _packed_for(cfg, W, ann.device)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, cfg["label_smoothing"], cfg["att_gamma"], exact=cfg["exact"],
                                     use_tc=cfg["use_tc"], logits_f32=False, backward=True, keep_logits=False,
@@ -288,7 +303,7 @@ class _TrainLogits(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ann, caps, lens, cfg, *params):
         W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
-        pw = PackedWeights(W, dtype=cfg["dtype"], device=ann.device, backward=True)
+        pw = _packed_for(cfg, W, ann.device)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, 0.0, 0.0, exact=cfg["exact"], use_tc=cfg["use_tc"],
                                     logits_f32=True, backward=True, keep_logits=True, sampled=cfg.get("sampled"),
@@ -378,7 +393,7 @@ class SAT(_Base):
 
     def _cfg(self):
         dt = self._dtype()
-        return dict(dtype=dt, exact=(dt == torch.float32), use_tc=(dt == torch.bfloat16),
+        return dict(owner=self, dtype=dt, exact=(dt == torch.float32), use_tc=(dt == torch.bfloat16),
                     label_smoothing=float(self.hparams.label_smoothing), att_gamma=float(self.hparams.att_gamma),
                     pad_idx=self.stoi("<PAD>"), weight_tying=bool(self.hparams.weight_tying and self.hparams.deep_output))
 

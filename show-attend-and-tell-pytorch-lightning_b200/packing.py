@@ -29,60 +29,81 @@ def deinterleave_gates(w):
 
 
 class PackedWeights:
-    """Device copies of the decoder weights in kernel layout.  `W` maps reference names to tensors
-    (any device/dtype); `dtype` is the kernel operand dtype."""
+    """Device copies of the decoder weights in kernel layout (SatWeights), produced by ONE kernel (sat_pack_weights) from
+    the fp32 master parameters.  `W` maps reference names to tensors; `dtype` is the kernel operand dtype.  The buffers
+    are persistent: call repack(W) after an optimizer step instead of building a new object."""
+
+    _SRC = (("embedding", "embedding.weight"), ("fact_w", "init_lstm.factorize.weight"), ("fact_b", "init_lstm.factorize.bias"),
+            ("init_w", "init_lstm.init.weight"), ("init_b", "init_lstm.init.bias"), ("w_ih", "lstm.weight_ih_l0"),
+            ("w_hh", "lstm.weight_hh_l0"), ("b_ih", "lstm.bias_ih_l0"), ("b_hh", "lstm.bias_hh_l0"),
+            ("enc_att", "attention.encoder_att.weight"), ("dec_att", "attention.decoder_att.weight"),
+            ("f_att", "attention.f_att.weight"), ("beta_w", "beta.0.weight"), ("beta_b", "beta.0.bias"),
+            ("out_hidden", "output.hidden.weight"), ("out_context", "output.context.weight"),
+            ("out_w", "output.output.weight"), ("out_b", "output.output.bias"))
 
     def __init__(self, W, dtype=torch.float32, device="cuda", backward=True):
         self.dtype = dtype
-        dev = torch.device(device)
-        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32)
-        emb = f32(W["embedding.weight"])
-        wih, whh = f32(W["lstm.weight_ih_l0"]), f32(W["lstm.weight_hh_l0"])
-        wa, wh = f32(W["attention.encoder_att.weight"]), f32(W["attention.decoder_att.weight"])
-        wb, bb = f32(W["beta.0.weight"]), f32(W["beta.0.bias"])
-        who = f32(W["output.hidden.weight"])
-        # DeepOutput(deep=False) has no context projection (model.py:120-121): pack zeros and flag the plain epilogues
-        self.plain_output = W.get("output.context.weight", None) is None
-        wzo = torch.zeros(who.shape[0], wa.shape[1], device=dev) if self.plain_output else f32(W["output.context.weight"])
-        wo = f32(W["output.output.weight"])
-        bo = W.get("output.output.bias", None)
-        V, E = emb.shape
-        H = whh.shape[1]
-        D = wa.shape[1]
-        A = wa.shape[0]
+        dev = self.device = torch.device(device)
+        V, E = W["embedding.weight"].shape
+        H = W["lstm.weight_hh_l0"].shape[1]
+        A, D = W["attention.encoder_att.weight"].shape
         self.dims = dict(V=V, E=E, H=H, D=D, A=A)
-        s = lambda t: t.to(dtype).contiguous()
-        self.t = t = {}
-        t["Wa"] = s(wa)
-        whcat = torch.cat([wh, wb, interleave_gates(whh), who], 0)
-        t["Whcat"] = s(whcat)
-        t["bhcat"] = torch.cat([torch.zeros(A, device=dev), bb, torch.zeros(4 * H + E, device=dev)]).contiguous()
-        t["Wihz"] = s(interleave_gates(wih[:, E:]))
-        t["Wihe"] = s(interleave_gates(wih[:, :E]))
-        t["bg"] = interleave_gates(f32(W["lstm.bias_ih_l0"]) + f32(W["lstm.bias_hh_l0"]))
-        whozo = torch.cat([who, wzo], 1)
-        t["Whozo"] = s(whozo)
-        t["Wo"] = s(wo)
-        t["bo"] = f32(bo).contiguous() if bo is not None else None
-        t["wf"] = f32(W["attention.f_att.weight"]).reshape(-1).contiguous()
-        t["Emb"] = s(emb)
-        t["Wfact"] = s(f32(W["init_lstm.factorize.weight"]))
-        t["bfact"] = f32(W["init_lstm.factorize.bias"]).contiguous()
-        t["Winit"] = s(f32(W["init_lstm.init.weight"]))
-        t["binit"] = f32(W["init_lstm.init.bias"]).contiguous()
+        # DeepOutput(deep=False) has no context projection (model.py:120-121): its slots stay zero, plain epilogues
+        self.plain_output = W.get("output.context.weight", None) is None
+        NH3, NH4 = A + D + 4 * H, A + D + 4 * H + E
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        f = torch.float32
+        t = self.t = {}
+        t["Wa"] = z((A, D), dtype)
+        t["Whcat"] = z((NH4, H), dtype)
+        t["bhcat"] = z((NH4,), f)
+        t["Wihz"] = z((4 * H, D), dtype)
+        t["Wihe"] = z((4 * H, E), dtype)
+        t["bg"] = z((4 * H,), f)
+        t["Whozo"] = z((E, H + D), dtype)
+        t["Wo"] = z((V, E), dtype)
+        t["bo"] = z((V,), f) if W.get("output.output.bias", None) is not None else None
+        t["wf"] = z((A,), f)
+        t["Emb"] = z((V, E), dtype)
+        t["Wfact"] = z((E, D), dtype)
+        t["bfact"] = z((E,), f)
+        t["Winit"] = z((2 * H, E), dtype)
+        t["binit"] = z((2 * H,), f)
         if backward:
-            NH3 = A + D + 4 * H
-            t["WoT"] = s(wo.t())
-            t["WhozoT"] = s(whozo.t())
-            t["WihzT"] = s(interleave_gates(wih[:, E:]).t())
-            t["WiheT"] = s(interleave_gates(wih[:, :E]).t())
-            t["WhcatT"] = s(whcat[:NH3].t())
-            t["WaT"] = s(wa.t())
-            t["WinitT"] = s(f32(W["init_lstm.init.weight"]).t())
-            t["WfactT"] = s(f32(W["init_lstm.factorize.weight"]).t())
+            t["WoT"] = z((E, V), dtype)
+            t["WhozoT"] = z((H + D, E), dtype)
+            t["WihzT"] = z((D, 4 * H), dtype)
+            t["WiheT"] = z((E, 4 * H), dtype)
+            t["WhcatT"] = z((H, NH3), dtype)
+            t["WaT"] = z((D, A), dtype)
+            t["WinitT"] = z((E, 2 * H), dtype)
+            t["WfactT"] = z((D, E), dtype)
         self.c = _lib.SatWeights()
         for name, _ in _lib.SatWeights._fields_:
             setattr(self.c, name, _lib.ptr(t.get(name)))
+        self._d = _lib.SatDims()
+        self._d.B = self._d.Bi = self._d.ncap = 1
+        self._d.L, self._d.D, self._d.A, self._d.E, self._d.H, self._d.V, self._d.T = 1, D, A, E, H, V, 1
+        self._d.dtype = _lib.dtype_code(dtype)
+        self.repack(W)
+
+    def repack(self, W):
+        """(re)fill every packed buffer from the current master parameters: one kernel launch."""
+        m = _lib.SatMasterWeights()
+        keep = []
+        for field, name in self._SRC:
+            p = W.get(name, None)
+            if p is None:
+                setattr(m, field, None)
+                continue
+            x = p.detach()
+            if x.device != self.device or x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(x)
+            setattr(m, field, x.data_ptr())
+        self._keep = keep            # sources must outlive the (asynchronous) kernel
+        _lib.check(_lib.lib().sat_pack_weights(C.byref(self._d), C.byref(m), C.byref(self.c), _lib.stream_ptr()), "sat_pack_weights")
+        return self
 
     def ref(self):
         return C.byref(self.c)

@@ -33,7 +33,7 @@ def test_header_symbols_are_exported():
 def test_struct_mirrors_match():
     from sat_b200 import _lib
     L = _lib.lib()
-    for i, st in enumerate((_lib.SatDims, _lib.SatWeights, _lib.SatTrainBuffers, _lib.SatDecodeBuffers)):
+    for i, st in enumerate((_lib.SatDims, _lib.SatWeights, _lib.SatTrainBuffers, _lib.SatDecodeBuffers, _lib.SatMasterWeights)):
         assert L.sat_abi_sizeof(i) == ctypes.sizeof(st)
 
 
