@@ -81,3 +81,29 @@ def test_greedy_bf16_runs_and_mostly_agrees(use_tc):
     got = cuda_caption(W, ann, 1, 30, dtype=torch.bfloat16, use_tc=use_tc)
     agree = sum(1 for a, b in zip(got[0], ref[0]) if a[:3] == b[:3])
     assert agree >= 3          # bf16 token ids are not expected to be bit-exact
+
+
+def test_decode_single_image_and_wide_beam():
+    """one image, beam wider than typical (k=8) and k=1, tiny vocabulary: exercises shrinking beams down to zero."""
+    D, A, E, H, V = 64, 32, 32, 64, 64
+    W = O.random_weights(D, A, E, H, V, seed=21, sharpen=True)
+    W["output.output.bias"][V - 1] = 2.0
+    g = torch.Generator().manual_seed(22)
+    ann = torch.randn(1, D, 3, 3, generator=g)
+    for k in (1, 8):
+        ref = O.caption(W, ann, VOC(V), beamk=k, max_gen_length=12, rescore_method="LN", return_all=True)
+        got = cuda_caption(W, ann, k, 12, 1.0, "LN", 0.5, True)
+        assert got[0] == ref[0]
+        assert max(abs(x - y) for x, y in zip(got[1][0], ref[1][0])) < 1e-4
+        assert len(got[0][0]) == k            # every beam ends up as exactly one finished hypothesis
+
+
+def test_decode_temperature_list_cycles_per_step():
+    z, W, _ = load_golden("decode_small")
+    V, max_len = int(z["dims"][4]), int(z["dims"][5])
+    ann = torch.from_numpy(z["ann"])
+    temps = [1.0, 0.6, 1.4]
+    ref = O.caption(W, ann, VOC(V), beamk=3, max_gen_length=max_len, temperature=temps, rescore_method="WR")
+    got = cuda_caption(W, ann, 3, max_len, temps, "WR")
+    assert got[0] == ref[0]
+    assert max(abs(x - y) for x, y in zip(got[1], ref[1])) < 1e-4

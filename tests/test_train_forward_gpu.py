@@ -78,3 +78,29 @@ def test_forward_bf16_vs_oracle(use_tc):
     assert relerr(r["logits"], ref["logits"]) < 2e-2
     assert abs(r["loss"] - float(ref["loss"])) < 2e-2 * abs(float(ref["loss"]))
     assert relerr(r["alphas"], ref["alphas"]) < 2e-2
+
+
+@pytest.mark.parametrize("cfg,lens_override", [
+    (dict(Bi=1, ncap=1, hw=(2, 2), D=64, A=32, E=32, H=64, V=128, T=5, ragged=False), None),          # single caption, L=4
+    (dict(Bi=3, ncap=1, hw=(1, 1), D=64, A=32, E=32, H=64, V=128, T=4, ragged=False), [[1], [4], [2]]),   # L=1, shortest length 1
+    (dict(Bi=2, ncap=3, hw=(3, 5), D=128, A=64, E=64, H=128, V=256, T=6, ragged=False), [[6, 1, 3], [2, 6, 6]]),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_edge_shapes(cfg, lens_override, dtype):
+    """ragged / minimal inputs: one caption, one location, length-1 captions, several captions per image."""
+    W, ann, caps, lens = synth(**cfg)
+    if lens_override is not None:
+        lens = torch.tensor(lens_override)
+    ref = O.train_loss(W, ann, caps, lens, label_smoothing=0.1, att_gamma=1.0)
+    fp32 = dtype == torch.float32
+    r = run_cuda_forward(W, ann, caps, lens, 0.1, 1.0, dtype=dtype, exact=fp32, use_tc=not fp32, logits_f32=fp32)
+    tol = 1e-5 if fp32 else 2e-2
+    assert relerr(r["alphas"], ref["alphas"]) < tol
+    assert relerr(r["logits"], ref["logits"]) < tol
+    assert abs(r["loss"] - float(ref["loss"])) < tol * abs(float(ref["loss"]))
+    # rows past their length are exactly zero, like the reference's pre-zeroed buffers (model.py:504-506)
+    B, T = r["logits"].shape[:2]
+    fl = lens.reshape(-1)
+    for b in range(B):
+        assert float(r["logits"][b, int(fl[b]):].abs().max() if int(fl[b]) < T else 0.0) == 0.0
+        assert float(r["alphas"][b, int(fl[b]):].abs().max() if int(fl[b]) < T else 0.0) == 0.0
