@@ -3,7 +3,8 @@
 //
 //   warp 0    : TMA producer  (cp.async.bulk.tensor.2d, 128B-swizzled tiles, 4-stage mbarrier ring)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
-//   warps 2-5 : epilogue: tcgen05.ld (32 lanes x 16 columns per instruction) -> fused epilogue functor
+//   warps 2-9 : epilogue: tcgen05.ld (32 lanes x 16 columns per instruction) -> shared-memory transpose -> fused
+//               epilogue functor with coalesced global accesses (two warps per TMEM lane quarter, each half the columns)
 //
 // The epilogue functors are the same ones the SIMT core runs (LSTM cell, tanh+add, CE, plain store ...), so
 // every fused stage of the decoder exists on both cores.  Tiles: BM = 128, BN in {64,128}, BK = 64.
@@ -16,7 +17,9 @@
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, THREADS = 192;
+constexpr int BM = 128, BK = 64;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter: the fused epilogues are issue/latency-bound
+constexpr int THREADS = 64 + EPI_WARPS * 32;
 // operand ring depth: 4 x 24 KB at BN = 64 and 3 x 32 KB at BN = 128 -> 96 KB per CTA, two CTAs per SM, so one CTA's
 // epilogue overlaps the other's TMA/MMA main loop (the kernels are not persistent)
 template <int BN> struct Stages { static constexpr int value = BN >= 128 ? 3 : 4; };
@@ -183,9 +186,11 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
     float* tile = reinterpret_cast<float*>(&s.a[0][0]);
     static_assert((size_t)BM * LDT * sizeof(float) <= sizeof(s.a) + sizeof(s.w), "staging tile must fit the ring");
     const int row = q * 32 + lane;
+    const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp moves
+    constexpr int CH = BN / 2;
     if (nkb > 0) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = half * CH; c < (half + 1) * CH; c += 16) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
 #pragma unroll
@@ -193,15 +198,15 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
           *reinterpret_cast<float4*>(&tile[row * LDT + c + g * 4]) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
       }
     } else {
-      for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4*>(&tile[row * LDT + c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = half * CH; c < (half + 1) * CH; c += 4) *reinterpret_cast<float4*>(&tile[row * LDT + c]) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     constexpr int LPR = BN / 4;                // lanes per row
     constexpr int RPW = 32 / LPR;              // rows per warp pass
-    const int ew = warp - 2;                   // 0..3
+    const int ew = warp - 2;                   // 0..EPI_WARPS-1
     const int lr = lane / LPR, lc = (lane % LPR) * 4;
     const int n = n0 + lc;
-    constexpr int NIT = BM / (4 * RPW);       // rows per thread
+    constexpr int NIT = BM / (EPI_WARPS * RPW);   // rows per thread
     constexpr int UN = 4;                      // rows whose epilogue operands are loaded before any dependent math
     static_assert(NIT % UN == 0, "row loop must divide");
 #pragma unroll 1
@@ -210,13 +215,13 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
       bool ok[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const int m = m0 + ew * RPW + lr + (i0 + u) * 4 * RPW;
+        const int m = m0 + ew * RPW + lr + (i0 + u) * EPI_WARPS * RPW;
         ok[u] = m < M && n < N;
         if (ok[u]) ctx[u] = epi.load(m, n);
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const int r = ew * RPW + lr + (i0 + u) * 4 * RPW;
+        const int r = ew * RPW + lr + (i0 + u) * EPI_WARPS * RPW;
         if (ok[u]) {
           const float4 a = *reinterpret_cast<const float4*>(&tile[r * LDT + lc]);
           const float a4[4] = {a.x, a.y, a.z, a.w};
