@@ -78,6 +78,8 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32, ATTP_THREADS = CW * 32 + 32;
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
@@ -351,10 +353,9 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
     SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  kern<<<rows, ATTP_FWD_CW * 32 + 32, smem, st>>>(ann, P, wf, hp, ldhp, lens, t, ncap, L, D, A, scale, alpha, ld_alpha, qsave, z, gz, beta,
-                                         ld_z);
+  SAT_CUDA(sat_launch_pdl(kern, dim3(rows), dim3(ATTP_FWD_CW * 32 + 32), smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D, A, scale, alpha,
+                          ld_alpha, qsave, z, gz, beta, ld_z));
   SAT_COUNT_LAUNCH();
-  SAT_LAUNCH_OK();
   return 0;
 }
 
@@ -384,6 +385,8 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32, ATTP_THREADS = CW * 32 + 32;
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);

@@ -46,6 +46,27 @@ extern int g_sat_prof_kind;
 void sat_prof_mark(cudaStream_t st);
 #define SAT_PROF(kind, st) do { if (g_sat_prof_kind == (kind)) sat_prof_mark(st); } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The decoder is a long chain of short dependent kernels.  Kernels launched through sat_launch_pdl may be scheduled
+// while their predecessor drains; they call SAT_PDL_TRIGGER() first (so their own successor can do the same) and
+// SAT_PDL_WAIT() before the first global-memory access that depends on (or could disturb) the predecessor.
+#define SAT_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define SAT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <typename Kern, typename... Args>
+static inline cudaError_t sat_launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ---- typed loads / stores ------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

@@ -58,19 +58,20 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     SAT_PROF(3, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
     SAT_PROF(3, st);
-    row_topk_kernel<<<R, 256, topk_smem, st>>>(b.logits, b.top_scores, b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART,
-                                               b.tokEND, b.tokUNK, b.cand_val, b.cand_idx);
+    SAT_CUDA(sat_launch_pdl(row_topk_kernel, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
+                            (const int32_t*)b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK, b.cand_val,
+                            b.cand_idx));
     SAT_COUNT_LAUNCH();
     const int in = step & 1, out = in ^ 1;
-    beam_update_kernel<<<n_img, 32, 0, st>>>(bp, step, b.cand_val, b.cand_idx, b.kcur, b.top_scores, b.cur_tok, b.src_row, b.alive,
-                                             b.tok_hist + in * hist_sz, b.asrc_hist + in * hist_sz, b.tok_hist + out * hist_sz,
-                                             b.asrc_hist + out * hist_sz, b.fin_tokens, b.fin_asrc, b.fin_len, b.fin_score,
-                                             b.fin_ppl, b.fin_count);
+    SAT_CUDA(sat_launch_pdl(beam_update_kernel, dim3(n_img), dim3(32), 0, st, bp, step, (const float*)b.cand_val,
+                            (const int32_t*)b.cand_idx, b.kcur, b.top_scores, b.cur_tok, b.src_row, b.alive,
+                            (const int32_t*)(b.tok_hist + in * hist_sz), (const int32_t*)(b.asrc_hist + in * hist_sz),
+                            b.tok_hist + out * hist_sz, b.asrc_hist + out * hist_sz, b.fin_tokens, b.fin_asrc, b.fin_len, b.fin_score,
+                            b.fin_ppl, b.fin_count));
     SAT_COUNT_LAUNCH();
-    gather_state_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>((const TS*)b.hn, b.cn, b.src_row, b.alive,
-                                                                                      (TS*)b.h, b.c, R, H);
+    SAT_CUDA(sat_launch_pdl(gather_state_kernel<TS>, dim3((unsigned)(((int64_t)R * H + 255) / 256)), dim3(256), 0, st, (const TS*)b.hn,
+                            (const float*)b.cn, (const int32_t*)b.src_row, (const int32_t*)b.alive, (TS*)b.h, b.c, R, H));
     SAT_COUNT_LAUNCH();
-    SAT_LAUNCH_OK();
   }
   return 0;
 }

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256)
 row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur,
                 int k, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
                 float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
   extern __shared__ __align__(16) float smem[];
   float* x = smem;            // [V]  scaled logits, masked entries set to -inf after the softmax statistics
   float* scratch = x + V;     // [33]
@@ -113,6 +115,8 @@ beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, c
                    const int32_t* __restrict__ asrc_in, int32_t* __restrict__ tok_out, int32_t* __restrict__ asrc_out,
                    int32_t* __restrict__ fin_tokens, int32_t* __restrict__ fin_asrc, int32_t* __restrict__ fin_len,
                    float* __restrict__ fin_score, float* __restrict__ fin_ppl, int32_t* __restrict__ fin_count) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
   constexpr int KMAX = 32;
   __shared__ float nval[KMAX];
   __shared__ int nword[KMAX], nsrc[KMAX], dst[KMAX];
@@ -225,6 +229,8 @@ beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, c
 template <typename T>
 __global__ void gather_state_kernel(const T* __restrict__ hn, const float* __restrict__ cn, const int32_t* __restrict__ src_row,
                                     const int32_t* __restrict__ alive, T* __restrict__ h, float* __restrict__ c, int R, int H) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)R * H) return;
   const int64_t r = idx / H;

@@ -124,6 +124,9 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
   const int nkb = kb_end - kb_begin;
   constexpr uint32_t STAGE_BYTES = (BM * BK + BN * BK) * sizeof(bf16);
 
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue now; this kernel's prologue
+  // (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of its predecessor and only then waits for it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&s.full[i], 1);
@@ -137,15 +140,18 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s.tmem_base;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // predecessor grid complete and its writes visible
 
   if (warp == 0) {
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
       for (int i = 0; i < nkb; ++i) {
         const int kb = kb_begin + i;
         const int st = i % STAGES;
@@ -294,8 +300,17 @@ static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, i
     SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
-  kern<<<grid, THREADS, smem, stream>>>(maps, M, N, A.k[0], A.nseg == 2 ? A.k[1] : 0, epi);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SAT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, M, N, A.k[0], A.nseg == 2 ? A.k[1] : 0, epi));
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   return 0;

@@ -474,6 +474,8 @@ __global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* 
                                      int64_t dh_stride, const float* __restrict__ dHo, int64_t ld_dho, float* __restrict__ dc,
                                      TS* __restrict__ dG, int64_t ld_dg, const int32_t* __restrict__ lens, int t, int B,
                                      int H) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int b = idx / H, j = idx - b * H;
@@ -520,6 +522,8 @@ attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
   extern __shared__ __align__(16) float smem[];
   constexpr int VN = Vec16<T>::N;
   constexpr int NW = ATT_THREADS / 32;
+  SAT_PDL_TRIGGER();      // launched through sat_launch_pdl by the backward driver
+  SAT_PDL_WAIT();
   float* dz_s = smem;                         // [D]
   float* dal = dz_s + D;                      // [L] (padded to 4)
   float* qs = dal + ((L + 3) & ~3);           // [A]

@@ -49,25 +49,23 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   for (int t = T - 1; t >= 0; --t) {
     TS* DY_t = (TS*)b.DY + (int64_t)t * B * NH3;
     const float* dHZ_t = b.dHZ + (int64_t)t * B * (H + D);
-    lstm_bwd_step_kernel<TS, kExact><<<(B * H + 255) / 256, 256, 0, st>>>(
+    SAT_CUDA(sat_launch_pdl(lstm_bwd_step_kernel<TS, kExact>, dim3((B * H + 255) / 256), dim3(256), 0, st,
         (const TS*)b.Gates + (int64_t)t * B * 4 * H, b.Cs + (int64_t)t * B * H, b.Cs + (int64_t)(t + 1) * B * H, b.dh, sk_dh,
-        (int64_t)B * H, dHZ_t, H + D, b.dc, DY_t + A + D, NH3, b.lens, t, B, H);
+        (int64_t)B * H, dHZ_t, H + D, b.dc, DY_t + A + D, NH3, b.lens, t, B, H));
     SAT_COUNT_LAUNCH();
-    SAT_LAUNCH_OK();
     // dgz = dG * Wihz     (A operand: DY_t[:, A+D:], K = 4H)
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + A + D, NH3, 4 * H), (const TS*)w.WihzT, 4 * H, B, D,
                              EpiStore<float>{b.dgz, D, nullptr, nullptr, 0, (int64_t)B * D}, st, sk_dgz)));
     SAT_PROF(2, st);
-    att_k<<<B, att_threads, att_smem, st>>>(ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
+    SAT_CUDA(sat_launch_pdl(att_k, dim3(B), dim3(att_threads), att_smem, st, ann, (const TS*)b.P, w.wf, b.Q + (int64_t)t * B * A, b.alphas + (int64_t)t * L,
                                             (int64_t)T * L, b.S, (const TS*)b.Z + (int64_t)t * B * D,
                                             (const TS*)b.Beta + (int64_t)t * B * D, b.dgz, sk_dgz, (int64_t)B * D, dHZ_t + H, H + D, b.lens,
                                             t, d.ncap,
                                             B, L, D, A, scale, b.att_gamma, b.gscale,
                                             b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, dann_tc ? (TS*)b.dP16 : (TS*)nullptr, (TS*)b.dZ + (int64_t)t * B * D,
-                                            DY_t, NH3, b.dwf_part + (int64_t)t * B * A);
+                                            DY_t, NH3, b.dwf_part + (int64_t)t * B * A));
     SAT_PROF(2, st);
     SAT_COUNT_LAUNCH();
-    SAT_LAUNCH_OK();
     // dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (rows inactive at t keep their dh)
     // (rows not active at t have an all-zero DY row, and their dh is still zero in backward order, so a plain store is exact)
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t, NH3, NH3), (const TS*)w.WhcatT, NH3, B, H,
