@@ -56,7 +56,8 @@ __device__ __forceinline__ void sat_named_bar(int id, int nthreads) {
 
 constexpr int ATTP_MAXCW = 16;                       // max consumer warps (template parameter CW of the kernels)
 constexpr int ATTP_FWD_CW = 8;                       // forward: 8 consumer warps measured fastest (17.8 us vs 25.8 us at B=256 bf16)
-constexpr int ATTP_BWD_CW = 16;                      // backward: 16 consumer warps hide the dP read-modify-write latency better
+constexpr int ATTP_BWD_CW = 12;                      // backward: 12 consumer warps at <= 78 registers keep two CTAs per SM (16 warps
+                                                     // at 96 registers dropped to one CTA per SM = two waves at B=256)
 constexpr int ATTP_NST = 6;
 constexpr int ATTP_STAGE_BYTES = 16384;
 constexpr int ATTP_KA = 2;                           // attention_dim <= 256 on the pipelined kernel
@@ -373,7 +374,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
 constexpr int ATTB_VPL = 4;      // 16-byte annotation vectors per lane kept in registers (D <= 1024 bf16 / 512 fp32)
 
 template <typename T, bool kExact, int CW>
-__global__ void __launch_bounds__(CW * 32 + 32)
+__global__ void __launch_bounds__(CW * 32 + 32, 2)      // two CTAs per SM: all B=256 captions resident in one wave
 attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ P, const float* __restrict__ wf,
                                const float* __restrict__ q_t, const float* __restrict__ alpha, int64_t ld_alpha,
                                const float* __restrict__ S, const T* __restrict__ z_t, const T* __restrict__ beta_t,
