@@ -152,6 +152,8 @@ typedef struct SatTrainBuffers {
   float* dXe;            /* [T,B,E]      grad wrt embedded words                                   */
   float* d_init_out;     /* [Bi,2H]                                                               */
   float* df1;            /* [Bi,E]                                                                */
+  void* d_init_out16;    /* [Bi,2H] s    operand-dtype copies feeding the tensor-core init-path GEMMs (may be NULL: SIMT) */
+  void* df116;           /* [Bi,E] s                                                              */
   float* dmean;          /* [Bi,D]                                                                */
   void* d_ann;           /* [B,L,D] s    grad wrt annotations, one slab per caption row (host sums the ncap rows of an image) */
   /* scalars */

@@ -162,6 +162,20 @@ struct EpiStore {
   __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, load(m, n)); }
 };
 
+// C (fp32) = acc, plus an operand-dtype copy C16 (feeds a following tensor-core GEMM)
+template <typename TS>
+struct EpiStoreDual {
+  float* C; TS* C16; int64_t ldc;
+  struct Ctx {};
+  __device__ __forceinline__ Ctx load(int, int) const { return Ctx{}; }
+  __device__ __forceinline__ void apply(int m, int n, const float (&acc)[4], const Ctx&) const {
+    const float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    st4(C + (int64_t)m * ldc + n, v);
+    st4(C16 + (int64_t)m * ldc + n, v);
+  }
+  __device__ __forceinline__ void operator()(int m, int n, const float (&acc)[4]) const { apply(m, n, acc, Ctx{}); }
+};
+
 // d_ann[b,l,:] = acc (= dP[b,l,:] * Wa) + sum_t alpha[b,t,l] * dZ[t,b,:] + dmean[img,:] * mean_scale
 // rows m = b*L + l   (d_a += alpha (x) dz ; d_a += dP W_a ; mean path)
 template <typename TS>

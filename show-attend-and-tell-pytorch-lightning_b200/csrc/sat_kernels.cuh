@@ -244,8 +244,8 @@ __global__ void init_state_kernel(const float* __restrict__ init_out, T* __restr
 
 // inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i
 static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int ns_dh, int64_t dh_stride,
-                                             const float* __restrict__ dc0, float* __restrict__ d_init_out, int B, int H,
-                                             int ncap) {
+                                             const float* __restrict__ dc0, float* __restrict__ d_init_out,
+                                             bf16* __restrict__ d_init_out16, int B, int H, int ncap) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, 2H]
   const int Bi = B / ncap;
   if (idx >= (int64_t)Bi * 2 * H) return;
@@ -263,6 +263,7 @@ static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int 
     }
   }
   d_init_out[idx] = s;
+  if (d_init_out16) d_init_out16[idx] = __float2bfloat16_rn(s);
 }
 
 // =============================================================================================

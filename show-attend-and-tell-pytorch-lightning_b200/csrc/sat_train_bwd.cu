@@ -81,14 +81,22 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     SAT_COUNT_LAUNCH();
   }
   // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
-  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, b.d_init_out, B, H, d.ncap);
+  const bool init_tc = tc && !std::is_same<TS, float>::value && b.d_init_out16 != nullptr && b.df116 != nullptr;
+  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, b.d_init_out,
+                                                                  init_tc ? (bf16*)b.d_init_out16 : (bf16*)nullptr, B, H, d.ncap);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
-  SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.d_init_out, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,
-                              EpiStore<float>{b.df1, E, nullptr, nullptr, 0}, st)));
-  SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.df1, E, E), (const TS*)w.WfactT, E, Bi, D,
-                              EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));
-
+  if (init_tc) {
+    SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.d_init_out16, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,
+                             EpiStoreDual<TS>{b.df1, (TS*)b.df116, E}, st)));
+    SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.df116, E, E), (const TS*)w.WfactT, E, Bi, D,
+                             EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));
+  } else {
+    SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.d_init_out, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,
+                                EpiStore<float>{b.df1, E, nullptr, nullptr, 0}, st)));
+    SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.df1, E, E), (const TS*)w.WfactT, E, Bi, D,
+                                EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));
+  }
   if (b.dropout_p > 0.0f) {       // InitLSTM dropout on the mean (model.py:78)
     dropout_bwd_kernel<<<(unsigned)(((int64_t)Bi * D + 255) / 256), 256, 0, st>>>(b.dmean, (int64_t)Bi * D, b.dropout_p, b.dropout_seed, 1u);
     SAT_COUNT_LAUNCH();

@@ -72,6 +72,9 @@ class TrainBuffers:
             t["dXe"] = mk((T, B, E), f)
             t["d_init_out"] = mk((Bi, 2 * H), f)
             t["df1"] = mk((Bi, E), f)
+            if dtype != torch.float32:
+                t["d_init_out16"] = mk((Bi, 2 * H), s)
+                t["df116"] = mk((Bi, E), s)
             t["dmean"] = mk((Bi, D), f)
             t["d_ann"] = mk((B, L, D), s)          # per caption row; the host sums the ncap rows of an image
         self.c = _lib.SatTrainBuffers()
