@@ -42,18 +42,21 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   BeamParams bp{k, V, S, b.tokEND, b.rescore, b.reward, S + 1};
   const int64_t hist_sz = (int64_t)R * (S + 1);
 
+  // k == 1 (greedy): a live row always continues from itself, so the post-LSTM state is used in place (buffer ping-pong)
+  // instead of being gathered by source row
+  void* h_cur = b.h; float* c_cur = b.c; void* h_nxt = b.hn; float* c_nxt = b.cn;
   for (int step = 0; step <= S; ++step) {
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.h, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
                              st)));
     SAT_PROF(1, st);
     SAT_TRY((launch_attention_fwd<TS, kExact>(ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, R, k, L, D, A, scale,
                                               b.alpha_all + (int64_t)step * R * L, L, nullptr, (TS*)b.z, (TS*)b.gz,
                                               (TS*)nullptr, D, st)));
     SAT_PROF(1, st);
-    EpiLstm<TS, kExact> epi{b.GxV, 4 * H, b.hp + A + D, NH3, (const TS*)b.h, b.c, (TS*)b.hn, b.cn, H, H,
+    EpiLstm<TS, kExact> epi{b.GxV, 4 * H, b.hp + A + D, NH3, (const TS*)h_cur, c_cur, (TS*)h_nxt, c_nxt, H, H,
                             (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.gz, D, D), (const TS*)w.Wihz, D, R, 4 * H, epi, st)));
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(b.hn, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(h_nxt, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
                              EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok, d.plain_output, 0.0f, 0ull, 0}, st)));
     SAT_PROF(3, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
@@ -69,9 +72,15 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
                             b.tok_hist + out * hist_sz, b.asrc_hist + out * hist_sz, b.fin_tokens, b.fin_asrc, b.fin_len, b.fin_score,
                             b.fin_ppl, b.fin_count));
     SAT_COUNT_LAUNCH();
-    SAT_CUDA(sat_launch_pdl(gather_state_kernel<TS>, dim3((unsigned)(((int64_t)R * H + 255) / 256)), dim3(256), 0, st, (const TS*)b.hn,
-                            (const float*)b.cn, (const int32_t*)b.src_row, (const int32_t*)b.alive, (TS*)b.h, b.c, R, H));
-    SAT_COUNT_LAUNCH();
+    if (k == 1) {
+      void* th = h_cur; h_cur = h_nxt; h_nxt = th;
+      float* tcp = c_cur; c_cur = c_nxt; c_nxt = tcp;
+    } else {
+      SAT_CUDA(sat_launch_pdl(gather_state_kernel<TS>, dim3((unsigned)(((int64_t)R * H + 255) / 256)), dim3(256), 0, st,
+                              (const TS*)b.hn, (const float*)b.cn, (const int32_t*)b.src_row, (const int32_t*)b.alive, (TS*)b.h, b.c, R,
+                              H));
+      SAT_COUNT_LAUNCH();
+    }
   }
   return 0;
 }

@@ -422,34 +422,39 @@ static __global__ void ntok_kernel(const int32_t* __restrict__ lens, int B, floa
 }
 
 // S[b,l] = sum_t alphas[b,t,l]                                                  model.py:594
-static __global__ void alpha_sum_kernel(const float* __restrict__ alphas, float* __restrict__ S, int B, int T_, int L) {
+// also writes the CTA's partial of sum (1-S)^2 so that the final reduction touches gridDim.x values instead of B*L
+static __global__ void __launch_bounds__(256)
+alpha_sum_kernel(const float* __restrict__ alphas, float* __restrict__ S, float* __restrict__ reg_part, int B, int T_, int L) {
+  __shared__ float scratch[33];
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)B * L) return;
-  const int64_t b = idx / L;
-  const int l = (int)(idx - b * L);
-  float s = 0.0f;
-  for (int t = 0; t < T_; ++t) s += alphas[(b * T_ + t) * L + l];
-  S[idx] = s;
+  float r = 0.0f;
+  if (idx < (int64_t)B * L) {
+    const int64_t b = idx / L;
+    const int l = (int)(idx - b * L);
+    float s = 0.0f;
+    for (int t = 0; t < T_; ++t) s += alphas[(b * T_ + t) * L + l];
+    S[idx] = s;
+    r = (1.0f - s) * (1.0f - s);
+  }
+  r = block_sum(r, scratch);
+  if (threadIdx.x == 0) reg_part[blockIdx.x] = r;
 }
 
 // loss = mean_tok(row_loss) + gamma * mean_{b,l} (1-S)^2 ; accuracy.  Single CTA, fixed summation order.
 static __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_argmax,
-                     const int32_t* __restrict__ caps, const int32_t* __restrict__ lens, const float* __restrict__ S,
-                     int B, int T_, int L, int caplen, float gamma, float* __restrict__ out) {
+                     const int32_t* __restrict__ tok_next, const int32_t* __restrict__ lens, const float* __restrict__ reg_part,
+                     int nparts, int B, int T_, int L, int caplen, float gamma, float* __restrict__ out) {
   __shared__ float scratch[33];
   float ce = 0.0f, hit = 0.0f, reg = 0.0f;
   for (int m = threadIdx.x; m < B * T_; m += blockDim.x) {
     const int t = m / B, b = m - t * B;
     if (t < lens[b]) {
       ce += row_loss[m];
-      hit += (row_argmax[m] == caps[(int64_t)b * caplen + t + 1]) ? 1.0f : 0.0f;
+      hit += (row_argmax[m] == tok_next[(int64_t)b * caplen + t + 1]) ? 1.0f : 0.0f;
     }
   }
-  for (int i = threadIdx.x; i < B * L; i += blockDim.x) {
-    const float d = 1.0f - S[i];
-    reg = fmaf(d, d, reg);
-  }
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) reg += reg_part[i];
   ce = block_sum(ce, scratch);
   hit = block_sum(hit, scratch);
   reg = block_sum(reg, scratch);

@@ -138,9 +138,12 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   }
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
-  alpha_sum_kernel<<<(B * L + 255) / 256, 256, 0, st>>>(b.alphas, b.S, B, T, L);
+  // per-CTA partials of sum (1-S)^2 live in the (by now dead) hp scratch buffer
+  const int nparts = (B * L + 255) / 256;
+  SAT_REQUIRE((int64_t)nparts <= (int64_t)B * NH3, "reduction scratch too small");
+  alpha_sum_kernel<<<nparts, 256, 0, st>>>(b.alphas, b.S, b.hp, B, T, L);
   SAT_COUNT_LAUNCH();
-  loss_finalize_kernel<<<1, 1024, 0, st>>>(b.row_loss, b.row_argmax, b.caps, b.lens, b.S, B, T, L, caplen, b.att_gamma, b.out);
+  loss_finalize_kernel<<<1, 1024, 0, st>>>(b.row_loss, b.row_argmax, b.caps, b.lens, b.hp, nparts, B, T, L, caplen, b.att_gamma, b.out);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   (void)Bi;
