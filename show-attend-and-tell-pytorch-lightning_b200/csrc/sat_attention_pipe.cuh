@@ -79,8 +79,10 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32, ATTP_THREADS = CW * 32 + 32;
+  // Programmatic dependent launch: ann, P and lens are never written inside a launch chain (P's GEMM is always followed
+  // by a fully serialised launch), so the ring is primed while the predecessor kernel is still draining; everything that
+  // reads the predecessor's output (or writes) sits behind SAT_PDL_WAIT() on the consumer side.
   SAT_PDL_TRIGGER();
-  SAT_PDL_WAIT();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
@@ -99,6 +101,7 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   const bool active = lens == nullptr || t < lens[b];
   float* alpha_b = alpha + (int64_t)b * ld_alpha;
   if (!active) {
+    SAT_PDL_WAIT();
     for (int l = tid; l < L; l += ATTP_THREADS) alpha_b[l] = 0.0f;
     for (int d = tid; d < D; d += ATTP_THREADS) {
       z[(int64_t)b * ld_z + d] = from_f<T>(0.f);
@@ -120,13 +123,6 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  const float* hp_b = hp + (int64_t)b * ldhp;
-  for (int a = tid; a < A; a += ATTP_THREADS) {
-    const float q = hp_b[a];
-    qs[a] = q;
-    ws[a] = wf[a];
-    if (qsave) qsave[(int64_t)b * A + a] = q;
   }
   __syncthreads();
 
@@ -158,6 +154,15 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   }
 
   // ===== consumers (256 threads, named barrier 1) =====
+  SAT_PDL_WAIT();
+  const float* hp_b = hp + (int64_t)b * ldhp;
+  for (int a = tid; a < A; a += ATTP_CONSUMERS) {
+    const float q = hp_b[a];
+    qs[a] = q;
+    ws[a] = wf[a];
+    if (qsave) qsave[(int64_t)b * A + a] = q;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
   // beta_pre of the columns this thread finalises is fetched now, long before it is needed
   float bpre[8];
 #pragma unroll
@@ -372,6 +377,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
 //   Same math and summation structure per row as attention_step_bwd_kernel (kept as the fallback).
 // =============================================================================================
 constexpr int ATTB_VPL = 4;      // 16-byte annotation vectors per lane kept in registers (D <= 1024 bf16 / 512 fp32)
+constexpr int ATTB_RPW = 6;      // dP rows per warp in flight in phase D (a 64-row P stage over 12 warps)
 
 template <typename T, bool kExact, int CW>
 __global__ void __launch_bounds__(CW * 32 + 32, 2)      // two CTAs per SM: all B=256 captions resident in one wave
@@ -386,13 +392,12 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32, ATTP_THREADS = CW * 32 + 32;
-  SAT_PDL_TRIGGER();
-  SAT_PDL_WAIT();
+  SAT_PDL_TRIGGER();      // as in the forward kernel: the producer primes the ring before SAT_PDL_WAIT()
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
   const int L4 = (L + 3) & ~3;
-  float* dal = reinterpret_cast<float*>(smem_raw + sizeof(AttPipeSmem));   // [L4] dalpha, then de
+  float* dal = reinterpret_cast<float*>(smem_raw + sizeof(AttPipeSmem));   // [L4] regulariser term, then dalpha, then de
   float* als = dal + L4;                // [L4] alpha of this row
   float* dz_s = als + L4;               // [D]
   float* qs = dz_s + D;                 // [A]
@@ -404,6 +409,7 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
 
   T* dy_b = DY_t + (int64_t)b * ld_dy;
   if (t >= lens[b]) {
+    SAT_PDL_WAIT();
     for (int i = tid; i < A + D; i += ATTP_THREADS) dy_b[i] = from_f<T>(0.f);
     for (int d = tid; d < D; d += ATTP_THREADS) dZ_t[(int64_t)b * D + d] = from_f<T>(0.f);
     for (int a = tid; a < A; a += ATTP_THREADS) dwf_t[(int64_t)b * A + a] = 0.0f;
@@ -450,24 +456,37 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   }
 
   // ===== consumers =====
+  SAT_PDL_WAIT();
   const float g = gscale ? *gscale : 1.0f;
   const float* alpha_b = alpha + (int64_t)b * ld_alpha;
-  // phase A
-  for (int d = tid; d < D; d += ATTP_CONSUMERS) {
-    float dg = 0.0f;
-    for (int sp = 0; sp < ns_dgz; ++sp) dg += dgz[(int64_t)sp * dgz_stride + (int64_t)b * D + d];
-    const float bt = to_f(beta_t[(int64_t)b * D + d]);
-    const float zz = to_f(z_t[(int64_t)b * D + d]);
-    const float dzv = dZout[(int64_t)b * ld_dzout + d] + dg * bt;
-    dz_s[d] = dzv;
-    dZ_t[(int64_t)b * D + d] = from_f<T>(dzv);
-    dy_b[A + d] = from_f<T>(dg * zz * bt * (1.0f - bt));
+  // phase A: every global load of this phase is issued up front (4 columns per thread, one latency), and the
+  // per-location additive terms of dalpha (regulariser, external grad) are staged in dal[] so that phase B is pure smem
+  const float regc = g * gamma * (-2.0f) / ((float)B * (float)L);
+  for (int d4 = tid * 4; d4 < D; d4 += ATTP_CONSUMERS * 4) {
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < ns_dgz; ++sp) {
+      const float4 p4 = *reinterpret_cast<const float4*>(dgz + (int64_t)sp * dgz_stride + (int64_t)b * D + d4);
+      dg.x += p4.x; dg.y += p4.y; dg.z += p4.z; dg.w += p4.w;
+    }
+    const float4 bt = ld4(beta_t + (int64_t)b * D + d4);
+    const float4 zz = ld4(z_t + (int64_t)b * D + d4);
+    const float4 dzo = *reinterpret_cast<const float4*>(dZout + (int64_t)b * ld_dzout + d4);
+    const float4 dzv = make_float4(dzo.x + dg.x * bt.x, dzo.y + dg.y * bt.y, dzo.z + dg.z * bt.z, dzo.w + dg.w * bt.w);
+    *reinterpret_cast<float4*>(dz_s + d4) = dzv;
+    st4(dZ_t + (int64_t)b * D + d4, dzv);
+    st4(dy_b + A + d4, make_float4(dg.x * zz.x * bt.x * (1.0f - bt.x), dg.y * zz.y * bt.y * (1.0f - bt.y),
+                                   dg.z * zz.z * bt.z * (1.0f - bt.z), dg.w * zz.w * bt.w * (1.0f - bt.w)));
   }
   for (int a = tid; a < A; a += ATTP_CONSUMERS) {
     qs[a] = q_t[(int64_t)b * A + a];
     ws[a] = wf[a];
   }
-  for (int l = tid; l < L; l += ATTP_CONSUMERS) als[l] = alpha_b[l];
+  for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+    als[l] = alpha_b[l];
+    float extra = regc * (1.0f - S[(int64_t)b * L + l]);
+    if (dalpha_ext) extra += dalpha_ext[(int64_t)b * ld_alpha + l];
+    dal[l] = extra;
+  }
   sat_named_bar(1, ATTP_CONSUMERS);
 
   // phase B: dalpha from the annotation stages (one warp per row, lanes over 16-byte vectors of the row)
@@ -482,7 +501,6 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
       for (int i = 0; i < VN; ++i) dzr[k][i] = cv < NV ? dz_s[cv * VN + i] : 0.0f;
     }
   }
-  const float regc = g * gamma * (-2.0f) / ((float)B * (float)L);
   int it = 0;
   for (int j = 0; j < nA; ++j, ++it) {
     const int st = it % ATTP_NST;
@@ -511,12 +529,7 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
         }
       }
       s = warp_sum(s);
-      if (lane == 0) {
-        const int gl = r0 + l;
-        float v = s + regc * (1.0f - S[(int64_t)b * L + gl]);
-        if (dalpha_ext) v += dalpha_ext[(int64_t)b * ld_alpha + gl];
-        dal[gl] = v;
-      }
+      if (lane == 0) dal[r0 + l] += s;
     }
     __syncwarp();
     if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
@@ -554,19 +567,19 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
     const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
     const int r0 = j * RCP, rows = min(RCP, L - r0);
-    for (int l0 = warp; l0 < rows; l0 += 4 * ATTP_CWARPS) {
+    for (int l0 = warp; l0 < rows; l0 += ATTB_RPW * ATTP_CWARPS) {
 #pragma unroll
       for (int k = 0; k < ATTP_KA; ++k) {
         const int a = lane * 4 + 128 * k;
         if (a < A) {
-          float4 acc4[4];
+          float4 acc4[ATTB_RPW];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {          // 4 rows of dP in flight before any dependent math
+          for (int u = 0; u < ATTB_RPW; ++u) {   // all dP rows of this warp in flight before any dependent math
             const int l = l0 + u * ATTP_CWARPS;
             acc4[u] = l < rows ? *reinterpret_cast<const float4*>(dPb + (int64_t)(r0 + l) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < ATTB_RPW; ++u) {
             const int l = l0 + u * ATTP_CWARPS;
             if (l < rows) {
               const float de = dal[r0 + l];

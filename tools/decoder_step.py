@@ -15,6 +15,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--no-tc", action="store_true")
 ap.add_argument("--decode", type=int, default=0, help="run batched decode with this beam width instead of training")
+ap.add_argument("--profile", type=int, default=0, help="also report the in-situ per-launch time of kernel kind 1 (att fwd) / 2 (att bwd) / 3 (vocab GEMM)")
 args = ap.parse_args()
 
 from oracle import sat_oracle as O  # noqa: E402  (weights generator only)
@@ -53,5 +54,14 @@ else:
         ev1.record()
         torch.cuda.synchronize()
         times.append(ev0.elapsed_time(ev1))
+    if args.profile:
+        from sat_b200 import _lib
+        _lib.profile_begin(args.profile)
+        for it in range(3):
+            buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True)
+            G, d_ann = decoder.train_backward(pw, buf)
+        torch.cuda.synchronize()
+        ms, n = _lib.profile_end()
+        print("kind %d: %d launches, %.2f us per launch" % (args.profile, n, 1e3 * ms / max(n, 1)))
     times = sorted(times[2:] or times)
     print("train fwd+bwd B=%d: median %.3f ms (min %.3f) over %d iters  loss %.4f" % (B, times[len(times) // 2], times[0], len(times), float(buf.t["out"][0])))
