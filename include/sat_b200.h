@@ -149,6 +149,8 @@ typedef struct SatTrainBuffers {
   float* dann_tmp;       /* [B,L,D]      fp32 scratch of the tensor-core d_ann path (alpha (x) dz + mean term); may be
                                          NULL in fp32 mode                                                    */
   float* dwf_part;       /* [T,B,A]      per-(b,t) partial of d f_att.weight                       */
+  float* de;             /* [T,B,L]      scaled softmax-backward term of each step; dP is rebuilt from it, Q and P
+                                          after the time loop (NULL: the slower step-by-step accumulation is used)  */
   float* dXe;            /* [T,B,E]      grad wrt embedded words                                   */
   float* d_init_out;     /* [Bi,2H]                                                               */
   float* df1;            /* [Bi,E]                                                                */

@@ -34,7 +34,7 @@ class SatTrainBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "caps", "lens", "sampled", "tok", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
                  "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
-                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dann_tmp", "dwf_part", "dXe", "d_init_out",
+                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dann_tmp", "dwf_part", "de", "dXe", "d_init_out",
                  "df1", "d_init_out16", "df116", "dmean", "d_ann")] + \
                [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("dropout_p", C.c_float),
                 ("emb_dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("logits_f32", C.c_int32),

@@ -377,7 +377,6 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
 //   Same math and summation structure per row as attention_step_bwd_kernel (kept as the fallback).
 // =============================================================================================
 constexpr int ATTB_VPL = 4;      // 16-byte annotation vectors per lane kept in registers (D <= 1024 bf16 / 512 fp32)
-constexpr int ATTB_RPW = 6;      // dP rows per warp in flight in phase D (a 64-row P stage over 12 warps)
 
 template <typename T, bool kExact, int CW>
 __global__ void __launch_bounds__(CW * 32 + 32, 2)      // two CTAs per SM: all B=256 captions resident in one wave
@@ -388,7 +387,7 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
                                int64_t ld_dzout, const int32_t* __restrict__ lens, int t, int ncap, int B, int L, int D, int A,
                                float scale, float gamma, const float* __restrict__ gscale,
                                const float* __restrict__ dalpha_ext, float* __restrict__ dP, T* __restrict__ dP16,
-                               T* __restrict__ dZ_t, T* __restrict__ DY_t, int64_t ld_dy, float* __restrict__ dwf_t) {
+                               T* __restrict__ dZ_t, T* __restrict__ DY_t, int64_t ld_dy, float* __restrict__ dwf_t, float* __restrict__ de_t) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32, ATTP_THREADS = CW * 32 + 32;
@@ -464,9 +463,14 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   const float regc = g * gamma * (-2.0f) / ((float)B * (float)L);
   for (int d4 = tid * 4; d4 < D; d4 += ATTP_CONSUMERS * 4) {
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int sp = 0; sp < ns_dgz; ++sp) {
-      const float4 p4 = *reinterpret_cast<const float4*>(dgz + (int64_t)sp * dgz_stride + (int64_t)b * D + d4);
-      dg.x += p4.x; dg.y += p4.y; dg.z += p4.z; dg.w += p4.w;
+    for (int sp0 = 0; sp0 < ns_dgz; sp0 += 8) {      // split-K partials: 8 independent loads in flight, then the adds
+      float4 p4[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        p4[u] = (sp0 + u) < ns_dgz ? *reinterpret_cast<const float4*>(dgz + (int64_t)(sp0 + u) * dgz_stride + (int64_t)b * D + d4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { dg.x += p4[u].x; dg.y += p4[u].y; dg.z += p4[u].z; dg.w += p4[u].w; }
     }
     const float4 bt = ld4(beta_t + (int64_t)b * D + d4);
     const float4 zz = ld4(z_t + (int64_t)b * D + d4);
@@ -544,7 +548,11 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   dot = 0.0f;
 #pragma unroll
   for (int w2 = 0; w2 < ATTP_CWARPS; ++w2) dot += hd->red_a[w2];
-  for (int l = tid; l < L; l += ATTP_CONSUMERS) dal[l] = als[l] * (dal[l] - dot) * scale;   // de_l * scale
+  for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+    const float de = als[l] * (dal[l] - dot) * scale;   // de_l * scale
+    dal[l] = de;
+    de_t[(int64_t)b * L + l] = de;      // kept for the deferred dP pass (dP_deferred_kernel)
+  }
   sat_named_bar(1, ATTP_CONSUMERS);
 
   // phase D: through tanh into P, q, wf (lane owns attention columns lane*4 + 128k)
@@ -560,44 +568,34 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
       dw[k][i] = 0.0f;
     }
   }
-  float* dPb = dP + (int64_t)b * L * A;
-  const bool last = dP16 != nullptr && t == 0;
+  // (dP itself is not touched here: it is rebuilt after the time loop from the saved de_t and q_t, which removes a
+  //  2 x B*L*A*4-byte read-modify-write per step)
   for (int j = 0; j < nP; ++j, ++it) {
     const int st = it % ATTP_NST;
     sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
     const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
     const int r0 = j * RCP, rows = min(RCP, L - r0);
-    for (int l0 = warp; l0 < rows; l0 += ATTB_RPW * ATTP_CWARPS) {
+    for (int l0 = warp * 4; l0 < rows; l0 += ATTP_CWARPS * 4) {      // 4 rows in flight per warp
 #pragma unroll
       for (int k = 0; k < ATTP_KA; ++k) {
         const int a = lane * 4 + 128 * k;
         if (a < A) {
-          float4 acc4[ATTB_RPW];
+          float4 p[4];
+          float de[4];
 #pragma unroll
-          for (int u = 0; u < ATTB_RPW; ++u) {   // all dP rows of this warp in flight before any dependent math
-            const int l = l0 + u * ATTP_CWARPS;
-            acc4[u] = l < rows ? *reinterpret_cast<const float4*>(dPb + (int64_t)(r0 + l) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = (l0 + u) < rows;
+            p[u] = ok ? ld4(Ps + (size_t)(l0 + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+            de[u] = ok ? dal[r0 + l0 + u] : 0.0f;
           }
 #pragma unroll
-          for (int u = 0; u < ATTB_RPW; ++u) {
-            const int l = l0 + u * ATTP_CWARPS;
-            if (l < rows) {
-              const float de = dal[r0 + l];
-              const float4 p = ld4(Ps + (size_t)l * A + a);
-              const float pv[4] = {p.x, p.y, p.z, p.w};
-              float o[4];
+          for (int u = 0; u < 4; ++u) {
+            const float pv[4] = {p[u].x, p[u].y, p[u].z, p[u].w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float uu = sat_tanh<kExact>(pv[i] + qreg[k][i]);
-                const float dpu = de * wreg[k][i] * (1.0f - uu * uu);
-                o[i] = dpu;
-                dq[k][i] += dpu;
-                dw[k][i] = fmaf(de, uu, dw[k][i]);
-              }
-              float4 r = acc4[u];
-              r.x += o[0]; r.y += o[1]; r.z += o[2]; r.w += o[3];
-              *reinterpret_cast<float4*>(dPb + (int64_t)(r0 + l) * A + a) = r;
-              if (last) st4(dP16 + ((int64_t)b * L + r0 + l) * A + a, r);
+            for (int i = 0; i < 4; ++i) {
+              const float uu = sat_tanh<kExact>(pv[i] + qreg[k][i]);
+              dq[k][i] = fmaf(de[u] * wreg[k][i], 1.0f - uu * uu, dq[k][i]);
+              dw[k][i] = fmaf(de[u], uu, dw[k][i]);
             }
           }
         }
@@ -624,6 +622,67 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     for (int w2 = 0; w2 < ATTP_CWARPS; ++w2) { sq += red[w2 * 2 * A + a]; sw += red[w2 * 2 * A + A + a]; }
     dy_b[a] = from_f<T>(sq);
     dwf_t[(int64_t)b * A + a] = sw;
+  }
+}
+
+// dP[b,l,a] = sum_t de[t,b,l] * w_f[a] * (1 - tanh^2(P[img,l,a] + q[t,b,a])), t = lens[b]-1 .. 0: the grad wrt the
+// per-image projection P, rebuilt once after the time loop (model.py:100-104 under autograd).  One CTA per (row tile,
+// caption): q[:,b,:] and de[:,b,tile] are staged in smem, every warp walks 4 rows at a time, a lane owns 4 columns.
+constexpr int DPD_ROWS = 32;
+template <typename T, bool kExact>
+__global__ void __launch_bounds__(256)
+dP_deferred_kernel(const T* __restrict__ P, const float* __restrict__ wf, const float* __restrict__ Q,
+                   const float* __restrict__ de, const int32_t* __restrict__ lens, int ncap, int B, int L, int A,
+                   float* __restrict__ dP, T* __restrict__ dP16) {
+  extern __shared__ __align__(16) float dpd_smem[];
+  const int b = blockIdx.y, r0 = blockIdx.x * DPD_ROWS, rows = min(DPD_ROWS, L - r0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Tb = lens[b];
+  float* qs = dpd_smem;                       // [Tb][A]
+  float* des = qs + (size_t)Tb * A;           // [Tb][DPD_ROWS]
+  for (int i = tid; i < Tb * A; i += 256) qs[i] = Q[((int64_t)(i / A) * B + b) * A + (i % A)];
+  for (int i = tid; i < Tb * DPD_ROWS; i += 256) {
+    const int t = i / DPD_ROWS, l = i % DPD_ROWS;
+    des[i] = l < rows ? de[((int64_t)t * B + b) * L + r0 + l] : 0.0f;
+  }
+  __syncthreads();
+  const T* Pb = P + ((int64_t)(b / ncap) * L + r0) * A;
+  const int l0 = warp * 4;
+  if (l0 >= rows) return;
+  for (int a = lane * 4; a < A; a += 128) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wf + a);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    float pv[4][4], acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 p = (l0 + u) < rows ? ld4(Pb + (size_t)(l0 + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pv[u][0] = p.x; pv[u][1] = p.y; pv[u][2] = p.z; pv[u][3] = p.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[u][i] = 0.0f;
+    }
+    for (int t = Tb - 1; t >= 0; --t) {
+      const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)t * A + a);
+      const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+      const float4 d4 = *reinterpret_cast<const float4*>(des + (size_t)t * DPD_ROWS + l0);
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float uu = sat_tanh<kExact>(pv[u][i] + qv[i]);
+          acc[u][i] += dv[u] * wv[i] * (1.0f - uu * uu);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if ((l0 + u) < rows) {
+        const float4 r = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        const int64_t o = ((int64_t)b * L + r0 + l0 + u) * A + a;
+        *reinterpret_cast<float4*>(dP + o) = r;
+        if (dP16) st4(dP16 + o, r);
+      }
+    }
   }
 }
 

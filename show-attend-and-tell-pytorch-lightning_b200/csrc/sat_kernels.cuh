@@ -524,7 +524,7 @@ attention_step_bwd_kernel(const T* __restrict__ ann, const T* __restrict__ P, co
                           const int32_t* __restrict__ lens, int t, int ncap, int B, int L, int D, int A, float scale,
                           float gamma, const float* __restrict__ gscale, const float* __restrict__ dalpha_ext,
                           float* __restrict__ dP, T* __restrict__ dP16, T* __restrict__ dZ_t,
-                          T* __restrict__ DY_t, int64_t ld_dy, float* __restrict__ dwf_t) {
+                          T* __restrict__ DY_t, int64_t ld_dy, float* __restrict__ dwf_t, float* /*de_t: pipelined kernel only*/) {
   extern __shared__ __align__(16) float smem[];
   constexpr int VN = Vec16<T>::N;
   constexpr int NW = ATT_THREADS / 32;

@@ -35,12 +35,15 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   const int sk_dh = tc_dh ? tc::pick_splitk(B, H, NH3_) : 1;
   SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)sk_dh * B * H, st));
   SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)B * H, st));
-  SAT_CUDA(cudaMemsetAsync(b.dP, 0, sizeof(float) * (size_t)B * L * A, st));
   const bool dann_tc = tc && b.dP16 != nullptr && b.dann_tmp != nullptr && !std::is_same<TS, float>::value;
-  if (dann_tc) SAT_CUDA(cudaMemsetAsync(b.dP16, 0, sizeof(TS) * (size_t)B * L * A, st));
-
   const float scale = (float)(1.0 / sqrt((double)L));
-  const bool att_pipe = attention_bwd_pipe_ok<TS>(D, A);
+  // pipelined attention backward: saves de_t per step and dP is rebuilt once after the loop (dP_deferred_kernel);
+  // the plain kernel accumulates dP step by step and needs it zeroed
+  const bool att_pipe = attention_bwd_pipe_ok<TS>(D, A) && b.de != nullptr && A % 4 == 0;
+  if (!att_pipe) {
+    SAT_CUDA(cudaMemsetAsync(b.dP, 0, sizeof(float) * (size_t)B * L * A, st));
+    if (dann_tc) SAT_CUDA(cudaMemsetAsync(b.dP16, 0, sizeof(TS) * (size_t)B * L * A, st));
+  }
   const size_t att_smem = att_pipe ? attention_bwd_pipe_smem(L, D, A) : attention_bwd_smem(L, D, A);
   auto att_k = att_pipe ? attention_step_bwd_pipe_kernel<TS, kExact, ATTP_BWD_CW> : attention_step_bwd_kernel<TS, kExact>;
   const int att_threads = att_pipe ? ATTP_BWD_CW * 32 + 32 : ATT_THREADS;
@@ -63,7 +66,8 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
                                             t, d.ncap,
                                             B, L, D, A, scale, b.att_gamma, b.gscale,
                                             b.dalpha_ext ? b.dalpha_ext + (int64_t)t * L : nullptr, b.dP, dann_tc ? (TS*)b.dP16 : (TS*)nullptr, (TS*)b.dZ + (int64_t)t * B * D,
-                                            DY_t, NH3, b.dwf_part + (int64_t)t * B * A));
+                                            DY_t, NH3, b.dwf_part + (int64_t)t * B * A,
+                                            b.de ? b.de + (int64_t)t * B * L : (float*)nullptr));
     SAT_PROF(2, st);
     SAT_COUNT_LAUNCH();
     // dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (rows inactive at t keep their dh)
@@ -72,6 +76,15 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
                              EpiStore<float>{b.dh, H, nullptr, nullptr, 0, (int64_t)B * H}, st, sk_dh)));
   }
 
+  if (att_pipe) {
+    const size_t sm = sizeof(float) * (size_t)T * (A + DPD_ROWS);
+    auto kp = dP_deferred_kernel<TS, kExact>;
+    if (sm > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kp<<<dim3((L + DPD_ROWS - 1) / DPD_ROWS, B), 256, sm, st>>>((const TS*)b.P, w.wf, b.Q, b.de, b.lens, d.ncap, B, L, A, b.dP,
+                                                              dann_tc ? (TS*)b.dP16 : (TS*)nullptr);
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
+  }
   // dXe = dG * Wihe + dpre                               [M,E]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.DY + A + D, NH3, 4 * H), (const TS*)w.WiheT, 4 * H, M, E,
                            EpiStore<float, TS>{b.dXe, E, nullptr, d.plain_output ? (const TS*)nullptr : (const TS*)b.dpre, E}, st)));

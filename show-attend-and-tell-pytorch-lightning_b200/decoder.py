@@ -69,6 +69,7 @@ class TrainBuffers:
                 t["dP16"] = mk((B, L, A), s)
                 t["dann_tmp"] = mk((B, L, D), f)
             t["dwf_part"] = mk((T, B, A), f)
+            t["de"] = mk((T, B, L), f)
             t["dXe"] = mk((T, B, E), f)
             t["d_init_out"] = mk((Bi, 2 * H), f)
             t["df1"] = mk((Bi, E), f)
