@@ -376,6 +376,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
 //        dq = sum_l dpu, dwf partial
 //   Same math and summation structure per row as attention_step_bwd_kernel (kept as the fallback).
 // =============================================================================================
+constexpr int ATTB_MAXSEG = 4;   // column segments per annotation row (segmented phase B)
 constexpr int ATTB_VPL = 4;      // 16-byte annotation vectors per lane kept in registers (D <= 1024 bf16 / 512 fp32)
 
 template <typename T, bool kExact, int CW>
@@ -401,10 +402,11 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   float* dz_s = als + L4;               // [D]
   float* qs = dz_s + D;                 // [A]
   float* ws = qs + A;                   // [A]
-  float* red = ws + A;                  // [ATTP_CWARPS][2A]
+  float* dalp = ws + A;                 // [ATTB_MAXSEG][L4] per-column-segment partials (segmented phase B only)
   const uint32_t stage_off =
-      (uint32_t)((sizeof(AttPipeSmem) + sizeof(float) * (size_t)(2 * L4 + D + 2 * A + ATTP_CWARPS * 2 * A) + 127) & ~(size_t)127);
+      (uint32_t)((sizeof(AttPipeSmem) + sizeof(float) * (size_t)((2 + ATTB_MAXSEG) * L4 + D + 2 * A) + 127) & ~(size_t)127);
   uint8_t* stages = smem_raw + stage_off;
+  float* red = reinterpret_cast<float*>(stages);   // [ATTP_CWARPS][2A]: aliases the ring, used only after its last stage is drained
 
   T* dy_b = DY_t + (int64_t)b * ld_dy;
   if (t >= lens[b]) {
@@ -495,14 +497,30 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
 
   // phase B: dalpha from the annotation stages (one warp per row, lanes over 16-byte vectors of the row)
   const int NV = D / VN;
-  const bool regpath = NV <= 32 * ATTB_VPL;
+  // Short stages (rows of a stage < consumer warps) or rows longer than the register slice: split every row into nseg
+  // column segments so that (row, segment) items spread evenly over the warps; a warp always owns the same segment.
+  int seglen = 0, nseg = 1;
+  if (RCA < ATTP_CWARPS || NV > 32 * ATTB_VPL) {
+    int best = 1 << 30;
+    for (int c = 32; c <= 32 * ATTB_VPL; c += 32) {
+      const int ns = (NV + c - 1) / c;
+      if (ns > ATTB_MAXSEG || ATTP_CWARPS % ns != 0) continue;
+      const int cost = ((RCA * ns + ATTP_CWARPS - 1) / ATTP_CWARPS) * c;
+      if (cost <= best) { best = cost; seglen = c; nseg = ns; }
+    }
+  }
+  const bool segpath = seglen > 0;
+  const bool regpath = !segpath && NV <= 32 * ATTB_VPL;
+  const int seg = segpath ? warp % nseg : 0;
+  const int lw = warp / nseg, lstep = ATTP_CWARPS / nseg;     // segmented path: this warp's rows inside a stage
   float dzr[ATTB_VPL][VN];
-  if (regpath) {
+  if (regpath || segpath) {
 #pragma unroll
     for (int k = 0; k < ATTB_VPL; ++k) {
-      const int cv = lane + 32 * k;
+      const int cv = seg * seglen + lane + 32 * k;
+      const bool ok = cv < NV && (!segpath || 32 * k < seglen);
 #pragma unroll
-      for (int i = 0; i < VN; ++i) dzr[k][i] = cv < NV ? dz_s[cv * VN + i] : 0.0f;
+      for (int i = 0; i < VN; ++i) dzr[k][i] = ok ? dz_s[cv * VN + i] : 0.0f;
     }
   }
   int it = 0;
@@ -511,6 +529,23 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
     const T* As = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
     const int r0 = j * RCA, rows = min(RCA, L - r0);
+    if (segpath) {
+      for (int l = lw; l < rows; l += lstep) {
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ATTB_VPL; ++k) {
+          const int cv = seg * seglen + lane + 32 * k;
+          if (32 * k < seglen && cv < NV) {
+            float v[VN];
+            Vec16<T>::load_shared(As + (size_t)l * D + cv * VN, v);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) s = fmaf(v[i], dzr[k][i], s);
+          }
+        }
+        s = warp_sum(s);
+        if (lane == 0) dalp[seg * L4 + r0 + l] = s;
+      }
+    } else
     for (int l = warp; l < rows; l += ATTP_CWARPS) {
       float s = 0.0f;
       if (regpath) {
@@ -539,6 +574,13 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
   }
   sat_named_bar(1, ATTP_CONSUMERS);
+  if (segpath) {
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) {      // same thread -> location mapping as the loops below
+      float v = dal[l];
+      for (int sg = 0; sg < nseg; ++sg) v += dalp[sg * L4 + l];
+      dal[l] = v;
+    }
+  }
   // phase C: softmax backward
   float dot = 0.0f;
   for (int l = tid; l < L; l += ATTP_CONSUMERS) dot = fmaf(als[l], dal[l], dot);
@@ -604,6 +646,7 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
     __syncwarp();
     if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
   }
+  sat_named_bar(1, ATTP_CONSUMERS);     // every warp is done reading the ring before red[] overwrites it
 #pragma unroll
   for (int k = 0; k < ATTP_KA; ++k) {
     const int a = lane * 4 + 128 * k;
@@ -688,7 +731,7 @@ dP_deferred_kernel(const T* __restrict__ P, const float* __restrict__ wf, const 
 
 static inline size_t attention_bwd_pipe_smem(int L, int D, int A) {
   const int L4 = (L + 3) & ~3;
-  return ((sizeof(AttPipeSmem) + sizeof(float) * (size_t)(2 * L4 + D + 2 * A + ATTP_BWD_CW * 2 * A) + 127) & ~(size_t)127) + 128 +
+  return ((sizeof(AttPipeSmem) + sizeof(float) * (size_t)((2 + ATTB_MAXSEG) * L4 + D + 2 * A) + 127) & ~(size_t)127) + 128 +
          (size_t)ATTP_NST * ATTP_STAGE_BYTES;
 }
 

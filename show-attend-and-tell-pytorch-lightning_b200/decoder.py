@@ -178,21 +178,27 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
     G["attention.decoder_att.weight"] = dWh3[:A]
     G["beta.0.weight"] = dWh3[A:A + D]
     G["lstm.weight_hh_l0"] = deinterleave_gates(dWh3[A + D:])
-    G["beta.0.bias"] = DY[:, A:A + D].sum(0, dtype=torch.float32)
+    dy_sum = DY.sum(0, dtype=torch.float32)       # one pass over DY for both bias gradients
+    G["beta.0.bias"] = dy_sum[A:A + D]
     dG = DY[:, A + D:]
     dWihe = _mm_tn(dG, t["Xe"].reshape(M, E))
     dWihz = _mm_tn(dG, t["GZ"].reshape(M, D))
     G["lstm.weight_ih_l0"] = deinterleave_gates(torch.cat([dWihe, dWihz], 1))
-    db = deinterleave_gates(dG.sum(0, dtype=torch.float32))
+    db = deinterleave_gates(dy_sum[A + D:])
     G["lstm.bias_ih_l0"] = db
     G["lstm.bias_hh_l0"] = db.clone()
     G["attention.f_att.weight"] = t["dwf_part"].sum((0, 1)).reshape(1, A)
-    dP = t["dP"]
-    if ncap > 1:
-        dP = dP.reshape(Bi, ncap, L, A).sum(1)
     ann = t["ann"].reshape(Bi * L, D)
-    dPm = dP.reshape(Bi * L, A)
-    G["attention.encoder_att.weight"] = _mm_tn(dPm if ann.dtype == torch.float32 else dPm.to(ann.dtype), ann)
+    if ncap == 1 and d.use_tc and "dP16" in t and "dann_tmp" in t and ann.dtype != torch.float32:
+        dPm = t["dP16"].reshape(Bi * L, A)      # operand-dtype copy already written by the kernels
+    else:
+        dP = t["dP"]
+        if ncap > 1:
+            dP = dP.reshape(Bi, ncap, L, A).sum(1)
+        dPm = dP.reshape(Bi * L, A)
+        if ann.dtype != torch.float32:
+            dPm = dPm.to(ann.dtype)
+    G["attention.encoder_att.weight"] = _mm_tn(dPm, ann)
     dio = t["d_init_out"]
     G["init_lstm.init.weight"] = _mm_tn(dio, t["f1"].float())
     G["init_lstm.init.bias"] = dio.sum(0)

@@ -15,6 +15,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--no-tc", action="store_true")
 ap.add_argument("--decode", type=int, default=0, help="run batched decode with this beam width instead of training")
+ap.add_argument("--dims", type=str, default="", help="D,A,E,H,V,T,L override, e.g. 2048,128,256,1024,6400,20,196 (configs[2])")
 ap.add_argument("--profile", type=int, default=0, help="also report the in-situ per-launch time of kernel kind 1 (att fwd) / 2 (att bwd) / 3 (vocab GEMM)")
 args = ap.parse_args()
 
@@ -23,6 +24,8 @@ from sat_b200 import decode, decoder  # noqa: E402
 from sat_b200.packing import PackedWeights  # noqa: E402
 
 D, A, E, H, V, T, L = 512, 128, 256, 512, 6400, 20, 196
+if args.dims:
+    D, A, E, H, V, T, L = (int(x) for x in args.dims.split(","))
 dtype = torch.float32 if args.fp32 else torch.bfloat16
 W = O.random_weights(D, A, E, H, V, seed=0)
 g = torch.Generator(device="cuda").manual_seed(0)
