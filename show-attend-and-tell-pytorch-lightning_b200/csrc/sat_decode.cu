@@ -37,8 +37,10 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
 
   const float scale = (float)(1.0 / sqrt((double)L));
   const size_t topk_smem = sizeof(float) * (size_t)(V + 40);
-  if (topk_smem > 48 * 1024)
-    SAT_CUDA(cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+  // candidate selection: threshold kernel (SAT_TOPK_MODE=0 forces the plain scan kernel for A/B runs)
+  static const int topk_mode = getenv("SAT_TOPK_MODE") ? atoi(getenv("SAT_TOPK_MODE")) : 1;
+  auto topk_k = (topk_mode == 0 || k == 1) ? row_topk_kernel : row_topk_thresh_kernel;      // greedy: one scan is already minimal
+  if (topk_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(topk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
   BeamParams bp{k, V, S, b.tokEND, b.rescore, b.reward, S + 1};
   const int64_t hist_sz = (int64_t)R * (S + 1);
 
@@ -61,7 +63,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     SAT_PROF(3, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
     SAT_PROF(3, st);
-    SAT_CUDA(sat_launch_pdl(row_topk_kernel, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
+    SAT_CUDA(sat_launch_pdl(topk_k, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
                             (const int32_t*)b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK, b.cand_val,
                             b.cand_idx));
     SAT_COUNT_LAUNCH();

@@ -99,6 +99,153 @@ row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_
   }
 }
 
+// Same selection without one block-wide scan per candidate.  While summing the exponentials every thread keeps the
+// maximum of its strided slice; the kk-th largest of those 256 maxima is a lower bound T of the kk-th largest entry of
+// the row, so one more pass collects the (few) entries >= T and warp 0 orders them.  Rows with more than TOPK_CAP
+// entries >= T (massive ties) take the scan of row_topk_kernel.  The statistics (max, sum of exponentials) are
+// accumulated in exactly the order of row_topk_kernel, so both kernels emit bit-identical candidates.  kk <= 32.
+constexpr int TOPK_CAP = 256;
+__device__ __forceinline__ bool topk_before(float av, int ai, float bv, int bi) { return av > bv || (av == bv && ai < bi); }
+
+__global__ void __launch_bounds__(256)
+row_topk_thresh_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur,
+                       int k, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
+                       float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
+  extern __shared__ __align__(16) float smem[];
+  float* x = smem;            // [V]  scaled logits, masked entries set to -inf after the softmax statistics
+  float* scratch = x + V;     // [33]
+  __shared__ float c_val[TOPK_CAP];     // thread maxima, then the candidates
+  __shared__ int c_idx[TOPK_CAP];
+  __shared__ float s_T;
+  __shared__ int s_cnt;
+  const int r = blockIdx.x, n = r / k, j = r - n * k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kc = kcur[n];
+  if (j >= kc) return;
+  if (step == 0 && j != 0) return;                    // step 0 looks at beam 0 only (model.py:343)
+  const float* row = logits + (int64_t)r * V;
+  const bool s0 = step == 0;
+  float mx = -INFINITY;
+  for (int v = tid * 4; v < V; v += 256 * 4) {
+    float4 q = *reinterpret_cast<const float4*>(row + v);
+    q.x = q.x / temp; q.y = q.y / temp; q.z = q.z / temp; q.w = q.w / temp;
+    *reinterpret_cast<float4*>(x + v) = q;
+    mx = fmaxf(fmaxf(mx, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+  }
+  mx = block_max(mx, scratch);
+  float se = 0.0f, tm = -INFINITY;
+  for (int v = tid; v < V; v += 256) {
+    float xv = x[v];
+    se += expf(xv - mx);
+    if (v == tokSTART || v == tokPAD || (s0 && (v == tokEND || v == tokUNK))) { xv = -INFINITY; x[v] = xv; }
+    tm = fmaxf(tm, xv);
+  }
+  c_val[tid] = tm;
+  if (tid == 0) s_cnt = 0;
+  se = block_sum(se, scratch);          // (its barriers also publish c_val / s_cnt)
+  const float lse = logf(se);
+  const float base = s0 ? 0.0f : top_scores[r];
+  const int kk = s0 ? k : kc;
+  if (warp == 0) {                      // T = kk-th largest thread maximum (with multiplicity)
+    float m8[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m8[u] = c_val[lane + 32 * u];
+    float T = -INFINITY;
+    for (int i = 0; i < kk; ++i) {
+      float lb = m8[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u) lb = fmaxf(lb, m8[u]);
+      const float wb = warp_max(lb);
+      T = wb;
+      const unsigned who = __ballot_sync(0xffffffffu, lb == wb);
+      if (lane == __ffs(who) - 1) {     // remove one instance
+        bool done = false;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (!done && m8[u] == wb) { m8[u] = -INFINITY; done = true; }
+      }
+    }
+    if (lane == 0) s_T = T;
+  }
+  __syncthreads();
+  const float T = s_T;
+  for (int v = tid; v < V; v += 256) {
+    const float xv = x[v];
+    if (xv >= T) {
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < TOPK_CAP) { c_val[pos] = xv; c_idx[pos] = v; }
+    }
+  }
+  __syncthreads();
+  const int nc = s_cnt;
+  if (nc <= TOPK_CAP) {
+    if (warp != 0) return;
+    float cv[8];
+    int ci[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = lane + 32 * u;
+      cv[u] = c < nc ? c_val[c] : -INFINITY;
+      ci[u] = c < nc ? c_idx[c] : 0x7fffffff;
+    }
+    for (int i = 0; i < kk; ++i) {
+      float lb = cv[0];
+      int li = ci[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u)
+        if (topk_before(cv[u], ci[u], lb, li)) { lb = cv[u]; li = ci[u]; }
+      float bv = lb;
+      int bi = li;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (topk_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (li == bi && bi != 0x7fffffff) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (ci[u] == bi) { cv[u] = -INFINITY; ci[u] = 0x7fffffff; }
+      }
+      if (lane == 0) {
+        const float lp = (bv - mx) - lse;                            // -inf stays -inf
+        cand_val[(int64_t)r * k + i] = s0 ? lp : lp + base;
+        cand_idx[(int64_t)r * k + i] = bi;
+      }
+    }
+    return;
+  }
+  // massive ties: block-wide scan per candidate (as row_topk_kernel)
+  float pv = INFINITY;
+  int pi = -1;
+  for (int i = 0; i < kk; ++i) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = tid; v < V; v += 256) {
+      const float xv = x[v];
+      const bool after = (xv < pv) || (xv == pv && v > pi);
+      if (after && topk_before(xv, v, bv, bi)) { bv = xv; bi = v; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (topk_before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { c_val[warp] = bv; c_idx[warp] = bi; }
+    __syncthreads();
+    bv = c_val[0]; bi = c_idx[0];
+    for (int w = 1; w < 8; ++w)
+      if (topk_before(c_val[w], c_idx[w], bv, bi)) { bv = c_val[w]; bi = c_idx[w]; }
+    if (tid == 0) {
+      const float lp = (bv - mx) - lse;
+      cand_val[(int64_t)r * k + i] = s0 ? lp : lp + base;
+      cand_idx[(int64_t)r * k + i] = bi;
+    }
+    pv = bv; pi = bi;
+  }
+}
+
 struct BeamParams {
   int k, V, S;                 // beam width, vocab, max_gen_length
   int tokEND;

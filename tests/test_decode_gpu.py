@@ -107,3 +107,22 @@ def test_decode_temperature_list_cycles_per_step():
     got = cuda_caption(W, ann, 3, max_len, temps, "WR")
     assert got[0] == ref[0]
     assert max(abs(x - y) for x, y in zip(got[1], ref[1])) < 1e-4
+
+
+@pytest.mark.parametrize("n_tied", [20, 390])
+def test_beam_candidates_with_tied_logits(n_tied):
+    """Tied logits: candidates are taken in (value desc, vocabulary index asc) order.  20 ties stay inside the
+    threshold kernel's candidate list, 390 overflow it and take the block-wide scan."""
+    D, A, E, H, V, k = 64, 32, 32, 64, 1024, 3
+    W = O.random_weights(D, A, E, H, V, seed=31)
+    W["output.output.weight"].zero_()
+    W["output.output.bias"].zero_()
+    W["output.output.bias"][10:10 + n_tied] = 1.0
+    g = torch.Generator().manual_seed(32)
+    ann = torch.randn(2, D, 3, 3, generator=g)
+    caps, scores, _, _ = cuda_caption(W, ann, k, 6, 1.0, None, 0.5, True)
+    for i in range(2):
+        assert len(caps[i]) == k
+        for c in caps[i]:
+            assert len(c) == 6 and set(c) <= {10, 11, 12}, c           # never <END>: flushed at the maximum length
+        assert all(abs(s - scores[i][0]) < 1e-5 for s in scores[i])     # every hypothesis has the same score
