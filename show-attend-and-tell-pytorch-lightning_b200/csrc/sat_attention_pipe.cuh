@@ -60,6 +60,7 @@ constexpr int ATTP_BWD_CW = 12;                      // backward: 12 consumer wa
                                                      // at 96 registers dropped to one CTA per SM = two waves at B=256)
 constexpr int ATTP_NST = 6;
 constexpr int ATTP_STAGE_BYTES = 16384;
+constexpr size_t SAT_ATT_GROUP_MIN_BYTES = 0;   // per-image annotation tile from which the grouped kernel is used (measured faster at every size tried)
 constexpr int ATTP_KA = 2;                           // attention_dim <= 256 on the pipelined kernel
 
 struct AttPipeSmem {
@@ -316,6 +317,289 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
   }
 }
 
+// =============================================================================================
+// K1 grouped: the same pipeline with ONE CTA PER IMAGE serving up to G caption rows (the beams of beam search, or the
+// ncap captions of an image): the image's P and annotation tiles are streamed once and every stage is used by all rows,
+// instead of once per row through L2.  Per row the arithmetic and its summation order are those of
+// attention_step_fwd_pipe_kernel, so both kernels give bit-identical alpha / z / gz.
+//   smem: e[G][L4], q[G][A], w[A], ring; the cross-row-group reduction scratch red[G][RG*D] aliases the drained ring.
+// =============================================================================================
+template <typename T, bool kExact, int CW, int G>
+__global__ void __launch_bounds__(CW * 32 + 32, 2)
+attention_step_fwd_group_kernel(const T* __restrict__ ann, const T* __restrict__ P, const float* __restrict__ wf,
+                                const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t, int ncap,
+                                int L, int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha,
+                                float* __restrict__ qsave, T* __restrict__ z, T* __restrict__ gz, T* __restrict__ beta,
+                                int64_t ld_z) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int VN = Vec16<T>::N;
+  constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32;
+  SAT_PDL_TRIGGER();      // ann, P, lens are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = blockIdx.x;
+  const int row0 = img * ncap;          // first caption row of this image; rows row0 .. row0 + ncap - 1  (ncap <= G)
+  AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
+  const int L4 = (L + 3) & ~3;
+  float* e = reinterpret_cast<float*>(smem_raw + sizeof(AttPipeSmem));   // [G][L4]
+  float* qs = e + G * L4;               // [G][A]
+  float* ws = qs + G * A;               // [A]
+  float* part = ws + A;                 // [2][G][CW] softmax partials
+  const int NV = D / VN;
+  const int RG = NV >= ATTP_CONSUMERS ? 1 : ATTP_CONSUMERS / NV;
+  const uint32_t stage_off =
+      (uint32_t)((sizeof(AttPipeSmem) + sizeof(float) * (size_t)(G * L4 + G * A + A + 2 * G * CW) + 127) & ~(size_t)127);
+  uint8_t* stages = smem_raw + stage_off;
+  float* red = reinterpret_cast<float*>(stages);   // [G][RG * D], after the ring is drained
+
+  unsigned act = 0;                     // bit g: row row0+g takes part in this step
+  for (int g = 0; g < ncap; ++g)
+    if (lens == nullptr || t < lens[row0 + g]) act |= 1u << g;
+  const int RCP = ATTP_STAGE_BYTES / (A * (int)sizeof(T));
+  const int RCA = ATTP_STAGE_BYTES / (D * (int)sizeof(T));
+  const int nP = (L + RCP - 1) / RCP, nA = (L + RCA - 1) / RCA;
+
+  if (act != 0 && tid == 0) {
+    for (int i = 0; i < ATTP_NST; ++i) {
+      sat_mbar_init(&hd->full[i], 1);
+      sat_mbar_init(&hd->empty[i], ATTP_CWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == ATTP_CWARPS) {
+    if (lane == 0 && act != 0) {        // ===== producer =====
+      const T* Pb = P + (int64_t)img * L * A;
+      const T* ab = ann + (int64_t)img * L * D;
+      for (int i = 0; i < nP + nA; ++i) {
+        const int st = i % ATTP_NST;
+        const uint32_t ph = (uint32_t)(i / ATTP_NST) & 1u;
+        sat_mbar_wait(&hd->empty[st], ph ^ 1u);
+        const void* src;
+        uint32_t bytes;
+        if (i < nP) {
+          const int r0 = i * RCP, rows = min(RCP, L - r0);
+          src = Pb + (int64_t)r0 * A;
+          bytes = (uint32_t)(rows * A * (int)sizeof(T));
+        } else {
+          const int r0 = (i - nP) * RCA, rows = min(RCA, L - r0);
+          src = ab + (int64_t)r0 * D;
+          bytes = (uint32_t)(rows * D * (int)sizeof(T));
+        }
+        sat_mbar_expect_tx(&hd->full[st], bytes);
+        sat_bulk_g2s(stages + (size_t)st * ATTP_STAGE_BYTES, src, bytes, &hd->full[st]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  SAT_PDL_WAIT();
+  // rows that sit this step out get zero outputs (as the per-row kernel writes them)
+  for (int g = 0; g < ncap; ++g) {
+    if (act & (1u << g)) continue;
+    const int64_t r = row0 + g;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) alpha[r * ld_alpha + l] = 0.0f;
+    for (int d = tid; d < D; d += ATTP_CONSUMERS) {
+      z[r * ld_z + d] = from_f<T>(0.f);
+      gz[r * ld_z + d] = from_f<T>(0.f);
+      if (beta) beta[r * ld_z + d] = from_f<T>(0.f);
+    }
+    if (qsave) for (int a = tid; a < A; a += ATTP_CONSUMERS) qsave[r * A + a] = 0.0f;
+  }
+  if (act == 0) return;
+  for (int i = tid; i < ncap * A; i += ATTP_CONSUMERS) {
+    const int g = i / A, a = i - g * A;
+    const float q = hp[(int64_t)(row0 + g) * ldhp + a];
+    qs[g * A + a] = q;
+    if (qsave && (act & (1u << g))) qsave[(int64_t)(row0 + g) * A + a] = q;
+  }
+  for (int a = tid; a < A; a += ATTP_CONSUMERS) ws[a] = wf[a];
+  sat_named_bar(1, ATTP_CONSUMERS);
+
+  float wreg[ATTP_KA][4];
+#pragma unroll
+  for (int k = 0; k < ATTP_KA; ++k) {
+    const int a = lane * 4 + 128 * k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wreg[k][i] = a < A ? ws[a + i] : 0.0f;
+  }
+  int it = 0;
+  for (int i = 0; i < nP; ++i, ++it) {
+    const int st = it % ATTP_NST;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
+    const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
+    const int r0 = i * RCP, rows = min(RCP, L - r0);
+    for (int l0 = warp * 4; l0 < rows; l0 += ATTP_CWARPS * 4) {
+      float4 p[ATTP_KA][4];
+#pragma unroll
+      for (int k = 0; k < ATTP_KA; ++k) {
+        const int a = lane * 4 + 128 * k;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          p[k][u] = (a < A && (l0 + u) < rows) ? ld4(Ps + (size_t)(l0 + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int g = 0; g < ncap; ++g) {
+        if (!(act & (1u << g))) continue;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < ATTP_KA; ++k) {
+          const int a = lane * 4 + 128 * k;
+          if (a < A) {
+            const float4 q4 = *reinterpret_cast<const float4*>(qs + g * A + a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              s4[u] = fmaf(wreg[k][0], sat_tanh<kExact>(p[k][u].x + q4.x), s4[u]);
+              s4[u] = fmaf(wreg[k][1], sat_tanh<kExact>(p[k][u].y + q4.y), s4[u]);
+              s4[u] = fmaf(wreg[k][2], sat_tanh<kExact>(p[k][u].z + q4.z), s4[u]);
+              s4[u] = fmaf(wreg[k][3], sat_tanh<kExact>(p[k][u].w + q4.w), s4[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s4[u] += __shfl_xor_sync(0xffffffffu, s4[u], o);
+        }
+        if (lane < 4 && (l0 + lane) < rows) {
+          const float sv = lane == 0 ? s4[0] : (lane == 1 ? s4[1] : (lane == 2 ? s4[2] : s4[3]));
+          e[g * L4 + r0 + l0 + lane] = sv * scale;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  // softmax over L for every row (same partial / combine order as the per-row kernel)
+  float* pmax = part;
+  float* psum = part + G * CW;
+  for (int g = 0; g < ncap; ++g) {
+    float mx = -INFINITY;
+    if (act & (1u << g))
+      for (int l = tid; l < L; l += ATTP_CONSUMERS) mx = fmaxf(mx, e[g * L4 + l]);
+    mx = warp_max(mx);
+    if (lane == 0) pmax[g * CW + warp] = mx;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < ncap; ++g) {
+    if (!(act & (1u << g))) continue;
+    float mx = pmax[g * CW];
+#pragma unroll
+    for (int w2 = 1; w2 < ATTP_CWARPS; ++w2) mx = fmaxf(mx, pmax[g * CW + w2]);
+    float sum = 0.0f;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+      const float pe = sat_exp<kExact>(e[g * L4 + l] - mx);
+      e[g * L4 + l] = pe;
+      sum += pe;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) psum[g * CW + warp] = sum;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < ncap; ++g) {
+    float* eg = e + g * L4;
+    if (!(act & (1u << g))) {
+      for (int l = tid; l < L; l += ATTP_CONSUMERS) eg[l] = 0.0f;     // contributes nothing to the context loop
+      continue;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int w2 = 0; w2 < ATTP_CWARPS; ++w2) sum += psum[g * CW + w2];
+    float* alpha_r = alpha + (int64_t)(row0 + g) * ld_alpha;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+      const float al = eg[l] / sum;
+      eg[l] = al;
+      alpha_r[l] = al;
+    }
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+
+  // context: every annotation vector is loaded once and feeds all rows
+  float acc[G][VN];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[g][i] = 0.0f;
+  const int rg = RG == 1 ? 0 : tid / NV;
+  const int cv0 = RG == 1 ? tid : tid - rg * NV;
+  const int RPT = (RCA + RG - 1) / RG;
+  const bool worker = rg < RG && cv0 < NV;
+  for (int j = 0; j < nA; ++j, ++it) {
+    const int st = it % ATTP_NST;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
+    const T* As = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
+    const int r0 = j * RCA, rows = min(RCA, L - r0);
+    if (worker) {
+      const int lb = rg * RPT, le = min(rows, lb + RPT);
+      const T* ap = As + (size_t)lb * D + cv0 * VN;
+      const float* ep = e + r0 + lb;
+      int l = lb;
+      for (; l + 2 <= le; l += 2, ap += 2 * (size_t)D, ep += 2) {
+        float v[2][VN];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) Vec16<T>::load_shared(ap + (size_t)u * D, v[u]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g < ncap) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float al = ep[g * L4 + u];
+#pragma unroll
+              for (int i2 = 0; i2 < VN; ++i2) acc[g][i2] = fmaf(al, v[u][i2], acc[g][i2]);
+            }
+          }
+        }
+      }
+      for (; l < le; ++l, ap += D, ++ep) {
+        float v[VN];
+        Vec16<T>::load_shared(ap, v);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g < ncap) {
+            const float al = ep[g * L4];
+#pragma unroll
+            for (int i2 = 0; i2 < VN; ++i2) acc[g][i2] = fmaf(al, v[i2], acc[g][i2]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);     // the ring is drained: red[] may overwrite it
+  if (worker) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (g < ncap) {
+#pragma unroll
+        for (int i = 0; i < VN; ++i) red[((size_t)g * RG + rg) * D + cv0 * VN + i] = acc[g][i];
+      }
+    }
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < ncap; ++g) {
+    if (!(act & (1u << g))) continue;
+    const int64_t r = row0 + g;
+    const float* hp_r = hp + r * ldhp;
+    for (int d = tid; d < D; d += ATTP_CONSUMERS) {
+      float zs = 0.0f;
+      for (int q = 0; q < RG; ++q) zs += red[((size_t)g * RG + q) * D + d];
+      const float bt = sat_sigmoid<kExact>(hp_r[A + d]);
+      z[r * ld_z + d] = from_f<T>(zs);
+      gz[r * ld_z + d] = from_f<T>(bt * zs);
+      if (beta) beta[r * ld_z + d] = from_f<T>(bt);
+    }
+  }
+}
+
+template <int G>
+static inline size_t attention_fwd_group_smem(int L, int A) {
+  return ((sizeof(AttPipeSmem) + sizeof(float) * (size_t)(G * ((L + 3) & ~3) + G * A + A + 2 * G * ATTP_FWD_CW) + 127) & ~(size_t)127) +
+         128 + (size_t)ATTP_NST * ATTP_STAGE_BYTES;
+}
+
 static inline size_t attention_fwd_pipe_smem(int L, int D, int A, int vn) {
   constexpr int ATTP_CONSUMERS = ATTP_FWD_CW * 32;
   const int NV = D / vn;
@@ -351,6 +635,25 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     return 0;
+  }
+  // several caption rows per image (beams / captions): one CTA per image streams the tiles once for all of them when
+  // the per-image tile is large enough for the shared stream to pay (SAT_ATT_GROUP=0/1 forces the choice)
+  static const int group_mode = getenv("SAT_ATT_GROUP") ? atoi(getenv("SAT_ATT_GROUP")) : -1;
+  const bool group_fit = ncap >= 2 && ncap <= 8 && rows % ncap == 0 &&
+                         (size_t)ncap * (((D / Vec16<T>::N) >= ATTP_FWD_CW * 32 ? 1 : (ATTP_FWD_CW * 32) / (D / Vec16<T>::N)) * (size_t)D) *
+                                 sizeof(float) <= (size_t)ATTP_NST * ATTP_STAGE_BYTES;
+  const bool group = group_fit && (group_mode == 1 || (group_mode != 0 && (size_t)L * D * sizeof(T) >= SAT_ATT_GROUP_MIN_BYTES));
+  if (group) {
+    auto launch_g = [&](auto kern, size_t smem) -> int {
+      SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SAT_CUDA(sat_launch_pdl(kern, dim3(rows / ncap), dim3(ATTP_FWD_CW * 32 + 32), smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D, A,
+                              scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z));
+      SAT_COUNT_LAUNCH();
+      return 0;
+    };
+    if (ncap <= 3) return launch_g(attention_step_fwd_group_kernel<T, kExact, ATTP_FWD_CW, 3>, attention_fwd_group_smem<3>(L, A));
+    if (ncap <= 5) return launch_g(attention_step_fwd_group_kernel<T, kExact, ATTP_FWD_CW, 5>, attention_fwd_group_smem<5>(L, A));
+    return launch_g(attention_step_fwd_group_kernel<T, kExact, ATTP_FWD_CW, 8>, attention_fwd_group_smem<8>(L, A));
   }
   const size_t smem = attention_fwd_pipe_smem(L, D, A, Vec16<T>::N);
   auto kern = attention_step_fwd_pipe_kernel<T, kExact, ATTP_FWD_CW>;

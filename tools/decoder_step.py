@@ -46,6 +46,13 @@ if args.decode:
         ev1.record()
         torch.cuda.synchronize()
         times.append(ev0.elapsed_time(ev1))
+    if args.profile:
+        from sat_b200 import _lib
+        _lib.profile_begin(args.profile)
+        t = decode.decode_annotations(dw, ann, args.decode, 30, 1.0, None, 0.5, vocab)
+        torch.cuda.synchronize()
+        ms, n = _lib.profile_end()
+        print("kind %d: %d launches, %.2f us per launch" % (args.profile, n, 1e3 * ms / max(n, 1)))
     times = sorted(times[2:] or times)
     print("decode k=%d B=%d: median %.3f ms (min %.3f) over %d iters" % (args.decode, B, times[len(times) // 2], times[0], len(times)))
 else:
