@@ -498,9 +498,9 @@ attention_step_fwd_group_kernel(const T* __restrict__ ann, const T* __restrict__
     if (lane == 0) psum[g * CW + warp] = sum;
   }
   sat_named_bar(1, ATTP_CONSUMERS);
-  for (int g = 0; g < ncap; ++g) {
+  for (int g = 0; g < G; ++g) {
     float* eg = e + g * L4;
-    if (!(act & (1u << g))) {
+    if (g >= ncap || !(act & (1u << g))) {
       for (int l = tid; l < L; l += ATTP_CONSUMERS) eg[l] = 0.0f;     // contributes nothing to the context loop
       continue;
     }
@@ -540,15 +540,18 @@ attention_step_fwd_group_kernel(const T* __restrict__ ann, const T* __restrict__
         float v[2][VN];
 #pragma unroll
         for (int u = 0; u < 2; ++u) Vec16<T>::load_shared(ap + (size_t)u * D, v[u]);
+        float al[G][2];                 // straight-line code: rows g >= ncap carry alpha = 0 (zeroed above)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          if (g < ncap) {
+          al[g][0] = ep[g * L4];
+          al[g][1] = ep[g * L4 + 1];
+        }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float al = ep[g * L4 + u];
+        for (int u = 0; u < 2; ++u) {
 #pragma unroll
-              for (int i2 = 0; i2 < VN; ++i2) acc[g][i2] = fmaf(al, v[u][i2], acc[g][i2]);
-            }
+          for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int i2 = 0; i2 < VN; ++i2) acc[g][i2] = fmaf(al[g][u], v[u][i2], acc[g][i2]);
           }
         }
       }
@@ -557,11 +560,9 @@ attention_step_fwd_group_kernel(const T* __restrict__ ann, const T* __restrict__
         Vec16<T>::load_shared(ap, v);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          if (g < ncap) {
-            const float al = ep[g * L4];
+          const float al = ep[g * L4];
 #pragma unroll
-            for (int i2 = 0; i2 < VN; ++i2) acc[g][i2] = fmaf(al, v[i2], acc[g][i2]);
-          }
+          for (int i2 = 0; i2 < VN; ++i2) acc[g][i2] = fmaf(al, v[i2], acc[g][i2]);
         }
       }
     }
