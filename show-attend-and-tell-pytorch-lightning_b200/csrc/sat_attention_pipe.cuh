@@ -601,6 +601,269 @@ static inline size_t attention_fwd_group_smem(int L, int A) {
          128 + (size_t)ATTP_NST * ATTP_STAGE_BYTES;
 }
 
+// =============================================================================================
+// K1 grouped, tensor-core context (bf16 operands): as attention_step_fwd_group_kernel, but the context
+//   z[g, :] = sum_l alpha[g, l] * ann[l, :]          (g = the <= 8 caption rows of the image)
+// is an [8 x L] x [L x D] product, so it runs on mma.sync.m16n8k16 (rows 8..15 of the A tile are zero): the annotation
+// tile is streamed as 128-row x 64-column boxes by 2-D TMA with the 128-byte swizzle (conflict-free ldmatrix.trans),
+// column block by column block; warp w owns the 8 columns w*8.. of a box and keeps alpha (rounded to bf16) as A
+// fragments in registers for the whole kernel.  Scores and softmax are the fp32 code of the grouped kernel.
+// Needs bf16, L <= 256, D % 64 == 0, ncap <= 8.  Box rows past the image's L rows are multiplied by alpha = 0.
+// =============================================================================================
+constexpr int ATTG_BOX_ROWS = 128, ATTG_BOX_COLS = 64, ATTG_MAXKS = 16;     // 16 k-steps of 16 rows: L <= 256
+
+__device__ __forceinline__ uint32_t sat_pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <bool kExact, int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, 2)
+attention_step_fwd_group_tc_kernel(const __grid_constant__ CUtensorMap tm_ann, const bf16* __restrict__ P,
+                                   const float* __restrict__ wf, const float* __restrict__ hp, int64_t ldhp,
+                                   const int32_t* __restrict__ lens, int t, int ncap, int L, int D, int A, float scale,
+                                   float* __restrict__ alpha, int64_t ld_alpha, float* __restrict__ qsave, bf16* __restrict__ z,
+                                   bf16* __restrict__ gz, bf16* __restrict__ beta, int64_t ld_z) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  typedef bf16 T;
+  constexpr int G = 8;
+  constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32;
+  static_assert(CW == 8, "one consumer warp per 8-column slice of a 64-column box");
+  SAT_PDL_TRIGGER();      // ann, P, lens are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = blockIdx.x;
+  const int row0 = img * ncap;
+  AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
+  const int L4 = (L + 3) & ~3;
+  float* e = reinterpret_cast<float*>(smem_raw + sizeof(AttPipeSmem));   // [G][L4]
+  float* qs = e + G * L4;               // [G][A]
+  float* ws = qs + G * A;               // [A]
+  float* part = ws + A;                 // [2][G][CW]
+  const uint32_t base_u32 = sat_smem_u32(smem_raw);
+  const uint32_t hdr = (uint32_t)(sizeof(AttPipeSmem) + sizeof(float) * (size_t)(G * L4 + G * A + A + 2 * G * CW));
+  const uint32_t stage_off = ((base_u32 + hdr + 1023u) & ~1023u) - base_u32;       // 1024-byte aligned: 128B swizzle atom
+  uint8_t* stages = smem_raw + stage_off;
+
+  unsigned act = 0;
+  for (int g = 0; g < ncap; ++g)
+    if (lens == nullptr || t < lens[row0 + g]) act |= 1u << g;
+  const int RCP = ATTP_STAGE_BYTES / (A * (int)sizeof(T));
+  const int nP = (L + RCP - 1) / RCP;
+  const int nRB = (L + ATTG_BOX_ROWS - 1) / ATTG_BOX_ROWS, nCB = D / ATTG_BOX_COLS;
+
+  if (act != 0 && tid == 0) {
+    for (int i = 0; i < ATTP_NST; ++i) {
+      sat_mbar_init(&hd->full[i], 1);
+      sat_mbar_init(&hd->empty[i], ATTP_CWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == ATTP_CWARPS) {
+    if (lane == 0 && act != 0) {        // ===== producer: P chunks (1-D bulk), then annotation boxes (2-D, swizzled) =====
+      const T* Pb = P + (int64_t)img * L * A;
+      const int nbox = nCB * nRB;
+      for (int i = 0; i < nP + nbox; ++i) {
+        const int st = i % ATTP_NST;
+        const uint32_t ph = (uint32_t)(i / ATTP_NST) & 1u;
+        sat_mbar_wait(&hd->empty[st], ph ^ 1u);
+        if (i < nP) {
+          const int r0 = i * RCP, rows = min(RCP, L - r0);
+          const uint32_t bytes = (uint32_t)(rows * A * (int)sizeof(T));
+          sat_mbar_expect_tx(&hd->full[st], bytes);
+          sat_bulk_g2s(stages + (size_t)st * ATTP_STAGE_BYTES, Pb + (int64_t)r0 * A, bytes, &hd->full[st]);
+        } else {
+          const int bi = i - nP, cb = bi / nRB, rb = bi - cb * nRB;
+          sat_mbar_expect_tx(&hd->full[st], (uint32_t)(ATTG_BOX_ROWS * ATTG_BOX_COLS * sizeof(T)));
+          tc::tma_load_2d(&tm_ann, &hd->full[st], stages + (size_t)st * ATTP_STAGE_BYTES, cb * ATTG_BOX_COLS,
+                          img * L + rb * ATTG_BOX_ROWS);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  SAT_PDL_WAIT();
+  for (int g = 0; g < ncap; ++g) {
+    if (act & (1u << g)) continue;
+    const int64_t r = row0 + g;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) alpha[r * ld_alpha + l] = 0.0f;
+    for (int d = tid; d < D; d += ATTP_CONSUMERS) {
+      z[r * ld_z + d] = from_f<T>(0.f);
+      gz[r * ld_z + d] = from_f<T>(0.f);
+      if (beta) beta[r * ld_z + d] = from_f<T>(0.f);
+    }
+    if (qsave) for (int a = tid; a < A; a += ATTP_CONSUMERS) qsave[r * A + a] = 0.0f;
+  }
+  if (act == 0) return;
+  for (int i = tid; i < ncap * A; i += ATTP_CONSUMERS) {
+    const int g = i / A, a = i - g * A;
+    const float q = hp[(int64_t)(row0 + g) * ldhp + a];
+    qs[g * A + a] = q;
+    if (qsave && (act & (1u << g))) qsave[(int64_t)(row0 + g) * A + a] = q;
+  }
+  for (int a = tid; a < A; a += ATTP_CONSUMERS) ws[a] = wf[a];
+  sat_named_bar(1, ATTP_CONSUMERS);
+
+  float wreg[ATTP_KA][4];
+#pragma unroll
+  for (int k = 0; k < ATTP_KA; ++k) {
+    const int a = lane * 4 + 128 * k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wreg[k][i] = a < A ? ws[a + i] : 0.0f;
+  }
+  int it = 0;
+  for (int i = 0; i < nP; ++i, ++it) {
+    const int st = it % ATTP_NST;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
+    const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
+    const int r0 = i * RCP, rows = min(RCP, L - r0);
+    for (int l0 = warp * 4; l0 < rows; l0 += ATTP_CWARPS * 4) {
+      float4 p[ATTP_KA][4];
+#pragma unroll
+      for (int k = 0; k < ATTP_KA; ++k) {
+        const int a = lane * 4 + 128 * k;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          p[k][u] = (a < A && (l0 + u) < rows) ? ld4(Ps + (size_t)(l0 + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int g = 0; g < ncap; ++g) {
+        if (!(act & (1u << g))) continue;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < ATTP_KA; ++k) {
+          const int a = lane * 4 + 128 * k;
+          if (a < A) {
+            const float4 q4 = *reinterpret_cast<const float4*>(qs + g * A + a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              s4[u] = fmaf(wreg[k][0], sat_tanh<kExact>(p[k][u].x + q4.x), s4[u]);
+              s4[u] = fmaf(wreg[k][1], sat_tanh<kExact>(p[k][u].y + q4.y), s4[u]);
+              s4[u] = fmaf(wreg[k][2], sat_tanh<kExact>(p[k][u].z + q4.z), s4[u]);
+              s4[u] = fmaf(wreg[k][3], sat_tanh<kExact>(p[k][u].w + q4.w), s4[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s4[u] += __shfl_xor_sync(0xffffffffu, s4[u], o);
+        }
+        if (lane < 4 && (l0 + lane) < rows) {
+          const float sv = lane == 0 ? s4[0] : (lane == 1 ? s4[1] : (lane == 2 ? s4[2] : s4[3]));
+          e[g * L4 + r0 + l0 + lane] = sv * scale;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  float* pmax = part;
+  float* psum = part + G * CW;
+  for (int g = 0; g < ncap; ++g) {
+    float mx = -INFINITY;
+    if (act & (1u << g))
+      for (int l = tid; l < L; l += ATTP_CONSUMERS) mx = fmaxf(mx, e[g * L4 + l]);
+    mx = warp_max(mx);
+    if (lane == 0) pmax[g * CW + warp] = mx;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < ncap; ++g) {
+    if (!(act & (1u << g))) continue;
+    float mx = pmax[g * CW];
+#pragma unroll
+    for (int w2 = 1; w2 < ATTP_CWARPS; ++w2) mx = fmaxf(mx, pmax[g * CW + w2]);
+    float sum = 0.0f;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+      const float pe = sat_exp<kExact>(e[g * L4 + l] - mx);
+      e[g * L4 + l] = pe;
+      sum += pe;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) psum[g * CW + warp] = sum;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < G; ++g) {
+    float* eg = e + g * L4;
+    if (g >= ncap || !(act & (1u << g))) {
+      for (int l = tid; l < L; l += ATTP_CONSUMERS) eg[l] = 0.0f;
+      continue;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int w2 = 0; w2 < ATTP_CWARPS; ++w2) sum += psum[g * CW + w2];
+    float* alpha_r = alpha + (int64_t)(row0 + g) * ld_alpha;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+      const float al = eg[l] / sum;
+      eg[l] = al;
+      alpha_r[l] = al;
+    }
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+
+  // A fragments of alpha (row g = lane / 4 of the m16 tile, rows 8..15 zero), one pair of registers per 16-row k-step
+  const int g = lane >> 2, kk = (lane & 3) * 2;
+  uint32_t afr[ATTG_MAXKS][2];
+#pragma unroll
+  for (int ks = 0; ks < ATTG_MAXKS; ++ks) {
+    const int l = ks * 16 + kk;
+    const float* eg = e + g * L4;
+    afr[ks][0] = sat_pack_bf16x2(l < L ? eg[l] : 0.0f, l + 1 < L ? eg[l + 1] : 0.0f);
+    afr[ks][1] = sat_pack_bf16x2(l + 8 < L ? eg[l + 8] : 0.0f, l + 9 < L ? eg[l + 9] : 0.0f);
+  }
+  const bool row_on = g < ncap && (act & (1u << g));
+  const int64_t r = row0 + g;
+  const uint32_t stages_u32 = base_u32 + stage_off;
+  const int mrow = (lane >> 3) * 8 + (lane & 7);        // ldmatrix.x4: lane -> row of the 32-row slab it addresses
+  for (int cb = 0; cb < nCB; ++cb) {
+    const int d = cb * ATTG_BOX_COLS + warp * 8 + kk;   // this thread's two output columns d, d + 1
+    float2 hv = make_float2(0.f, 0.f);
+    if (row_on) hv = *reinterpret_cast<const float2*>(hp + r * ldhp + A + d);     // consumed after the boxes below
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+    for (int rb = 0; rb < ATTG_MAXKS / 8; ++rb) {
+      if (rb < nRB) {
+        const int st = it % ATTP_NST;
+        sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTP_NST) & 1u);
+        const uint32_t sb = stages_u32 + (uint32_t)st * ATTP_STAGE_BYTES;
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const int rr = k2 * 32 + mrow;
+          const uint32_t addr = sb + (uint32_t)rr * 128u + (uint32_t)((warp ^ (rr & 7)) << 4);
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(addr));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                       : "r"(afr[rb * 8 + 2 * k2][0]), "r"(0u), "r"(afr[rb * 8 + 2 * k2][1]), "r"(0u), "r"(b0), "r"(b1));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                       : "r"(afr[rb * 8 + 2 * k2 + 1][0]), "r"(0u), "r"(afr[rb * 8 + 2 * k2 + 1][1]), "r"(0u), "r"(b2), "r"(b3));
+        }
+        __syncwarp();
+        if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+        ++it;
+      }
+    }
+    if (row_on) {
+      const float bt0 = sat_sigmoid<kExact>(hv.x), bt1 = sat_sigmoid<kExact>(hv.y);
+      *reinterpret_cast<uint32_t*>(z + r * ld_z + d) = sat_pack_bf16x2(c0, c1);
+      *reinterpret_cast<uint32_t*>(gz + r * ld_z + d) = sat_pack_bf16x2(bt0 * c0, bt1 * c1);
+      if (beta) *reinterpret_cast<uint32_t*>(beta + r * ld_z + d) = sat_pack_bf16x2(bt0, bt1);
+    }
+  }
+}
+
+static inline size_t attention_fwd_group_tc_smem(int L, int A) {
+  return sizeof(AttPipeSmem) + sizeof(float) * (size_t)(8 * ((L + 3) & ~3) + 8 * A + A + 2 * 8 * ATTP_FWD_CW) + 1024 +
+         (size_t)ATTP_NST * ATTP_STAGE_BYTES;
+}
+
 static inline size_t attention_fwd_pipe_smem(int L, int D, int A, int vn) {
   constexpr int ATTP_CONSUMERS = ATTP_FWD_CW * 32;
   const int NV = D / vn;
@@ -644,6 +907,27 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
                          (size_t)ncap * (((D / Vec16<T>::N) >= ATTP_FWD_CW * 32 ? 1 : (ATTP_FWD_CW * 32) / (D / Vec16<T>::N)) * (size_t)D) *
                                  sizeof(float) <= (size_t)ATTP_NST * ATTP_STAGE_BYTES;
   const bool group = group_fit && (group_mode == 1 || (group_mode != 0 && (size_t)L * D * sizeof(T) >= SAT_ATT_GROUP_MIN_BYTES));
+  if constexpr (std::is_same<T, bf16>::value && !kExact) {
+    static const int group_tc_mode = getenv("SAT_ATT_GROUP_TC") ? atoi(getenv("SAT_ATT_GROUP_TC")) : 1;
+    if (group && group_tc_mode != 0 && L <= 16 * ATTG_MAXKS && D % ATTG_BOX_COLS == 0 && ld_z % 2 == 0 && ldhp % 2 == 0 && A % 2 == 0) {
+      // annotations as a 2-D tensor [n_img * L, D]; the map is rebuilt only when the buffer or shape changes
+      static CUtensorMap tm;
+      static const void* tm_ptr = nullptr;
+      static int64_t tm_rows = 0, tm_d = 0;
+      const int64_t n_rows = (int64_t)(rows / ncap) * L;
+      if (tm_ptr != (const void*)ann || tm_rows != n_rows || tm_d != D) {
+        SAT_TRY(tc::make_map(&tm, ann, n_rows, D, D, ATTG_BOX_ROWS));
+        tm_ptr = ann; tm_rows = n_rows; tm_d = D;
+      }
+      auto kern = attention_step_fwd_group_tc_kernel<kExact, ATTP_FWD_CW>;
+      const size_t smem = attention_fwd_group_tc_smem(L, A);
+      SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SAT_CUDA(sat_launch_pdl(kern, dim3(rows / ncap), dim3(ATTP_FWD_CW * 32 + 32), smem, st, tm, P, wf, hp, ldhp, lens, t, ncap, L, D, A,
+                              scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z));
+      SAT_COUNT_LAUNCH();
+      return 0;
+    }
+  }
   if (group) {
     auto launch_g = [&](auto kern, size_t smem) -> int {
       SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -80,6 +80,22 @@ def test_forward_bf16_vs_oracle(use_tc):
     assert relerr(r["alphas"], ref["alphas"]) < 2e-2
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(Bi=3, ncap=5, hw=(7, 7), D=512, A=128, E=256, H=512, V=1000, T=9, ragged=True),
+    dict(Bi=2, ncap=5, hw=(16, 16), D=2048, A=128, E=256, H=512, V=1000, T=5, ragged=True),     # config 5 tile, L=256
+    dict(Bi=2, ncap=8, hw=(14, 14), D=512, A=128, E=256, H=512, V=1000, T=6, ragged=True),      # L=196: boxes overrun the image
+    dict(Bi=3, ncap=2, hw=(14, 14), D=512, A=96, E=256, H=512, V=1000, T=6, ragged=False),
+])
+def test_forward_bf16_multi_caption_vs_oracle(cfg):
+    """several caption rows per image in bf16: the grouped attention kernel (tensor-core context, alpha rounded to bf16)."""
+    W, ann, caps, lens = synth(**cfg)
+    ref = O.train_loss(W, ann, caps, lens, label_smoothing=0.0, att_gamma=1.0)
+    r = run_cuda_forward(W, ann, caps, lens, 0.0, 1.0, dtype=torch.bfloat16, exact=False, use_tc=True, logits_f32=False)
+    assert relerr(r["logits"], ref["logits"]) < 2e-2
+    assert abs(r["loss"] - float(ref["loss"])) < 2e-2 * abs(float(ref["loss"]))
+    assert relerr(r["alphas"], ref["alphas"]) < 2e-2
+
+
 @pytest.mark.parametrize("cfg,lens_override", [
     (dict(Bi=1, ncap=1, hw=(2, 2), D=64, A=32, E=32, H=64, V=128, T=5, ragged=False), None),          # single caption, L=4
     (dict(Bi=3, ncap=1, hw=(1, 1), D=64, A=32, E=32, H=64, V=128, T=4, ragged=False), [[1], [4], [2]]),   # L=1, shortest length 1
