@@ -52,6 +52,18 @@ void sat_prof_mark(cudaStream_t st);
 // SAT_PDL_WAIT() before the first global-memory access that depends on (or could disturb) the predecessor.
 #define SAT_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define SAT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+// Kernels on this path read operands that are constant inside a driver's launch chain (annotations, P, packed weights)
+// BEFORE SAT_PDL_WAIT().  The single-op entry points (sat_linear, sat_attention_step_fwd) take caller-supplied operands
+// that may be the output of the caller's previous launch, so they launch without the attribute (SatNoPdlScope): the
+// kernel then starts only after everything before it in the stream has completed.
+static inline bool& sat_pdl_allowed() {
+  static bool allowed = true;
+  return allowed;
+}
+struct SatNoPdlScope {
+  SatNoPdlScope() { sat_pdl_allowed() = false; }
+  ~SatNoPdlScope() { sat_pdl_allowed() = true; }
+};
 template <typename Kern, typename... Args>
 static inline cudaError_t sat_launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -63,7 +75,7 @@ static inline cudaError_t sat_launch_pdl(Kern kern, dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = sat_pdl_allowed() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 

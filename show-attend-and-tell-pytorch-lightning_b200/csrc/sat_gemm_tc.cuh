@@ -140,9 +140,19 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (warp == 0 && lane == 0) {
+  // Inside the decoder drivers W is always a packed weight matrix, never written within the launch chain: thread 0 (which
+  // just initialised the barriers) starts the weight tiles of the first ring pass before griddepcontrol.wait; the
+  // activation tiles follow it.  (sat_linear, with a caller-supplied W, launches without the PDL attribute.)
+  const int npre = nkb < STAGES ? nkb : STAGES;
+  if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+    for (int i = 0; i < npre; ++i) {
+      const int kb = kb_begin + i;
+      const int kw = kb >= nkb0 ? k0 + (kb - nkb0) * BK : kb * BK;
+      mbar_expect_tx(&s.full[i], STAGE_BYTES);
+      tma_load_2d(&maps.w, &s.full[i], s.w[i], kw, n0);
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -156,13 +166,15 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
         const int kb = kb_begin + i;
         const int st = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&s.empty[st], ph ^ 1);
-        mbar_expect_tx(&s.full[st], STAGE_BYTES);
         const bool seg1 = kb >= nkb0;
         const int ka = (seg1 ? kb - nkb0 : kb) * BK;            // k offset inside the A segment
         const int kw = seg1 ? k0 + ka : ka;                      // k offset inside W
+        if (i >= npre) {                                         // first pass: tx count armed and W already in flight
+          mbar_wait(&s.empty[st], ph ^ 1);
+          mbar_expect_tx(&s.full[st], STAGE_BYTES);
+          tma_load_2d(&maps.w, &s.full[st], s.w[st], kw, n0);
+        }
         tma_load_2d(seg1 ? &maps.a[1] : &maps.a[0], &s.full[st], s.a[st], ka, m0);
-        tma_load_2d(&maps.w, &s.full[st], s.w[st], kw, n0);
       }
     }
   } else if (warp == 1) {
@@ -309,7 +321,7 @@ static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, i
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = sat_pdl_allowed() ? 1 : 0;
   SAT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, M, N, A.k[0], A.nseg == 2 ? A.k[1] : 0, epi));
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();

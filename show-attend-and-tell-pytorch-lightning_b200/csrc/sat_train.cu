@@ -22,6 +22,9 @@ static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void
   const int B = d.B, Bi = d.Bi, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H;
   const bool tc = d.use_tc != 0;
   // P = ann * Wa^T  ([Bi*L, D] x [A, D]^T)
+  // first launch of a driver: no PDL attribute, so that operands written by the caller's preceding launch (the weight
+  // pack kernel, the encoder) are complete and visible to every early (pre-wait) read of the kernels that follow
+  SatNoPdlScope first_launch;
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, Bi * L, A, EpiStore<TS>{(TS*)P, A, nullptr, nullptr, 0},
                            st)));
   // mean over locations, then the two Linear layers of InitLSTM (no nonlinearity between, model.py:79)
@@ -176,11 +179,12 @@ int sat_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const flo
     return gemm_tn<float, float>(false, gemm_a1(A, lda, K), (const float*)W, ldw, M, N,
                                  EpiStore<float>{(float*)C, ldc, bias, nullptr, 0}, st);
   } else if (dtype == SAT_BF16) {
-    if (c_f32)
-      return gemm_tn<bf16, bf16>(tc, gemm_a1(A, lda, K), (const bf16*)W, ldw, M, N,
-                                 EpiStore<float>{(float*)C, ldc, bias, nullptr, 0}, st);
-    return gemm_tn<bf16, bf16>(tc, gemm_a1(A, lda, K), (const bf16*)W, ldw, M, N, EpiStore<bf16>{(bf16*)C, ldc, bias, nullptr, 0},
-                               st);
+    SatNoPdlScope no_pdl;             // W is the caller's: it may be the output of the launch just before this one
+    const int rc = c_f32 ? gemm_tn<bf16, bf16>(tc, gemm_a1(A, lda, K), (const bf16*)W, ldw, M, N,
+                                               EpiStore<float>{(float*)C, ldc, bias, nullptr, 0}, st)
+                         : gemm_tn<bf16, bf16>(tc, gemm_a1(A, lda, K), (const bf16*)W, ldw, M, N,
+                                               EpiStore<bf16>{(bf16*)C, ldc, bias, nullptr, 0}, st);
+    return rc;
   }
   SAT_REQUIRE(false, "sat_linear: unknown dtype %d", dtype);
 }
@@ -201,6 +205,7 @@ int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, con
   SAT_REQUIRE(ann && P && wf && hp && alpha && z && gz, "sat_attention_step_fwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = (float)(1.0 / sqrt((double)d->L));
+  SatNoPdlScope no_pdl;               // ann / P are the caller's: they may be the output of the launch just before this one
 #define SAT_LAUNCH_ATT(TS, EX)                                                                                          \
   SAT_TRY((launch_attention_fwd<TS, EX>((const TS*)ann, (const TS*)P, wf, hp, ldhp, lens, t, d->B, d->ncap, d->L, d->D, d->A, \
                                         scale, alpha, ld_alpha, nullptr, (TS*)z, (TS*)gz, (TS*)beta, ld_z, st)))

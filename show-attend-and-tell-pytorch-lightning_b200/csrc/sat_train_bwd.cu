@@ -21,8 +21,11 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   const int M = T * B;
 
   // dpre = g * (dlogits * Wo) * (1 - Xo^2)            [M,E]
-  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dlogits, V, V), (const TS*)w.WoT, V, M, E,
-                           EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale, d.plain_output, b.dropout_p, b.dropout_seed}, st)));
+  {
+    SatNoPdlScope first_launch;       // first launch of the driver: everything the caller queued before is complete and visible
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dlogits, V, V), (const TS*)w.WoT, V, M, E,
+                             EpiDpre<TS>{(const TS*)b.Xo, (TS*)b.dpre, E, b.gscale, d.plain_output, b.dropout_p, b.dropout_seed}, st)));
+  }
   // dHZ = dpre * [W_ho | W_zo]                         [M,H+D]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dpre, E, E), (const TS*)w.WhozoT, E, M, H + D,
                            EpiStore<float>{b.dHZ, H + D, nullptr, nullptr, 0}, st)));
