@@ -366,11 +366,24 @@ ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t*
   const int y = caps[(int64_t)b * caplen + t + 1];
   float mx = -INFINITY, sx = 0.0f;
   int arg = 0x7fffffff;
-  for (int v = tid; v < V; v += 256) {
-    const float xv = to_f(row[v]);
-    x[v] = xv;
-    sx += xv;
-    if (xv > mx) { mx = xv; arg = v; }
+  const bool vec4 = (V & 3) == 0;       // 4 logits per access (rows are then 8 B (bf16) / 16 B (fp32) aligned)
+  if (vec4) {
+    for (int v = tid * 4; v < V; v += 256 * 4) {
+      const float4 q = ld4(row + v);
+      *reinterpret_cast<float4*>(x + v) = q;
+      sx += (q.x + q.y) + (q.z + q.w);
+      if (q.x > mx) { mx = q.x; arg = v; }
+      if (q.y > mx) { mx = q.y; arg = v + 1; }
+      if (q.z > mx) { mx = q.z; arg = v + 2; }
+      if (q.w > mx) { mx = q.w; arg = v + 3; }
+    }
+  } else {
+    for (int v = tid; v < V; v += 256) {
+      const float xv = to_f(row[v]);
+      x[v] = xv;
+      sx += xv;
+      if (xv > mx) { mx = xv; arg = v; }
+    }
   }
   // block argmax with lowest-index tie break (torch.argmax returns the first maximal index)
   for (int o = 16; o > 0; o >>= 1) {
@@ -384,7 +397,14 @@ ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t*
   for (int w = 1; w < 8; ++w)
     if (s_val[w] > mx || (s_val[w] == mx && s_arg[w] < arg)) { mx = s_val[w]; arg = s_arg[w]; }
   float se = 0.0f;
-  for (int v = tid; v < V; v += 256) se += sat_exp<kExact>(x[v] - mx);
+  if (vec4) {
+    for (int v = tid * 4; v < V; v += 256 * 4) {
+      const float4 q = *reinterpret_cast<const float4*>(x + v);
+      se += (sat_exp<kExact>(q.x - mx) + sat_exp<kExact>(q.y - mx)) + (sat_exp<kExact>(q.z - mx) + sat_exp<kExact>(q.w - mx));
+    }
+  } else {
+    for (int v = tid; v < V; v += 256) se += sat_exp<kExact>(x[v] - mx);
+  }
   se = block_sum(se, scratch);
   sx = block_sum(sx, scratch);
   const float lse = mx + (kExact ? logf(se) : __logf(se));
@@ -397,10 +417,24 @@ ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t*
   if (dlogits) {
     const float inv_ntok = *inv_ntok_p;
     const float sv = smoothing / (float)V;
-    for (int v = tid; v < V; v += 256) {
-      float p = sat_exp<kExact>(x[v] - lse) - sv;
-      if (v == y) p -= (1.0f - smoothing);
-      dlogits[(int64_t)m * V + v] = from_f<TD>(p * inv_ntok);
+    if (vec4) {
+      TD* drow = dlogits + (int64_t)m * V;
+      for (int v = tid * 4; v < V; v += 256 * 4) {
+        const float4 q = *reinterpret_cast<const float4*>(x + v);
+        float p0 = sat_exp<kExact>(q.x - lse) - sv, p1 = sat_exp<kExact>(q.y - lse) - sv;
+        float p2 = sat_exp<kExact>(q.z - lse) - sv, p3 = sat_exp<kExact>(q.w - lse) - sv;
+        if (y == v) p0 -= (1.0f - smoothing);
+        if (y == v + 1) p1 -= (1.0f - smoothing);
+        if (y == v + 2) p2 -= (1.0f - smoothing);
+        if (y == v + 3) p3 -= (1.0f - smoothing);
+        st4(drow + v, make_float4(p0 * inv_ntok, p1 * inv_ntok, p2 * inv_ntok, p3 * inv_ntok));
+      }
+    } else {
+      for (int v = tid; v < V; v += 256) {
+        float p = sat_exp<kExact>(x[v] - lse) - sv;
+        if (v == y) p -= (1.0f - smoothing);
+        dlogits[(int64_t)m * V + v] = from_f<TD>(p * inv_ntok);
+      }
     }
   }
 }
