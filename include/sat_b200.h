@@ -146,8 +146,7 @@ typedef struct SatTrainBuffers {
   float* dP;             /* [B,L,A]      accumulated grad wrt P                                    */
   void* dP16;            /* [B,L,A] s    copy of dP in the operand dtype, written at the last backward step (t = 0);
                                          feeds the tensor-core d_ann GEMM (may be NULL in fp32 mode)          */
-  float* dann_tmp;       /* [B,L,D]      fp32 scratch of the tensor-core d_ann path (alpha (x) dz + mean term); may be
-                                         NULL in fp32 mode                                                    */
+  float* dann_tmp;       /* unused (kept for layout stability): the tensor-core d_ann path now accumulates in d_ann; may be NULL */
   float* dwf_part;       /* [T,B,A]      per-(b,t) partial of d f_att.weight                       */
   float* de;             /* [T,B,L]      scaled softmax-backward term of each step; dP is rebuilt from it, Q and P
                                           after the time loop (NULL: the slower step-by-step accumulation is used)  */

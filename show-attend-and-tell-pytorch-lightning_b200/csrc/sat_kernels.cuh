@@ -689,10 +689,10 @@ static inline size_t attention_bwd_smem(int L, int D, int A) {
 // One CTA per (caption, 512-column chunk): dZ[:,b,chunk] and alpha[b,:,:] are staged in shared memory.
 // =============================================================================================
 constexpr int DANN_DC = 512;
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 dann_alpha_kernel(const float* __restrict__ alphas, const T* __restrict__ dZ, const float* __restrict__ dmean,
-                  float* __restrict__ tmp, int B, int T_, int L, int D, int ncap, float mean_scale) {
+                  TO* __restrict__ tmp, int B, int T_, int L, int D, int ncap, float mean_scale) {
   extern __shared__ __align__(16) float smem[];
   float* dzs = smem;                       // [T][DANN_DC]
   float* als = dzs + (size_t)T_ * DANN_DC; // [T][L]
@@ -723,6 +723,6 @@ dann_alpha_kernel(const float* __restrict__ alphas, const T* __restrict__ dZ, co
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if ((l0 + u) < L) *reinterpret_cast<float4*>(tmp + ((int64_t)b * L + l0 + u) * D + d0 + cq) = acc[u];
+      if ((l0 + u) < L) st4(tmp + ((int64_t)b * L + l0 + u) * D + d0 + cq, acc[u]);
   }
 }

@@ -38,7 +38,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   const int sk_dh = tc_dh ? tc::pick_splitk(B, H, NH3_) : 1;
   SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)sk_dh * B * H, st));
   SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)B * H, st));
-  const bool dann_tc = tc && b.dP16 != nullptr && b.dann_tmp != nullptr && !std::is_same<TS, float>::value;
+  const bool dann_tc = tc && b.dP16 != nullptr && !std::is_same<TS, float>::value;
   const float scale = (float)(1.0 / sqrt((double)L));
   // pipelined attention backward: saves de_t per step and dP is rebuilt once after the loop (dP_deferred_kernel);
   // the plain kernel accumulates dP step by step and needs it zeroed
@@ -121,16 +121,17 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   // (for ncap > 1 the buffer holds per-caption rows [B,L,D]; the host sums the ncap rows of an image)
   EpiDAnn<TS> epi_dann{(TS*)b.d_ann, b.alphas, (const TS*)b.dZ, b.dmean, B, T, L, D, d.ncap, 1.0f / ((float)L * (float)d.ncap)};
   if (dann_tc) {
-    // tensor-core path: attention part + mean term in fp32 scratch, then dP16 * Wa with that scratch as a residual
+    // tensor-core path: the attention part + mean term is written to d_ann itself (operand dtype), then dP16 * Wa is
+    // added in place by the GEMM epilogue (every element is read and written by the same thread)
     const size_t sm = sizeof(float) * ((size_t)T * DANN_DC + (size_t)T * L);
-    auto kd = dann_alpha_kernel<TS>;
+    auto kd = dann_alpha_kernel<TS, TS>;
     if (sm > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kd<<<dim3(B, (D + DANN_DC - 1) / DANN_DC), 256, sm, st>>>(b.alphas, (const TS*)b.dZ, b.dmean, b.dann_tmp, B, T, L, D, d.ncap,
+    kd<<<dim3(B, (D + DANN_DC - 1) / DANN_DC), 256, sm, st>>>(b.alphas, (const TS*)b.dZ, b.dmean, (TS*)b.d_ann, B, T, L, D, d.ncap,
                                                               1.0f / ((float)L * (float)d.ncap));
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.dP16, A, A), (const TS*)w.WaT, A, B * L, D,
-                             EpiStore<TS, float>{(TS*)b.d_ann, D, nullptr, b.dann_tmp, D, 0}, st)));
+                             EpiStore<TS, TS>{(TS*)b.d_ann, D, nullptr, (const TS*)b.d_ann, D, 0}, st)));
   } else {
     SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.dP, A, A), (const TS*)w.WaT, A, B * L, D, epi_dann, st)));
   }

@@ -67,7 +67,6 @@ class TrainBuffers:
             t["dP"] = mk((B, L, A), f)
             if dtype != torch.float32:
                 t["dP16"] = mk((B, L, A), s)
-                t["dann_tmp"] = mk((B, L, D), f)
             t["dwf_part"] = mk((T, B, A), f)
             t["de"] = mk((T, B, L), f)
             t["dXe"] = mk((T, B, E), f)
@@ -189,7 +188,7 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
     G["lstm.bias_hh_l0"] = db.clone()
     G["attention.f_att.weight"] = t["dwf_part"].sum((0, 1)).reshape(1, A)
     ann = t["ann"].reshape(Bi * L, D)
-    if ncap == 1 and d.use_tc and "dP16" in t and "dann_tmp" in t and ann.dtype != torch.float32:
+    if ncap == 1 and d.use_tc and "dP16" in t and ann.dtype != torch.float32:
         dPm = t["dP16"].reshape(Bi * L, A)      # operand-dtype copy already written by the kernels
     else:
         dP = t["dP"]
