@@ -13,6 +13,7 @@
 //   groups, 16 consumer warps, and single-lane mbarrier polling.
 #pragma once
 #include <stdlib.h>
+#include <algorithm>
 
 #include <type_traits>
 
@@ -859,6 +860,285 @@ attention_step_fwd_group_tc_kernel(const __grid_constant__ CUtensorMap tm_ann, c
   }
 }
 
+// =============================================================================================
+// K1 grouped, tensor-core context, ROW-STREAMED (bf16, D a multiple of 256 up to 2048): the 2-D box kernel above fetches
+// 128 bytes per annotation row per box, which costs DRAM page locality (3.6 TB/s at D=2048).  Here the tile is streamed
+// as whole rows (1-D bulk copies, one per row, issued by 8-16 lanes of the producer warp) into stages whose rows are
+// padded by 16 bytes, which makes ldmatrix.trans conflict-free without a swizzle.  The product is transposed:
+//   zT[d, g] = sum_l ann[l, d] * alpha[g, l]      mma.sync.m16n8k8: M = 16 columns d, N = 8 caption rows, K = 8 locations
+// so no MMA row is wasted; warp w owns columns [w*D/8, (w+1)*D/8) (MT 16-column tiles, 4 accumulator registers each).
+// =============================================================================================
+template <bool kExact, int CW, int MT>
+__global__ void __launch_bounds__(CW * 32 + 32, 2)
+attention_step_fwd_group_tcr_kernel(const bf16* __restrict__ ann, const bf16* __restrict__ P, const float* __restrict__ wf,
+                                    const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t, int ncap,
+                                    int L, int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha,
+                                    float* __restrict__ qsave, bf16* __restrict__ z, bf16* __restrict__ gz, bf16* __restrict__ beta,
+                                    int64_t ld_z, int rows_per_stage, int nst, int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  typedef bf16 T;
+  constexpr int G = 8;
+  constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32;
+  static_assert(CW == 8, "column ranges are split over 8 consumer warps");
+  SAT_PDL_TRIGGER();      // ann, P, lens are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = blockIdx.x;
+  const int row0 = img * ncap;
+  AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
+  const int L4 = (L + 3) & ~3;
+  float* e = reinterpret_cast<float*>(smem_raw + sizeof(AttPipeSmem));   // [G][L4]
+  float* qs = e + G * L4;               // [G][A]
+  float* ws = qs + G * A;               // [A]
+  float* part = ws + A;                 // [2][G][CW]
+  const uint32_t stage_off = (uint32_t)((sizeof(AttPipeSmem) + sizeof(float) * (size_t)(G * L4 + G * A + A + 2 * G * CW) + 127) & ~(size_t)127);
+  uint8_t* stages = smem_raw + stage_off;
+  float* red = reinterpret_cast<float*>(stages);   // [G][D] fp32, after the ring is drained
+  const int rowb = D * (int)sizeof(T) + 16;        // padded row pitch in a stage
+
+  unsigned act = 0;
+  for (int g = 0; g < ncap; ++g)
+    if (lens == nullptr || t < lens[row0 + g]) act |= 1u << g;
+  const int RCP = stage_bytes / (A * (int)sizeof(T));
+  const int nP = (L + RCP - 1) / RCP;
+  const int RS = rows_per_stage, nA = (L + RS - 1) / RS;
+
+  if (act != 0 && tid == 0) {
+    for (int i = 0; i < nst; ++i) {
+      sat_mbar_init(&hd->full[i], 1);
+      sat_mbar_init(&hd->empty[i], ATTP_CWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == ATTP_CWARPS) {
+    if (act != 0) {                     // ===== producer warp: lane 0 arms the barrier, lanes 0..RS-1 copy one row each =====
+      const T* Pb = P + (int64_t)img * L * A;
+      const T* ab = ann + (int64_t)img * L * D;
+      for (int i = 0; i < nP + nA; ++i) {
+        const int st = i % nst;
+        const uint32_t ph = (uint32_t)(i / nst) & 1u;
+        uint8_t* dst = stages + (size_t)st * stage_bytes;
+        if (lane == 0) sat_mbar_wait(&hd->empty[st], ph ^ 1u);
+        __syncwarp();
+        if (i < nP) {
+          if (lane == 0) {
+            const int r0 = i * RCP, rows = min(RCP, L - r0);
+            const uint32_t bytes = (uint32_t)(rows * A * (int)sizeof(T));
+            sat_mbar_expect_tx(&hd->full[st], bytes);
+            sat_bulk_g2s(dst, Pb + (int64_t)r0 * A, bytes, &hd->full[st]);
+          }
+        } else {
+          // the last stage is filled up to a whole 8-row k-step with copies of the last row (finite data; its alpha is 0)
+          const int r0 = (i - nP) * RS, rows = min(RS, (min(RS, L - r0) + 7) & ~7);
+          if (lane == 0) sat_mbar_expect_tx(&hd->full[st], (uint32_t)(rows * D * (int)sizeof(T)));
+          __syncwarp();
+          if (lane < rows)
+            sat_bulk_g2s(dst + (size_t)lane * rowb, ab + (int64_t)min(r0 + lane, L - 1) * D, (uint32_t)(D * sizeof(T)), &hd->full[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  SAT_PDL_WAIT();
+  for (int g = 0; g < ncap; ++g) {
+    if (act & (1u << g)) continue;
+    const int64_t r = row0 + g;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) alpha[r * ld_alpha + l] = 0.0f;
+    for (int d = tid; d < D; d += ATTP_CONSUMERS) {
+      z[r * ld_z + d] = from_f<T>(0.f);
+      gz[r * ld_z + d] = from_f<T>(0.f);
+      if (beta) beta[r * ld_z + d] = from_f<T>(0.f);
+    }
+    if (qsave) for (int a = tid; a < A; a += ATTP_CONSUMERS) qsave[r * A + a] = 0.0f;
+  }
+  if (act == 0) return;
+  for (int i = tid; i < ncap * A; i += ATTP_CONSUMERS) {
+    const int g = i / A, a = i - g * A;
+    const float q = hp[(int64_t)(row0 + g) * ldhp + a];
+    qs[g * A + a] = q;
+    if (qsave && (act & (1u << g))) qsave[(int64_t)(row0 + g) * A + a] = q;
+  }
+  for (int a = tid; a < A; a += ATTP_CONSUMERS) ws[a] = wf[a];
+  sat_named_bar(1, ATTP_CONSUMERS);
+
+  float wreg[ATTP_KA][4];
+#pragma unroll
+  for (int k = 0; k < ATTP_KA; ++k) {
+    const int a = lane * 4 + 128 * k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wreg[k][i] = a < A ? ws[a + i] : 0.0f;
+  }
+  int it = 0;
+  for (int i = 0; i < nP; ++i, ++it) {
+    const int st = it % nst;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / nst) & 1u);
+    const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * stage_bytes);
+    const int r0 = i * RCP, rows = min(RCP, L - r0);
+    for (int l0 = warp * 4; l0 < rows; l0 += ATTP_CWARPS * 4) {
+      float4 p[ATTP_KA][4];
+#pragma unroll
+      for (int k = 0; k < ATTP_KA; ++k) {
+        const int a = lane * 4 + 128 * k;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          p[k][u] = (a < A && (l0 + u) < rows) ? ld4(Ps + (size_t)(l0 + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int g = 0; g < ncap; ++g) {
+        if (!(act & (1u << g))) continue;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < ATTP_KA; ++k) {
+          const int a = lane * 4 + 128 * k;
+          if (a < A) {
+            const float4 q4 = *reinterpret_cast<const float4*>(qs + g * A + a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              s4[u] = fmaf(wreg[k][0], sat_tanh<kExact>(p[k][u].x + q4.x), s4[u]);
+              s4[u] = fmaf(wreg[k][1], sat_tanh<kExact>(p[k][u].y + q4.y), s4[u]);
+              s4[u] = fmaf(wreg[k][2], sat_tanh<kExact>(p[k][u].z + q4.z), s4[u]);
+              s4[u] = fmaf(wreg[k][3], sat_tanh<kExact>(p[k][u].w + q4.w), s4[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s4[u] += __shfl_xor_sync(0xffffffffu, s4[u], o);
+        }
+        if (lane < 4 && (l0 + lane) < rows) {
+          const float sv = lane == 0 ? s4[0] : (lane == 1 ? s4[1] : (lane == 2 ? s4[2] : s4[3]));
+          e[g * L4 + r0 + l0 + lane] = sv * scale;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  float* pmax = part;
+  float* psum = part + G * CW;
+  for (int g = 0; g < ncap; ++g) {
+    float mx = -INFINITY;
+    if (act & (1u << g))
+      for (int l = tid; l < L; l += ATTP_CONSUMERS) mx = fmaxf(mx, e[g * L4 + l]);
+    mx = warp_max(mx);
+    if (lane == 0) pmax[g * CW + warp] = mx;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < ncap; ++g) {
+    if (!(act & (1u << g))) continue;
+    float mx = pmax[g * CW];
+#pragma unroll
+    for (int w2 = 1; w2 < ATTP_CWARPS; ++w2) mx = fmaxf(mx, pmax[g * CW + w2]);
+    float sum = 0.0f;
+    for (int l = tid; l < L; l += ATTP_CONSUMERS) {
+      const float pe = sat_exp<kExact>(e[g * L4 + l] - mx);
+      e[g * L4 + l] = pe;
+      sum += pe;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) psum[g * CW + warp] = sum;
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < G; ++g) {
+    float* eg = e + g * L4;
+    if (g >= ncap || !(act & (1u << g))) {
+      for (int l = tid; l < L4; l += ATTP_CONSUMERS) eg[l] = 0.0f;
+      continue;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int w2 = 0; w2 < ATTP_CWARPS; ++w2) sum += psum[g * CW + w2];
+    float* alpha_r = alpha + (int64_t)(row0 + g) * ld_alpha;
+    for (int l = tid; l < L4; l += ATTP_CONSUMERS) {
+      const float al = l < L ? eg[l] / sum : 0.0f;
+      eg[l] = al;
+      if (l < L) alpha_r[l] = al;
+    }
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+
+  // context: zT[d, g] accumulators, MT tiles of 16 columns per warp
+  float acc[MT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[m][i] = 0.0f;
+  const int gq = lane >> 2, kk = (lane & 3) * 2;                 // B fragment: caption row gq, locations kk, kk + 1 of a k-step
+  const float* eg = e + gq * L4;
+  const int dw0 = warp * (MT * 16);                              // first column of this warp
+  // ldmatrix.x4.trans lane addressing: lanes 8j..8j+7 give the 8 location rows of matrix j = columns dw0 + 32 p + 8 j ..
+  const uint32_t lane_off = (uint32_t)((lane & 7) * rowb + (dw0 + (lane >> 3) * 8) * (int)sizeof(T));
+  const uint32_t stages_u32 = sat_smem_u32(stages);
+  for (int j = 0; j < nA; ++j, ++it) {
+    const int st = it % nst;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / nst) & 1u);
+    const uint32_t sb = stages_u32 + (uint32_t)st * (uint32_t)stage_bytes + lane_off;
+    const int r0 = j * RS, rows = min(RS, L - r0);
+    for (int k0 = 0; k0 < rows; k0 += 8) {                       // rows past L inside a k-step: alpha = 0 below, the stage holds
+      const int l = r0 + k0 + kk;                                // stale but finite data there
+      const uint32_t bfr = sat_pack_bf16x2(l < L ? eg[l] : 0.0f, l + 1 < L ? eg[l + 1] : 0.0f);
+      const uint32_t kb = sb + (uint32_t)(k0 * rowb);
+#pragma unroll
+      for (int p = 0; p < MT / 2; ++p) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(kb + (uint32_t)(p * 32 * (int)sizeof(T))));
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                     : "+f"(acc[2 * p][0]), "+f"(acc[2 * p][1]), "+f"(acc[2 * p][2]), "+f"(acc[2 * p][3])
+                     : "r"(a0), "r"(a1), "r"(bfr));
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                     : "+f"(acc[2 * p + 1][0]), "+f"(acc[2 * p + 1][1]), "+f"(acc[2 * p + 1][2]), "+f"(acc[2 * p + 1][3])
+                     : "r"(a2), "r"(a3), "r"(bfr));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);     // the ring is drained: red[] may overwrite it
+  // C fragment: acc[m][0..1] = column dw0 + 16 m + lane/4, caption rows kk, kk+1;  acc[m][2..3] = column + 8
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    const int d = dw0 + m * 16 + gq;
+    red[(size_t)kk * D + d] = acc[m][0];
+    red[(size_t)(kk + 1) * D + d] = acc[m][1];
+    red[(size_t)kk * D + d + 8] = acc[m][2];
+    red[(size_t)(kk + 1) * D + d + 8] = acc[m][3];
+  }
+  sat_named_bar(1, ATTP_CONSUMERS);
+  for (int g = 0; g < ncap; ++g) {
+    if (!(act & (1u << g))) continue;
+    const int64_t r = row0 + g;
+    const float* hp_r = hp + r * ldhp + A;
+    for (int d = tid * 2; d < D; d += ATTP_CONSUMERS * 2) {
+      const float2 zs = *reinterpret_cast<const float2*>(red + (size_t)g * D + d);
+      const float2 hv = *reinterpret_cast<const float2*>(hp_r + d);
+      const float bt0 = sat_sigmoid<kExact>(hv.x), bt1 = sat_sigmoid<kExact>(hv.y);
+      *reinterpret_cast<uint32_t*>(z + r * ld_z + d) = sat_pack_bf16x2(zs.x, zs.y);
+      *reinterpret_cast<uint32_t*>(gz + r * ld_z + d) = sat_pack_bf16x2(bt0 * zs.x, bt1 * zs.y);
+      if (beta) *reinterpret_cast<uint32_t*>(beta + r * ld_z + d) = sat_pack_bf16x2(bt0, bt1);
+    }
+  }
+}
+
+// stage geometry of the row-streamed kernel: 8 or 16 padded rows per stage, as many stages as fit ~97 KB (<= ATTP_NST)
+struct AttTcrGeom { int rows, nst, stage_bytes; size_t smem; };
+static inline AttTcrGeom attention_fwd_group_tcr_geom(int L, int D, int A) {
+  AttTcrGeom g;
+  const int rowb = D * 2 + 16;
+  g.rows = rowb * 16 <= 20 * 1024 ? 16 : 8;
+  g.stage_bytes = (g.rows * rowb + 127) & ~127;
+  g.nst = (int)std::min<size_t>(ATTP_NST, (size_t)(97 * 1024) / g.stage_bytes);
+  g.smem = ((sizeof(AttPipeSmem) + sizeof(float) * (size_t)(8 * ((L + 3) & ~3) + 8 * A + A + 2 * 8 * ATTP_FWD_CW) + 127) & ~(size_t)127) + 128 +
+           (size_t)g.nst * g.stage_bytes;
+  return g;
+}
+
 static inline size_t attention_fwd_group_tc_smem(int L, int A) {
   return sizeof(AttPipeSmem) + sizeof(float) * (size_t)(8 * ((L + 3) & ~3) + 8 * A + A + 2 * 8 * ATTP_FWD_CW) + 1024 +
          (size_t)ATTP_NST * ATTP_STAGE_BYTES;
@@ -910,6 +1190,21 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
   if constexpr (std::is_same<T, bf16>::value && !kExact) {
     static const int group_tc_mode = getenv("SAT_ATT_GROUP_TC") ? atoi(getenv("SAT_ATT_GROUP_TC")) : 1;
     if (group && group_tc_mode != 0 && L <= 16 * ATTG_MAXKS && D % ATTG_BOX_COLS == 0 && ld_z % 2 == 0 && ldhp % 2 == 0 && A % 2 == 0) {
+      static const int tcr_mode = getenv("SAT_ATT_GROUP_TCR") ? atoi(getenv("SAT_ATT_GROUP_TCR")) : 1;
+      // measured: row-streamed 89 vs box 100 us at D=2048 (C5), but 49 vs 43 us at D=512 (1 KB rows: too many small copies)
+      if ((tcr_mode == 2 || (tcr_mode == 1 && D >= 1024)) && (D == 512 || D == 1024 || D == 2048)) {
+        const AttTcrGeom gm = attention_fwd_group_tcr_geom(L, D, A);
+        auto launch_r = [&](auto kern) -> int {
+          SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
+          SAT_CUDA(sat_launch_pdl(kern, dim3(rows / ncap), dim3(ATTP_FWD_CW * 32 + 32), gm.smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D,
+                                  A, scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z, gm.rows, gm.nst, gm.stage_bytes));
+          SAT_COUNT_LAUNCH();
+          return 0;
+        };
+        if (D == 512) return launch_r(attention_step_fwd_group_tcr_kernel<kExact, ATTP_FWD_CW, 4>);
+        if (D == 1024) return launch_r(attention_step_fwd_group_tcr_kernel<kExact, ATTP_FWD_CW, 8>);
+        return launch_r(attention_step_fwd_group_tcr_kernel<kExact, ATTP_FWD_CW, 16>);
+      }
       // annotations as a 2-D tensor [n_img * L, D]; the map is rebuilt only when the buffer or shape changes
       static CUtensorMap tm;
       static const void* tm_ptr = nullptr;

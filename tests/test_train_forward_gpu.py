@@ -85,6 +85,7 @@ def test_forward_bf16_vs_oracle(use_tc):
     dict(Bi=2, ncap=5, hw=(16, 16), D=2048, A=128, E=256, H=512, V=1000, T=5, ragged=True),     # config 5 tile, L=256
     dict(Bi=2, ncap=8, hw=(14, 14), D=512, A=128, E=256, H=512, V=1000, T=6, ragged=True),      # L=196: boxes overrun the image
     dict(Bi=3, ncap=2, hw=(14, 14), D=512, A=96, E=256, H=512, V=1000, T=6, ragged=False),
+    dict(Bi=2, ncap=3, hw=(14, 14), D=1024, A=128, E=256, H=512, V=1000, T=5, ragged=True),      # row-streamed kernel, partial last stage
 ])
 def test_forward_bf16_multi_caption_vs_oracle(cfg):
     """several caption rows per image in bf16: the grouped attention kernel (tensor-core context, alpha rounded to bf16)."""
