@@ -1183,13 +1183,13 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
   // several caption rows per image (beams / captions): one CTA per image streams the tiles once for all of them when
   // the per-image tile is large enough for the shared stream to pay (SAT_ATT_GROUP=0/1 forces the choice)
   static const int group_mode = getenv("SAT_ATT_GROUP") ? atoi(getenv("SAT_ATT_GROUP")) : -1;
-  const bool group_fit = ncap >= 2 && ncap <= 8 && rows % ncap == 0 &&
+  const bool group_fit = ncap >= 2 && ncap <= 8 && rows % ncap == 0 && L <= 512 &&
                          (size_t)ncap * (((D / Vec16<T>::N) >= ATTP_FWD_CW * 32 ? 1 : (ATTP_FWD_CW * 32) / (D / Vec16<T>::N)) * (size_t)D) *
                                  sizeof(float) <= (size_t)ATTP_NST * ATTP_STAGE_BYTES;
   const bool group = group_fit && (group_mode == 1 || (group_mode != 0 && (size_t)L * D * sizeof(T) >= SAT_ATT_GROUP_MIN_BYTES));
   if constexpr (std::is_same<T, bf16>::value && !kExact) {
     static const int group_tc_mode = getenv("SAT_ATT_GROUP_TC") ? atoi(getenv("SAT_ATT_GROUP_TC")) : 1;
-    if (group && group_tc_mode != 0 && L <= 16 * ATTG_MAXKS && D % ATTG_BOX_COLS == 0 && ld_z % 2 == 0 && ldhp % 2 == 0 && A % 2 == 0) {
+    if (group && group_tc_mode != 0 && D % ATTG_BOX_COLS == 0 && ld_z % 2 == 0 && ldhp % 2 == 0 && A % 2 == 0) {
       static const int tcr_mode = getenv("SAT_ATT_GROUP_TCR") ? atoi(getenv("SAT_ATT_GROUP_TCR")) : 1;
       // measured: row-streamed 89 vs box 100 us at D=2048 (C5), but 49 vs 43 us at D=512 (1 KB rows: too many small copies)
       if ((tcr_mode == 2 || (tcr_mode == 1 && D >= 1024)) && (D == 512 || D == 1024 || D == 2048)) {
@@ -1205,6 +1205,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
         if (D == 1024) return launch_r(attention_step_fwd_group_tcr_kernel<kExact, ATTP_FWD_CW, 8>);
         return launch_r(attention_step_fwd_group_tcr_kernel<kExact, ATTP_FWD_CW, 16>);
       }
+      if (L <= 16 * ATTG_MAXKS) {
       // annotations as a 2-D tensor [n_img * L, D]; the map is rebuilt only when the buffer or shape changes
       static CUtensorMap tm;
       static const void* tm_ptr = nullptr;
@@ -1221,6 +1222,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
                               scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z));
       SAT_COUNT_LAUNCH();
       return 0;
+      }
     }
   }
   if (group) {

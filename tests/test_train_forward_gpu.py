@@ -86,6 +86,8 @@ def test_forward_bf16_vs_oracle(use_tc):
     dict(Bi=2, ncap=8, hw=(14, 14), D=512, A=128, E=256, H=512, V=1000, T=6, ragged=True),      # L=196: boxes overrun the image
     dict(Bi=3, ncap=2, hw=(14, 14), D=512, A=96, E=256, H=512, V=1000, T=6, ragged=False),
     dict(Bi=2, ncap=3, hw=(14, 14), D=1024, A=128, E=256, H=512, V=1000, T=5, ragged=True),      # row-streamed kernel, partial last stage
+    dict(Bi=2, ncap=3, hw=(18, 18), D=1024, A=128, E=256, H=512, V=1000, T=4, ragged=True),      # L = 324 > 256: row-streamed only
+    dict(Bi=2, ncap=3, hw=(18, 18), D=512, A=128, E=256, H=512, V=1000, T=4, ragged=True),       # L = 324, D = 512: scalar grouped kernel
 ])
 def test_forward_bf16_multi_caption_vs_oracle(cfg):
     """several caption rows per image in bf16: the grouped attention kernel (tensor-core context, alpha rounded to bf16)."""
