@@ -529,6 +529,47 @@ class SAT(_Base):
         return decode.caption_from_annotations(self, ann, beamk, max_gen_length, temperature, rescore_method,
                                                rescore_reward, return_all)
 
+    @torch.no_grad()
+    def caption_stream(self, batches, beamk=3, max_gen_length=32, temperature=1.0, rescore_method=None, rescore_reward=0.5,
+                       return_all=False):
+        """Bulk captioning (extension; the reference captions one call at a time): `batches` yields image tensors
+        ([n,3,S,S], pinned host memory or device).  Yields caption()'s four lists per batch, in order.  The host->device
+        copy of batch i+1 runs on a copy stream while batch i is computed, and the device work of batch i+1 is queued
+        before the host turns batch i's device arrays into Python lists, so copies, kernels and host work overlap."""
+        from . import decode
+        self.eval()
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(dev)
+
+        def stage(x):
+            with torch.cuda.stream(copy_stream):
+                y = x.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return y, ev
+
+        vocab = dict(PAD=self.stoi("<PAD>"), START=self.stoi("<START>"), END=self.stoi("<END>"), UNK=self.stoi("<UNK>"))
+        dw = decode.inference_weights(self)
+        it = iter(batches)
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None
+        pending = None
+        while staged is not None:
+            img, ev = staged
+            cur.wait_event(ev)
+            img.record_stream(cur)
+            nxt = next(it, None)
+            staged = stage(nxt) if nxt is not None else None
+            ann = self.encode(img)
+            bld = decoder.annotations_as_bld(ann, dw.pw.dtype)
+            t = decode.decode_annotations(dw, bld, int(beamk), max_gen_length, temperature, rescore_method, rescore_reward, vocab)
+            if pending is not None:
+                yield decode.assemble(*pending, return_all=return_all)
+            pending = (t, tuple(ann.shape[2:]))
+        if pending is not None:
+            yield decode.assemble(*pending, return_all=return_all)
+
     # ---- optimisers (model.py:720-817; host-side, stock torch) ---------------------------------
     def configure_optimizers(self):
         hp = self.hparams

@@ -247,3 +247,15 @@ def test_embed_norm_renormalises_like_nn_embedding():
     assert relerr(m.embedding.weight, ref_emb.weight) < 1e-6      # same side effect on the parameter
     used = caps[..., :-1].reshape(-1).unique()
     assert float(m.embedding.weight[used.cuda()].norm(dim=1).max()) <= 1.0 + 1e-5
+
+
+def test_caption_stream_matches_caption():
+    """bulk captioning over pinned host batches returns, batch by batch, exactly what caption() returns"""
+    m = build(seed=11)
+    batches = [batch(20 + i, ncap=1)[0].pin_memory() for i in range(3)]       # encoder = Identity: "images" are annotations
+    got = list(m.caption_stream(batches, beamk=3, max_gen_length=8, rescore_method="LN"))
+    assert len(got) == 3
+    for b, out in zip(batches, got):
+        ref = m.caption(b.cuda(), beamk=3, max_gen_length=8, rescore_method="LN")
+        assert out[0] == ref[0]
+        assert max(abs(x - y) for x, y in zip(out[1], ref[1])) < 1e-6
