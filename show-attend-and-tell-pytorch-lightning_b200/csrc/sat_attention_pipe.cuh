@@ -1560,12 +1560,12 @@ constexpr int DPD_ROWS = 32;
 template <typename T, bool kExact>
 __global__ void __launch_bounds__(256)
 dP_deferred_kernel(const T* __restrict__ P, const float* __restrict__ wf, const float* __restrict__ Q,
-                   const float* __restrict__ de, const int32_t* __restrict__ lens, int ncap, int B, int L, int A,
+                   const float* __restrict__ de, const int32_t* __restrict__ lens, int ncap, int B, int L, int A, int Tmax,
                    float* __restrict__ dP, T* __restrict__ dP16) {
   extern __shared__ __align__(16) float dpd_smem[];
   const int b = blockIdx.y, r0 = blockIdx.x * DPD_ROWS, rows = min(DPD_ROWS, L - r0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Tb = lens[b];
+  const int Tb = min(lens[b], Tmax);    // shared memory is sized for Tmax steps
   float* qs = dpd_smem;                       // [Tb][A]
   float* des = qs + (size_t)Tb * A;           // [Tb][DPD_ROWS]
   for (int i = tid; i < Tb * A; i += 256) qs[i] = Q[((int64_t)(i / A) * B + b) * A + (i % A)];

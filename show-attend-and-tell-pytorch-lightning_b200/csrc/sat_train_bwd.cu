@@ -83,7 +83,7 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     const size_t sm = sizeof(float) * (size_t)T * (A + DPD_ROWS);
     auto kp = dP_deferred_kernel<TS, kExact>;
     if (sm > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kp<<<dim3((L + DPD_ROWS - 1) / DPD_ROWS, B), 256, sm, st>>>((const TS*)b.P, w.wf, b.Q, b.de, b.lens, d.ncap, B, L, A, b.dP,
+    kp<<<dim3((L + DPD_ROWS - 1) / DPD_ROWS, B), 256, sm, st>>>((const TS*)b.P, w.wf, b.Q, b.de, b.lens, d.ncap, B, L, A, T, b.dP,
                                                               dann_tc ? (TS*)b.dP16 : (TS*)nullptr);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, decoder
+from . import _lib, _redzone, decoder
 from .packing import PackedWeights
 
 RESCORE = {None: 0, "LN": 1, "WR": 2, "BAR": 3}
@@ -43,7 +43,12 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     dtype = dw.pw.dtype
     d = decoder.make_dims(R, n_img, L, D, A, E, H, V, S + 1, dtype, dw.exact, dw.use_tc, dw.pw.plain_output)
     f, s, i32 = torch.float32, dtype, torch.int32
-    mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+    _n = [0]
+
+    def mk(shape, dt):                  # torch.empty unless SAT_REDZONE=1 (guard bands, tests)
+        _n[0] += 1
+        return _redzone.empty(shape, dt, dev, "decode buffer #%d" % _n[0])
+
     t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * H), f),
              h=mk((R, H), s), c=mk((R, H), f), hn=mk((R, H), s), cn=mk((R, H), f), hp=mk((R, A + D + 4 * H), f),
              z=mk((R, D), s), gz=mk((R, D), s), xo=mk((R, E), s), logits=mk((R, V), f), alpha_all=mk((S + 1, R, L), f),

@@ -7,7 +7,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, _redzone
 from .packing import PackedWeights, deinterleave_gates
 
 
@@ -29,8 +29,8 @@ class TrainBuffers:
         B, Bi, L, D, A, E, H, V, T = d.B, d.Bi, d.L, d.D, d.A, d.E, d.H, d.V, d.T
         NH3 = A + D + 4 * H
         s, f = dtype, torch.float32
-        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
         t = self.t = {}
+        mk = lambda shape, dt: _redzone.empty(shape, dt, device, "train buffer #%d" % len(t))   # torch.empty unless SAT_REDZONE=1
         t["tok"] = mk((T, B), torch.int32)
         t["P"] = mk((Bi, L, A), s)
         t["meanv"] = mk((Bi, D), s)
