@@ -339,6 +339,17 @@ def run_train(args):
             "avg_launch_us": 1e3 * att_ms / max(att_n, 1), "algorithmic_bytes_per_launch": att_bytes,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
 
+    # the backward attention kernel is the largest single decoder item by time; report it next to the forward kernel
+    _lib.profile_begin(2)
+    for _ in range(3):
+        dec_step()
+    attb_ms, attb_n = _lib.profile_end()
+    attb_bytes = B * (DIMS["L"] * (DIMS["A"] + DIMS["D"]) * s + 2 * DIMS["D"] * s + 8 * DIMS["L"])
+    attb = attb_bytes / (attb_ms / max(attb_n, 1) * 1e-3) / 1e9 if attb_n else None
+    roof["other_kernels"] = [{"kernel": "attention_step_bwd_pipe_kernel", "bound": "hbm", "achieved": attb, "peak": peak,
+                              "unit": "GB/s", "frac": (attb / peak) if attb else None, "launches_timed": attb_n,
+                              "avg_launch_us": 1e3 * attb_ms / max(attb_n, 1), "algorithmic_bytes_per_launch": attb_bytes}]
+
     line = None
     if rank == 0:
         line = {
