@@ -57,8 +57,9 @@ __device__ __forceinline__ void sat_named_bar(int id, int nthreads) {
 
 constexpr int ATTP_MAXCW = 16;                       // max consumer warps (template parameter CW of the kernels)
 constexpr int ATTP_FWD_CW = 8;                       // forward: 8 consumer warps measured fastest (17.8 us vs 25.8 us at B=256 bf16)
-constexpr int ATTP_BWD_CW = 12;                      // backward: 12 consumer warps at <= 78 registers keep two CTAs per SM (16 warps
-                                                     // at 96 registers dropped to one CTA per SM = two waves at B=256)
+constexpr int ATTP_BWD_CW = 8;                       // backward: with the dP accumulation deferred, 8 consumer warps (16-row stages:
+                                                     // 2 rows per warp, 86 registers) beat 12 (25.1 vs 27.3 us at C2, 91 vs 97 us at
+                                                     // C3 dims) and 16 (30 us, spills); two CTAs per SM either way
 constexpr int ATTP_NST = 6;
 constexpr int ATTP_STAGE_BYTES = 16384;
 constexpr size_t SAT_ATT_GROUP_MIN_BYTES = 0;   // per-image annotation tile from which the grouped kernel is used (measured faster at every size tried)
