@@ -1431,20 +1431,39 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
         s = warp_sum(s);
         if (lane == 0) dalp[seg * L4 + r0 + l] = s;
       }
-    } else
-    for (int l = warp; l < rows; l += ATTP_CWARPS) {
-      float s = 0.0f;
-      if (regpath) {
+    } else if (regpath) {
+      // two rows of the stage per pass (independent FMA chains and shuffle trees)
+      for (int l = warp; l < rows; l += 2 * ATTP_CWARPS) {
+        const int l2 = l + ATTP_CWARPS;
+        const bool h2 = l2 < rows;
+        float s = 0.0f, s2 = 0.0f, sb = 0.0f, s2b = 0.0f;
 #pragma unroll
         for (int k = 0; k < ATTB_VPL; ++k) {
           const int cv = lane + 32 * k;
           if (cv < NV) {
-            float v[VN];
+            float v[VN], v2[VN];
             Vec16<T>::load_shared(As + (size_t)l * D + cv * VN, v);
+            Vec16<T>::load_shared(As + (size_t)(h2 ? l2 : l) * D + cv * VN, v2);
 #pragma unroll
-            for (int i = 0; i < VN; ++i) s = fmaf(v[i], dzr[k][i], s);
+            for (int i = 0; i < VN; i += 2) {
+              s = fmaf(v[i], dzr[k][i], s);
+              sb = fmaf(v[i + 1], dzr[k][i + 1], sb);
+              s2 = fmaf(v2[i], dzr[k][i], s2);
+              s2b = fmaf(v2[i + 1], dzr[k][i + 1], s2b);
+            }
           }
         }
+        s = warp_sum(s + sb);
+        s2 = warp_sum(s2 + s2b);
+        if (lane == 0) {
+          dal[r0 + l] += s;
+          if (h2) dal[r0 + l2] += s2;
+        }
+      }
+    } else
+    for (int l = warp; l < rows; l += ATTP_CWARPS) {
+      float s = 0.0f;
+      if (false) {
       } else {
         for (int cv = lane; cv < NV; cv += 32) {
           float v[VN];
