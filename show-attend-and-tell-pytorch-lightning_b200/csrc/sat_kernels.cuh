@@ -520,18 +520,28 @@ __global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* 
   if (idx >= B * H) return;
   const int b = idx / H, j = idx - b * H;
   TS* dg = dG + (int64_t)b * ld_dg + 4 * j;
-  if (t >= lens[b]) {
+  // every operand is fetched before the first dependent instruction (one exposed latency; all addresses are valid for
+  // finished rows too)
+  const int len_b = lens[b];
+  const float4 g4 = ld4(gates + (int64_t)b * 4 * H + 4 * j);
+  const float cp = c_prev[idx], cn = c_next[idx];
+  const float dho = dHo[(int64_t)b * ld_dho + j], dc_in = dc[idx];
+  float dhs = 0.0f;
+  for (int sp0 = 0; sp0 < ns_dh; sp0 += 8) {      // split-K partials of the h-chain GEMM, 8 loads in flight
+    float p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) p[u] = (sp0 + u) < ns_dh ? dh[(int64_t)(sp0 + u) * dh_stride + idx] : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dhs += p[u];
+  }
+  if (t >= len_b) {
     st4(dg, make_float4(0.f, 0.f, 0.f, 0.f));
     return;
   }
-  const float4 g4 = ld4(gates + (int64_t)b * 4 * H + 4 * j);
   const float gi = g4.x, gf = g4.y, gg = g4.z, go = g4.w;
-  const float cp = c_prev[idx], cn = c_next[idx];
   const float tc = sat_tanh<kExact>(cn);
-  float dhs = 0.0f;
-  for (int sp = 0; sp < ns_dh; ++sp) dhs += dh[(int64_t)sp * dh_stride + idx];     // split-K partials of the h-chain GEMM
-  const float dht = dhs + dHo[(int64_t)b * ld_dho + j];
-  const float dct = dc[idx] + dht * go * (1.0f - tc * tc);
+  const float dht = dhs + dho;
+  const float dct = dc_in + dht * go * (1.0f - tc * tc);
   st4(dg, make_float4(dct * gg * gi * (1.0f - gi), dct * cp * gf * (1.0f - gf), dct * gi * (1.0f - gg * gg),
                       dht * tc * go * (1.0f - go)));
   dc[idx] = dct * gf;
