@@ -1578,7 +1578,7 @@ attention_step_bwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
 // caption): q[:,b,:] and de[:,b,tile] are staged in smem, every warp walks 4 rows at a time, a lane owns 4 columns.
 constexpr int DPD_ROWS = 32;
 template <typename T, bool kExact>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 dP_deferred_kernel(const T* __restrict__ P, const float* __restrict__ wf, const float* __restrict__ Q,
                    const float* __restrict__ de, const int32_t* __restrict__ lens, int ncap, int B, int L, int A, int Tmax,
                    float* __restrict__ dP, T* __restrict__ dP16) {
