@@ -16,7 +16,12 @@
  *  - dtype is the operand/storage type of activations and packed weights (SAT_F32 or
  *    SAT_BF16); accumulation, cell state, softmax, losses are always fp32;
  *  - shapes: B caption rows (= Bi images * ncap), L locations, D encoder_dim, A attention_dim,
- *    E embed_dim, H decoder_dim, V vocab, T decoder steps.  D, A, E, H, V must be multiples of 8.
+ *    E embed_dim, H decoder_dim, V vocab, T decoder steps.  The kernels work on STORAGE dims D, A, E, H, V that are
+ *    multiples of 8 (16-byte vectors, TMA rows); a module with other sizes (V = words above min_count + 4, 100/300-d GloVe
+ *    embeddings ...) is zero-padded by sat_pack_weights: SatDims carries both the storage dims and the module's true dims
+ *    (D0 .. V0).  Zero weights keep every padded lane exactly zero through forward and backward; padded vocabulary
+ *    entries carry a bias of -inf, the cross-entropy / top-k kernels never select them, parameter gradients are written
+ *    with the true shapes.
  *  - "gate-interleaved": row 4*j+g of a packed LSTM weight is row g*H+j of the torch weight
  *    (g = 0..3 for i,f,g,o), so the four gates of hidden unit j are adjacent output columns.
  */
@@ -33,7 +38,7 @@ extern "C" {
 #define SAT_BF16 1
 #define SAT_ERR_INVALID (-1)
 
-#define SAT_ABI_VERSION 1
+#define SAT_ABI_VERSION 2
 
 typedef struct SatDims {
   int32_t B, Bi, ncap;
@@ -42,6 +47,8 @@ typedef struct SatDims {
   int32_t exact;      /* 1: libm-accurate tanh/exp (fp32 parity mode); 0: MUFU approximations */
   int32_t use_tc;     /* 1: tcgen05 tensor-core GEMMs where the shape allows (bf16 only); 0: SIMT FFMA GEMMs */
   int32_t plain_output; /* 1: DeepOutput with deep=False (model.py:128-129: x = W_ho h', no tanh / embedding / context); 0: deep */
+  int32_t D0, A0, E0, H0, V0; /* true sizes of the reference module (<= the storage dims above; 0 = same as storage) */
+  int32_t reserved0;
 } SatDims;
 
 /* Packed decoder weights (device).  "s" = storage dtype of SatDims.dtype. */
@@ -125,13 +132,20 @@ typedef struct SatTrainBuffers {
   void* Beta;            /* [T,B,D] s    beta_t                                                    */
   void* Gates;           /* [T,B,4H] s   post-activation i,f,g,o (gate-interleaved)                */
   void* Xo;              /* [T,B,E] s    tanh(Xe + W_ho h' + W_zo z)                               */
-  void* logits;          /* [T,B,V]      s, or fp32 when logits_f32 != 0; zeros where inactive     */
+  void* logits;          /* [T,B,V]      s, or fp32 when logits_f32 != 0; zeros where inactive.  May be NULL when ce_stats is
+                                         given (fused path)                                        */
   void* dlogits;         /* [T,B,V] s    (softmax - target dist)/N_tok; may alias `logits` when the
                                          caller does not need the logits back; NULL = not wanted   */
   float* row_loss;       /* [T,B]        per-token loss (0 where inactive)                         */
   int32_t* row_argmax;   /* [T,B]        argmax_v logits (-1 where inactive)                       */
   float* S;              /* [B,L]        sum_t alphas                                              */
-  float* out;            /* [8]          loss, cross-entropy part, doubly-stochastic part, accuracy, 1/N_tok, N_tok */
+  float* out;            /* [8]          loss, cross-entropy part, doubly-stochastic part, accuracy, 1/N_tok, N_tok,
+                                         [6] = 1 when a caption held a word id outside [0, V0) (such ids are fed as <PAD>) */
+  /* fused vocabulary projection + cross entropy (tensor-core mode, logits == NULL): the [T,B,V] logits are never written;
+   * the forward keeps per-tile soft-max statistics, the backward-enabled forward recomputes the tiles into dlogits */
+  float* ce_stats;       /* [T*B, ceil(V/128), 4]  max, sum exp(x - max), sum x, arg-max per 128-column tile; NULL = unfused path */
+  float* row_lse;        /* [T*B]        log-sum-exp of every token row                            */
+  float* row_xt;         /* [T*B]        logit of the target word                                  */
   /* bwd */
   const float* gscale;   /* [1]          upstream d(loss) (device scalar)                          */
   const float* dalpha_ext; /* [B,T,L] or NULL: extra upstream grad wrt alphas (API path: train_batch's alphas
@@ -146,7 +160,6 @@ typedef struct SatTrainBuffers {
   float* dP;             /* [B,L,A]      accumulated grad wrt P                                    */
   void* dP16;            /* [B,L,A] s    copy of dP in the operand dtype, written at the last backward step (t = 0);
                                          feeds the tensor-core d_ann GEMM (may be NULL in fp32 mode)          */
-  float* dann_tmp;       /* unused (kept for layout stability): the tensor-core d_ann path now accumulates in d_ann; may be NULL */
   float* dwf_part;       /* [T,B,A]      per-(b,t) partial of d f_att.weight                       */
   float* de;             /* [T,B,L]      scaled softmax-backward term of each step; dP is rebuilt from it, Q and P
                                           after the time loop (NULL: the slower step-by-step accumulation is used)  */
@@ -187,6 +200,8 @@ typedef struct SatDecodeBuffers {
   void* xo;              /* [R,E] s                                                               */
   float* logits;         /* [R,V]                                                                 */
   float* alpha_all;      /* [S+1,R,L]  alpha of every step and row (histories hold row indices)    */
+  float* topk_stats;     /* [R, ceil(V/128), 4] or NULL: greedy (k = 1) tensor-core decode keeps per-tile soft-max statistics
+                                         and the best word instead of writing the logits                       */
   float* cand_val;       /* [R,k]                                                                 */
   int32_t* cand_idx;     /* [R,k]                                                                 */
   int32_t* tok_hist;     /* [2,R,S+1]  generated words per live beam (ping-pong)                   */
@@ -210,7 +225,7 @@ typedef struct SatDecodeBuffers {
 
 int sat_version(void);
 const char* sat_last_error(void);
-/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers, 3 SatDecodeBuffers, 4 SatMasterWeights */
+/* sizeof() of the ABI structs as compiled, so the ctypes mirror can verify itself: 0 SatDims, 1 SatWeights, 2 SatTrainBuffers, 3 SatDecodeBuffers, 4 SatMasterWeights, 5 SatParamGrads */
 int sat_abi_sizeof(int which);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 unsigned long long sat_launch_count(void);
@@ -231,6 +246,12 @@ int sat_profile_end(float* total_ms, int* count);
  * Replaces torch.nn.Linear call sites model.py:72-73,90-92,119-123,188. */
 int sat_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                int32_t M, int32_t N, int32_t K, int32_t dtype, int32_t c_f32, int32_t use_tc, void* stream);
+
+/* C[z][N1,N2] (fp32, ldc, one slab of N1*ldc floats per k split z < splitk) = sum over the z-th share of the Krows rows of
+ * A[k,n1] * B[k,n2]: the "NT" GEMM core of the weight gradients dW = dY^T X (what autograd's mm_backward does for the
+ * nn.Linear call sites model.py:72-73,90-92,119-123,188).  Exported for unit tests; sat_train_param_grads is the user. */
+int sat_linear_nt(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t Krows, int32_t N1, int32_t N2,
+                  int32_t dtype, int32_t use_tc, int32_t splitk, void* stream);
 
 /* Once per image: P = ann * Wa^T (model.py:100), mean over L (model.py:78), factorize/init Linear
  * layers (model.py:79) and the [B,2H] -> [2,B,H] state reinterpretation (model.py:79-80) into
@@ -256,9 +277,44 @@ int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b,
 
 /* Hand-written BPTT of sat_train_forward (what autograd derives from model.py:510-548): fills
  * dlogits-derived buffers, DY, dZ, dP, dwf_part, dXe, d_init_out, df1, dmean, d_ann.  The
- * reductions over (b,t) that produce parameter gradients are plain GEMMs on these buffers and
- * are done by the host (cuBLAS through torch). */
+ * reductions over (b,t) that produce the parameter gradients are sat_train_param_grads below. */
 int sat_train_backward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
+
+/* Destinations of the parameter gradients: fp32 device buffers with the reference's parameter shapes (true dims, contiguous;
+ * SURVEY.md §A.3).  NULL = not wanted. */
+typedef struct SatParamGrads {
+  float* embedding;    /* embedding.weight [V0,E0]  (row pad_idx is zero: nn.Embedding(padding_idx), model.py:162)     */
+  float* fact_w;       /* init_lstm.factorize.weight [E0,D0]   */
+  float* fact_b;       /* init_lstm.factorize.bias [E0]        */
+  float* init_w;       /* init_lstm.init.weight [2H0,E0]       */
+  float* init_b;       /* init_lstm.init.bias [2H0]            */
+  float* w_ih;         /* lstm.weight_ih_l0 [4H0,E0+D0]        */
+  float* w_hh;         /* lstm.weight_hh_l0 [4H0,H0]           */
+  float* b_ih;         /* lstm.bias_ih_l0 [4H0]                */
+  float* b_hh;         /* lstm.bias_hh_l0 [4H0]                */
+  float* enc_att;      /* attention.encoder_att.weight [A0,D0] */
+  float* dec_att;      /* attention.decoder_att.weight [A0,H0] */
+  float* f_att;        /* attention.f_att.weight [1,A0]        */
+  float* beta_w;       /* beta.0.weight [D0,H0]                */
+  float* beta_b;       /* beta.0.bias [D0]                     */
+  float* out_hidden;   /* output.hidden.weight [E0,H0]         */
+  float* out_context;  /* output.context.weight [E0,D0] (deep output only) */
+  float* out_w;        /* output.output.weight [V0,E0]; NULL when weight-tied */
+  float* out_b;        /* output.output.bias [V0] or NULL      */
+  int32_t pad_idx;     /* embedding row whose own gradient is zero, -1 = none */
+  int32_t weight_tying;/* 1: output.output.weight IS embedding.weight (model.py:198-199): its gradient is added into `embedding` */
+} SatParamGrads;
+
+/* Bytes of scratch sat_train_param_grads needs for these dims (split-k partials, column-sum partials). */
+int64_t sat_param_grads_workspace_bytes(const SatDims* d);
+
+/* Parameter gradients of the step whose buffers `b` holds (after sat_train_forward + sat_train_backward): the reductions
+ * over (t, b) that autograd performs for model.py:510-548 -- dW = dY^T X on the tensor cores (split-k, partials added in
+ * fixed order), bias / f_att column sums, the embedding segment sum, gate de-interleave and un-padding -- all inside the
+ * library and bit-reproducible from run to run (the reference trains with deterministic=True, train.py:271).
+ * `workspace` is 256-byte aligned device memory of at least sat_param_grads_workspace_bytes(d) bytes. */
+int sat_train_param_grads(const SatDims* d, const SatTrainBuffers* b, const SatParamGrads* g, void* workspace, int64_t workspace_bytes,
+                          void* stream);
 
 /* GxV[v,:] = Emb[v,:] * Wihe^T + bg for every vocabulary entry (once per set of weights). */
 int sat_decode_prepare_weights(const SatDims* d, const SatWeights* w, float* GxV, void* stream);

@@ -15,7 +15,8 @@ vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # all device pointers travel a
 
 class SatDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("B", "Bi", "ncap", "L", "D", "A", "E", "H", "V", "T", "dtype", "exact", "use_tc", "plain_output")]
+                ("B", "Bi", "ncap", "L", "D", "A", "E", "H", "V", "T", "dtype", "exact", "use_tc", "plain_output",
+                 "D0", "A0", "E0", "H0", "V0", "reserved0")]
 
 
 class SatWeights(C.Structure):
@@ -34,7 +35,8 @@ class SatTrainBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "caps", "lens", "sampled", "tok", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
                  "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
-                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dann_tmp", "dwf_part", "de", "dXe", "d_init_out",
+                 "ce_stats", "row_lse", "row_xt",
+                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dwf_part", "de", "dXe", "d_init_out",
                  "df1", "d_init_out16", "df116", "dmean", "d_ann")] + \
                [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("dropout_p", C.c_float),
                 ("emb_dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("logits_f32", C.c_int32),
@@ -44,15 +46,23 @@ class SatTrainBuffers(C.Structure):
 class SatDecodeBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "P", "meanv", "f1", "init_out", "GxV", "h", "c", "hn", "cn", "hp", "z", "gz", "xo", "logits",
-                 "alpha_all", "cand_val", "cand_idx", "tok_hist", "asrc_hist", "top_scores", "cur_tok", "src_row", "alive",
+                 "alpha_all", "topk_stats", "cand_val", "cand_idx", "tok_hist", "asrc_hist", "top_scores", "cur_tok", "src_row", "alive",
                  "kcur", "fin_tokens", "fin_asrc", "fin_len", "fin_score", "fin_ppl", "fin_count", "temps")] + \
                [("k", C.c_int32), ("max_gen_length", C.c_int32), ("rescore", C.c_int32), ("reward", C.c_float),
                 ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32)]
 
 
+class SatParamGrads(C.Structure):
+    _fields_ = [(n, vp) for n in
+                ("embedding", "fact_w", "fact_b", "init_w", "init_b", "w_ih", "w_hh", "b_ih", "b_hh", "enc_att", "dec_att",
+                 "f_att", "beta_w", "beta_b", "out_hidden", "out_context", "out_w", "out_b")] + \
+               [("pad_idx", C.c_int32), ("weight_tying", C.c_int32)]
+
+
 EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end", "sat_dropout_multiplier", "sat_pack_weights",
-           "sat_linear", "sat_prepare_images",
-           "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward", "sat_decode_prepare_weights", "sat_decode"]
+           "sat_linear", "sat_linear_nt", "sat_prepare_images",
+           "sat_attention_step_fwd", "sat_train_forward", "sat_train_backward", "sat_param_grads_workspace_bytes", "sat_train_param_grads",
+           "sat_decode_prepare_weights", "sat_decode"]
 
 _lib = None
 
@@ -83,7 +93,7 @@ def lib():
     L.sat_last_error.restype = C.c_char_p
     L.sat_launch_count.restype = C.c_ulonglong
     L.sat_abi_sizeof.argtypes = [C.c_int]
-    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers, SatDecodeBuffers, SatMasterWeights)):
+    for i, st in enumerate((SatDims, SatWeights, SatTrainBuffers, SatDecodeBuffers, SatMasterWeights, SatParamGrads)):
         if L.sat_abi_sizeof(i) != C.sizeof(st):
             raise SatError("ABI mismatch for %s: lib %d vs ctypes %d" % (st.__name__, L.sat_abi_sizeof(i), C.sizeof(st)))
     L.sat_dropout_multiplier.argtypes = [C.c_float, C.c_uint64, C.c_uint32, C.c_uint64]
@@ -93,11 +103,16 @@ def lib():
     L.sat_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.sat_linear.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                              C.c_int32, C.c_int32, C.c_int32, vp]
+    L.sat_linear_nt.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, vp]
     L.sat_prepare_images.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), vp, vp, vp, vp, vp, vp, vp, vp]
     L.sat_attention_step_fwd.argtypes = [C.POINTER(SatDims), vp, vp, vp, vp, C.c_int64, vp, C.c_int32, vp, C.c_int64,
                                          vp, vp, vp, C.c_int64, vp]
     L.sat_train_forward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
     L.sat_train_backward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
+    L.sat_param_grads_workspace_bytes.argtypes = [C.POINTER(SatDims)]
+    L.sat_param_grads_workspace_bytes.restype = C.c_int64
+    L.sat_train_param_grads.argtypes = [C.POINTER(SatDims), C.POINTER(SatTrainBuffers), C.POINTER(SatParamGrads), vp, C.c_int64, vp]
     L.sat_decode_prepare_weights.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), vp, vp]
     L.sat_decode.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatDecodeBuffers), vp]
     _lib = L

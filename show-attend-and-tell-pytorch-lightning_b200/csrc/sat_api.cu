@@ -67,6 +67,7 @@ int sat_abi_sizeof(int which) {
     case 2: return (int)sizeof(SatTrainBuffers);
     case 3: return (int)sizeof(SatDecodeBuffers);
     case 4: return (int)sizeof(SatMasterWeights);
+    case 5: return (int)sizeof(SatParamGrads);
     default: return -1;
   }
 }

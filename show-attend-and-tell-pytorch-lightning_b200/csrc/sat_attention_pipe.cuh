@@ -78,14 +78,17 @@ attention_step_fwd_pipe_kernel(const T* __restrict__ ann, const T* __restrict__ 
                                const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t, int ncap,
                                int L, int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha,
                                float* __restrict__ qsave, T* __restrict__ z, T* __restrict__ gz, T* __restrict__ beta,
-                               int64_t ld_z) {
+                               int64_t ld_z, int lens_dyn) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32, ATTP_THREADS = CW * 32 + 32;
-  // Programmatic dependent launch: ann, P and lens are never written inside a launch chain (P's GEMM is always followed
-  // by a fully serialised launch), so the ring is primed while the predecessor kernel is still draining; everything that
-  // reads the predecessor's output (or writes) sits behind SAT_PDL_WAIT() on the consumer side.
+  // Programmatic dependent launch: ann and P are never written inside a launch chain (P's GEMM is always followed by a
+  // fully serialised launch), so the ring is primed while the predecessor kernel is still draining; everything that
+  // reads the predecessor's output (or writes) sits behind SAT_PDL_WAIT() on the consumer side.  `lens` is constant in
+  // the training chain (lens_dyn = 0) but is the beam-liveness array in decode, rewritten every step by
+  // beam_update_kernel (lens_dyn = 1): there every thread waits for the predecessors BEFORE reading it.
   SAT_PDL_TRIGGER();
+  if (lens_dyn) SAT_PDL_WAIT();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   AttPipeSmem* hd = reinterpret_cast<AttPipeSmem*>(smem_raw);
@@ -332,11 +335,12 @@ attention_step_fwd_group_kernel(const T* __restrict__ ann, const T* __restrict__
                                 const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t, int ncap,
                                 int L, int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha,
                                 float* __restrict__ qsave, T* __restrict__ z, T* __restrict__ gz, T* __restrict__ beta,
-                                int64_t ld_z) {
+                                int64_t ld_z, int lens_dyn) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int VN = Vec16<T>::N;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32;
-  SAT_PDL_TRIGGER();      // ann, P, lens are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  SAT_PDL_TRIGGER();      // ann, P are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  if (lens_dyn) SAT_PDL_WAIT();      // decode: lens (= alive) is rewritten every step by beam_update_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.x;
   const int row0 = img * ncap;          // first caption row of this image; rows row0 .. row0 + ncap - 1  (ncap <= G)
@@ -625,13 +629,14 @@ attention_step_fwd_group_tc_kernel(const __grid_constant__ CUtensorMap tm_ann, c
                                    const float* __restrict__ wf, const float* __restrict__ hp, int64_t ldhp,
                                    const int32_t* __restrict__ lens, int t, int ncap, int L, int D, int A, float scale,
                                    float* __restrict__ alpha, int64_t ld_alpha, float* __restrict__ qsave, bf16* __restrict__ z,
-                                   bf16* __restrict__ gz, bf16* __restrict__ beta, int64_t ld_z) {
+                                   bf16* __restrict__ gz, bf16* __restrict__ beta, int64_t ld_z, int lens_dyn) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   typedef bf16 T;
   constexpr int G = 8;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32;
   static_assert(CW == 8, "one consumer warp per 8-column slice of a 64-column box");
-  SAT_PDL_TRIGGER();      // ann, P, lens are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  SAT_PDL_TRIGGER();      // ann, P are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  if (lens_dyn) SAT_PDL_WAIT();      // decode: lens (= alive) is rewritten every step by beam_update_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.x;
   const int row0 = img * ncap;
@@ -875,13 +880,14 @@ attention_step_fwd_group_tcr_kernel(const bf16* __restrict__ ann, const bf16* __
                                     const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t, int ncap,
                                     int L, int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha,
                                     float* __restrict__ qsave, bf16* __restrict__ z, bf16* __restrict__ gz, bf16* __restrict__ beta,
-                                    int64_t ld_z, int rows_per_stage, int nst, int stage_bytes) {
+                                    int64_t ld_z, int lens_dyn, int rows_per_stage, int nst, int stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   typedef bf16 T;
   constexpr int G = 8;
   constexpr int ATTP_CWARPS = CW, ATTP_CONSUMERS = CW * 32;
   static_assert(CW == 8, "column ranges are split over 8 consumer warps");
-  SAT_PDL_TRIGGER();      // ann, P, lens are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  SAT_PDL_TRIGGER();      // ann, P are never written inside a launch chain: the ring is primed before SAT_PDL_WAIT()
+  if (lens_dyn) SAT_PDL_WAIT();      // decode: lens (= alive) is rewritten every step by beam_update_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.x;
   const int row0 = img * ncap;
@@ -1171,7 +1177,7 @@ static inline bool attention_pipe_ok(int L, int D, int A) {
 template <typename T, bool kExact>
 static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const float* hp, int64_t ldhp, const int32_t* lens,
                                 int t, int rows, int ncap, int L, int D, int A, float scale, float* alpha, int64_t ld_alpha,
-                                float* qsave, T* z, T* gz, T* beta, int64_t ld_z, cudaStream_t st) {
+                                float* qsave, T* z, T* gz, T* beta, int64_t ld_z, cudaStream_t st, int lens_dyn = 0) {
   if (!attention_pipe_ok<T>(L, D, A)) {
     const size_t sm1 = attention_fwd_smem(L, D, A, Vec16<T>::N);
     auto k1 = attention_step_fwd_kernel<T, kExact>;
@@ -1198,7 +1204,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
         auto launch_r = [&](auto kern) -> int {
           SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
           SAT_CUDA(sat_launch_pdl(kern, dim3(rows / ncap), dim3(ATTP_FWD_CW * 32 + 32), gm.smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D,
-                                  A, scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z, gm.rows, gm.nst, gm.stage_bytes));
+                                  A, scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z, lens_dyn, gm.rows, gm.nst, gm.stage_bytes));
           SAT_COUNT_LAUNCH();
           return 0;
         };
@@ -1208,19 +1214,22 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
       }
       if (L <= 16 * ATTG_MAXKS) {
       // annotations as a 2-D tensor [n_img * L, D]; the map is rebuilt only when the buffer or shape changes
-      static CUtensorMap tm;
-      static const void* tm_ptr = nullptr;
-      static int64_t tm_rows = 0, tm_d = 0;
+      static thread_local CUtensorMap tm;
+      static thread_local const void* tm_ptr = nullptr;
+      static thread_local int64_t tm_rows = 0, tm_d = 0;
+      static thread_local int tm_dev = -1;
       const int64_t n_rows = (int64_t)(rows / ncap) * L;
-      if (tm_ptr != (const void*)ann || tm_rows != n_rows || tm_d != D) {
+      int dev_now = 0;
+      SAT_CUDA(cudaGetDevice(&dev_now));
+      if (tm_ptr != (const void*)ann || tm_rows != n_rows || tm_d != D || tm_dev != dev_now) {
         SAT_TRY(tc::make_map(&tm, ann, n_rows, D, D, ATTG_BOX_ROWS));
-        tm_ptr = ann; tm_rows = n_rows; tm_d = D;
+        tm_ptr = ann; tm_rows = n_rows; tm_d = D; tm_dev = dev_now;
       }
       auto kern = attention_step_fwd_group_tc_kernel<kExact, ATTP_FWD_CW>;
       const size_t smem = attention_fwd_group_tc_smem(L, A);
       SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SAT_CUDA(sat_launch_pdl(kern, dim3(rows / ncap), dim3(ATTP_FWD_CW * 32 + 32), smem, st, tm, P, wf, hp, ldhp, lens, t, ncap, L, D, A,
-                              scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z));
+                              scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z, lens_dyn));
       SAT_COUNT_LAUNCH();
       return 0;
       }
@@ -1230,7 +1239,7 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
     auto launch_g = [&](auto kern, size_t smem) -> int {
       SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SAT_CUDA(sat_launch_pdl(kern, dim3(rows / ncap), dim3(ATTP_FWD_CW * 32 + 32), smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D, A,
-                              scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z));
+                              scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z, lens_dyn));
       SAT_COUNT_LAUNCH();
       return 0;
     };
@@ -1240,13 +1249,15 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
   }
   const size_t smem = attention_fwd_pipe_smem(L, D, A, Vec16<T>::N);
   auto kern = attention_step_fwd_pipe_kernel<T, kExact, ATTP_FWD_CW>;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  static size_t smem_set[64] = {0};           // the attribute is per device
+  int dev_now = 0;
+  SAT_CUDA(cudaGetDevice(&dev_now));
+  if (smem > smem_set[dev_now & 63]) {
     SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+    smem_set[dev_now & 63] = smem;
   }
   SAT_CUDA(sat_launch_pdl(kern, dim3(rows), dim3(ATTP_FWD_CW * 32 + 32), smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D, A, scale, alpha,
-                          ld_alpha, qsave, z, gz, beta, ld_z));
+                          ld_alpha, qsave, z, gz, beta, ld_z, lens_dyn));
   SAT_COUNT_LAUNCH();
   return 0;
 }

@@ -56,13 +56,14 @@ void sat_prof_mark(cudaStream_t st);
 // BEFORE SAT_PDL_WAIT().  The single-op entry points (sat_linear, sat_attention_step_fwd) take caller-supplied operands
 // that may be the output of the caller's previous launch, so they launch without the attribute (SatNoPdlScope): the
 // kernel then starts only after everything before it in the stream has completed.
-static inline bool& sat_pdl_allowed() {
-  static bool allowed = true;
+inline bool& sat_pdl_allowed() {          // one flag per host thread for the whole library (inline: shared by all translation units)
+  static thread_local bool allowed = true;      // per host thread: drivers on different threads / streams do not interfere
   return allowed;
 }
 struct SatNoPdlScope {
-  SatNoPdlScope() { sat_pdl_allowed() = false; }
-  ~SatNoPdlScope() { sat_pdl_allowed() = true; }
+  bool prev;
+  SatNoPdlScope() : prev(sat_pdl_allowed()) { sat_pdl_allowed() = false; }
+  ~SatNoPdlScope() { sat_pdl_allowed() = prev; }      // scopes nest
 };
 template <typename Kern, typename... Args>
 static inline cudaError_t sat_launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

@@ -7,6 +7,7 @@
 #include "sat_gemm.cuh"
 #include "sat_attention_pipe.cuh"
 #include "sat_kernels.cuh"
+#include "sat_vocab_ce.cuh"
 
 namespace {
 
@@ -19,8 +20,13 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   const TS* ann = (const TS*)b.ann;
 
   // once per image: P = ann * Wa^T, mean, InitLSTM
-  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, n_img * L, A,
-                           EpiStore<TS>{(TS*)b.P, A, nullptr, nullptr, 0}, st)));
+  {
+    // first launch of the driver: no PDL attribute, so that operands written by the caller's preceding launch (the weight
+    // pack kernel, the encoder) are complete and visible to every early (pre-wait) read of the kernels that follow
+    SatNoPdlScope first_launch;
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(ann, D, D), (const TS*)w.Wa, D, n_img * L, A,
+                             EpiStore<TS>{(TS*)b.P, A, nullptr, nullptr, 0}, st)));
+  }
   const int NV = D / Vec16<TS>::N;
   mean_L_kernel<TS><<<dim3((NV + 31) / 32, n_img), 256, 0, st>>>(ann, (TS*)b.meanv, L, D, 0.0f, 0ull);
   SAT_COUNT_LAUNCH();
@@ -28,7 +34,8 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
                            EpiStore<TS>{(TS*)b.f1, E, w.bfact, nullptr, 0}, st)));
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.f1, E, E), (const TS*)w.Winit, E, n_img, 2 * H,
                            EpiStore<float>{b.init_out, 2 * H, w.binit, nullptr, 0}, st)));
-  init_state_decode_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>(b.init_out, (TS*)b.h, b.c, n_img, k, H);
+  init_state_decode_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>(b.init_out, 2 * H, (TS*)b.h, b.c, n_img, k,
+                                                                                         d.H0 ? d.H0 : H, H);
   SAT_COUNT_LAUNCH();
   decode_init_kernel<<<(R + 255) / 256, 256, 0, st>>>(b.cur_tok, b.alive, b.top_scores, b.kcur, b.fin_count, b.fin_len, R, n_img, k,
                                                       b.tokSTART);
@@ -37,6 +44,12 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
 
   const float scale = (float)(1.0 / sqrt((double)L));
   const size_t topk_smem = sizeof(float) * (size_t)(V + 40);
+  const int V0 = d.V0 ? d.V0 : V;
+  // greedy on the tensor cores: soft-max statistics and the best word come out of the vocabulary GEMM's epilogue
+  const bool fuse_greedy = k == 1 && b.topk_stats != nullptr && std::is_same<TS, bf16>::value && tc && !kExact &&
+                           tc::operands_ok(gemm_a1(b.xo, E, E), w.Wo, E);
+  SAT_REQUIRE(fuse_greedy || topk_smem <= 227 * 1024, "vocabulary of %d words needs %zu bytes of shared memory per row in the top-k kernel "
+              "(limit 227 KB)", V, topk_smem);
   // candidate selection: threshold kernel (SAT_TOPK_MODE=0 forces the plain scan kernel for A/B runs)
   static const int topk_mode = getenv("SAT_TOPK_MODE") ? atoi(getenv("SAT_TOPK_MODE")) : 1;
   auto topk_k = (topk_mode == 0 || k == 1) ? row_topk_kernel : row_topk_thresh_kernel;      // greedy: one scan is already minimal
@@ -53,7 +66,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     SAT_PROF(1, st);
     SAT_TRY((launch_attention_fwd<TS, kExact>(ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, R, k, L, D, A, scale,
                                               b.alpha_all + (int64_t)step * R * L, L, nullptr, (TS*)b.z, (TS*)b.gz,
-                                              (TS*)nullptr, D, st)));
+                                              (TS*)nullptr, D, st, /*lens_dyn=*/1)));
     SAT_PROF(1, st);
     EpiLstm<TS, kExact> epi{b.GxV, 4 * H, b.hp + A + D, NH3, (const TS*)h_cur, c_cur, (TS*)h_nxt, c_nxt, H, H,
                             (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
@@ -61,12 +74,24 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(h_nxt, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
                              EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok, d.plain_output, 0.0f, 0ull, 0}, st)));
     SAT_PROF(3, st);
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
-    SAT_PROF(3, st);
-    SAT_CUDA(sat_launch_pdl(topk_k, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
-                            (const int32_t*)b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK, b.cand_val,
-                            b.cand_idx));
-    SAT_COUNT_LAUNCH();
+    if (fuse_greedy) {
+      tc::VocabArgs va{};
+      va.bias = w.bo; va.V0 = V0; va.NT = (V + 127) / 128; va.stats = reinterpret_cast<float4*>(b.topk_stats);
+      va.alive = b.alive; va.inv_temp = 1.0f / b.temps[step];
+      va.tokPAD = b.tokPAD; va.tokSTART = b.tokSTART; va.tokEND = b.tokEND; va.tokUNK = b.tokUNK; va.step0 = step == 0;
+      SAT_TRY((tc::launch_vocab<tc::VOCAB_GREEDY>(gemm_a1(b.xo, E, E), (const bf16*)w.Wo, E, R, V, va, st)));
+      SAT_PROF(3, st);
+      SAT_CUDA(sat_launch_pdl(tc::greedy_finalize_kernel, dim3((R + 7) / 8), dim3(256), 0, st, (const float4*)va.stats, va.NT,
+                              (const int32_t*)b.alive, (const float*)b.top_scores, R, (int)(step == 0), b.cand_val, b.cand_idx));
+      SAT_COUNT_LAUNCH();
+    } else {
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
+      SAT_PROF(3, st);
+      SAT_CUDA(sat_launch_pdl(topk_k, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
+                              (const int32_t*)b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK, b.cand_val,
+                              b.cand_idx));
+      SAT_COUNT_LAUNCH();
+    }
     const int in = step & 1, out = in ^ 1;
     SAT_CUDA(sat_launch_pdl(beam_update_kernel, dim3(n_img), dim3(32), 0, st, bp, step, (const float*)b.cand_val,
                             (const int32_t*)b.cand_idx, b.kcur, b.top_scores, b.cur_tok, b.src_row, b.alive,
@@ -94,6 +119,7 @@ extern "C" {
 int sat_decode_prepare_weights(const SatDims* d, const SatWeights* w, float* GxV, void* stream) {
   SAT_REQUIRE(d && w && GxV && w->Emb && w->Wihe && w->bg, "sat_decode_prepare_weights: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  SatNoPdlScope no_pdl;               // the packed weights may be the output of the launch just before this one (sat_pack_weights)
   const bool tc = d->use_tc != 0;
   if (d->dtype == SAT_F32)
     return gemm_tn<float, float>(false, gemm_a1(w->Emb, d->E, d->E), (const float*)w->Wihe, d->E, d->V, 4 * d->H,
@@ -107,11 +133,12 @@ int sat_decode(const SatDims* d, const SatWeights* w, SatDecodeBuffers* b, void*
   SAT_REQUIRE(d->dtype == SAT_F32 || d->dtype == SAT_BF16, "unknown dtype %d", d->dtype);
   SAT_REQUIRE(d->B == d->Bi * d->ncap && d->ncap == b->k && b->k >= 1 && b->k <= 32, "sat_decode: rows %d != n_img %d * k %d (k <= 32)",
               d->B, d->Bi, b->k);
-  SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0, "dims must be multiples of 8");
+  SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0, "storage dims must be multiples of 8");
+  SAT_REQUIRE(d->H0 >= 0 && d->H0 <= d->H && d->V0 >= 0 && d->V0 <= d->V, "true dims must not exceed the storage dims");
   SAT_REQUIRE(b->max_gen_length >= 1 && b->temps, "sat_decode: max_gen_length >= 1 and temps required");
-  SAT_REQUIRE(b->k + 4 <= d->V, "sat_decode: beam width %d too large for vocab %d", b->k, d->V);
+  SAT_REQUIRE(b->k + 4 <= (d->V0 ? d->V0 : d->V), "sat_decode: beam width %d too large for vocab %d", b->k, d->V0 ? d->V0 : d->V);
   SAT_REQUIRE(b->ann && b->P && b->meanv && b->f1 && b->init_out && b->GxV && b->h && b->c && b->hn && b->cn && b->hp && b->z &&
-                  b->gz && b->xo && b->logits && b->alpha_all && b->cand_val && b->cand_idx && b->tok_hist && b->asrc_hist &&
+                  b->gz && b->xo && (b->logits || b->topk_stats) && b->alpha_all && b->cand_val && b->cand_idx && b->tok_hist && b->asrc_hist &&
                   b->top_scores && b->cur_tok && b->src_row && b->alive && b->kcur && b->fin_tokens && b->fin_asrc && b->fin_len &&
                   b->fin_score && b->fin_ppl && b->fin_count,
               "sat_decode: NULL buffer");

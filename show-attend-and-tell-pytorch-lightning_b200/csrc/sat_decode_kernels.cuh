@@ -13,17 +13,19 @@ enum { SAT_RESCORE_NONE = 0, SAT_RESCORE_LN = 1, SAT_RESCORE_WR = 2, SAT_RESCORE
 // Per-image InitLSTM reinterpretation for a beam of k identical rows (model.py:265-269):
 //   h0[j] = o[(j % 2) * H : ...],  c0[j] = o[((k + j) % 2) * H : ...]   where o = init_out[img] ([2H]).
 template <typename T>
-__global__ void init_state_decode_kernel(const float* __restrict__ init_out, T* __restrict__ h0, float* __restrict__ c0,
-                                         int n_img, int k, int H) {
+__global__ void init_state_decode_kernel(const float* __restrict__ init_out, int64_t ld_io, T* __restrict__ h0, float* __restrict__ c0,
+                                         int n_img, int k, int H, int ld) {
+  // H = the module's true decoder_dim (the rule indexes the [2H] init vector); ld = storage pitch of the state rows
+  // (columns H..ld are padding and get zeros)
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)n_img * k * H) return;
-  const int jj = (int)(idx % H);
-  const int64_t row = idx / H;
+  if (idx >= (int64_t)n_img * k * ld) return;
+  const int jj = (int)(idx % ld);
+  const int64_t row = idx / ld;
   const int j = (int)(row % k);
   const int64_t n = row / k;
-  const float* o = init_out + n * 2 * H;
-  h0[idx] = from_f<T>(o[(j % 2) * H + jj]);
-  c0[idx] = o[((k + j) % 2) * H + jj];
+  const float* o = init_out + n * ld_io;
+  h0[idx] = from_f<T>(jj < H ? o[(j % 2) * H + jj] : 0.0f);
+  c0[idx] = jj < H ? o[((k + j) % 2) * H + jj] : 0.0f;
 }
 
 // scores = log_softmax(logit / temp) (model.py:330); <START>,<PAD> -> -inf (model.py:333); step 0 also

@@ -131,6 +131,88 @@ static int launch_gemm_tn_simt(const GemmOperandA& A, const TW* W, int64_t ldw, 
   return 0;
 }
 
+// ---- "NT" SIMT core: C[N1,N2] = sum_k A[k,n1] * B[k,n2] (weight gradients dW = dY^T X; fp32 parity mode and shapes
+// off the TMA grid).  Both operands are read along their contiguous dimension, so the shared tiles need no transpose.
+// gridDim.z splits the k range [0, Krows); partial z goes through the epilogue's zstride.
+template <typename TA, typename TB, typename Epi>
+__global__ void __launch_bounds__(SG_THREADS)
+gemm_nt_simt_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ B, int64_t ldb, int Krows, int N1, int N2, Epi epi) {
+  __shared__ __align__(16) float As[2][SG_BK][SG_BM + 4];
+  __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int lk = tid >> 4;             // k row inside the tile, 0..15
+  const int lc = (tid & 15) * 4;       // column inside the tile, 0..60
+  const int ty = tid >> 4, tx = tid & 15;
+  const int kper = (((Krows + gridDim.z - 1) / gridDim.z) + SG_BK - 1) / SG_BK * SG_BK;
+  const int kbeg = blockIdx.z * kper, kend = min(Krows, kbeg + kper);
+  const int ntiles = kend > kbeg ? (kend - kbeg + SG_BK - 1) / SG_BK : 0;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float4 ra, rb;
+  auto load_tile = [&](int it) {
+    const int k = kbeg + it * SG_BK + lk;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < kend) {
+      if (m0 + lc < N1) ra = ld4(A + (int64_t)k * lda + m0 + lc);
+      if (n0 + lc < N2) rb = ld4(B + (int64_t)k * ldb + n0 + lc);
+    }
+  };
+  auto store_tile = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lk][lc]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][lk][lc]) = rb;
+  };
+  if (ntiles > 0) {
+    load_tile(0);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) load_tile(it + 1);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    if (it + 1 < ntiles) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n < N2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < N1) epi(m, n, acc[i]);
+    }
+  }
+}
+
+template <typename TA, typename TB, typename Epi>
+static int launch_gemm_nt_simt(const TA* A, int64_t lda, const TB* B, int64_t ldb, int Krows, int N1, int N2, const Epi& epi,
+                               cudaStream_t stream, int splitk) {
+  if (N1 <= 0 || N2 <= 0) return 0;
+  SAT_REQUIRE(N1 % 4 == 0 && N2 % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, "gemm_nt: N1=%d N2=%d lda=%lld ldb=%lld must be multiples of 4", N1,
+              N2, (long long)lda, (long long)ldb);
+  dim3 grid((N2 + SG_BN - 1) / SG_BN, (N1 + SG_BM - 1) / SG_BM, splitk);
+  gemm_nt_simt_kernel<TA, TB, Epi><<<grid, SG_THREADS, 0, stream>>>(A, lda, B, ldb, Krows, N1, N2, epi);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
+
 // ---- epilogues -----------------------------------------------------------------------------
 
 // Epilogue concept (two-phase so that the tensor-core core can issue the global loads of several rows before

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <type_traits>
 
 #include "sat_gemm_simt.cuh"
 
@@ -97,6 +98,15 @@ struct Maps {
   CUtensorMap w;      // W: dims {Ktot, N}, box {64, BN}
 };
 
+// Epilogue functors come in two kinds.  The default kind is called per (row, 4 columns) after the accumulator tile has
+// been transposed through shared memory (coalesced global accesses).  A functor that declares
+//   static constexpr bool kRowOwner = true;
+// takes over the whole epilogue of a tile instead (run<BN>()): each thread keeps the accumulator ROW that tcgen05.ld
+// hands it, which makes per-row reductions over the tile's columns (soft-max statistics, arg-max) thread-local.
+template <typename T, typename = void> struct is_row_owner : std::false_type {};
+template <typename T> struct is_row_owner<T, std::void_t<decltype(T::kRowOwner)>> : std::bool_constant<T::kRowOwner> {};
+constexpr int AUX_FLOATS = 160;      // small per-CTA scratch that does not alias the operand ring (bias tile of a row-owner epilogue)
+
 template <int BN>
 struct Smem {
   static constexpr int STAGES = Stages<BN>::value;
@@ -106,7 +116,63 @@ struct Smem {
   uint64_t empty[STAGES];
   uint64_t tmem_full;
   uint32_t tmem_base;
+  alignas(16) float aux[AUX_FLOATS];
 };
+
+// ===== standard epilogue: TMEM -> registers -> shared (transpose) -> coalesced fused epilogue =====
+// A thread owns one accumulator ROW after tcgen05.ld; global accesses of the epilogue functors want a warp on
+// consecutive COLUMNS of one row.  The operand ring is idle once tmem_full fires, so it is reused as a [128][BN+4] fp32
+// staging tile (conflict-free: row stride = 4 mod 32 banks).  Called by the 8 epilogue warps (warp = 2..9).
+template <int BN, typename Epi>
+__device__ __forceinline__ void epilogue_tile(float* tile, uint32_t tmem, bool has_acc, int warp, int lane, int m0, int n0, int M, int N,
+                                              const Epi& epi) {
+  const int q = warp & 3;                    // TMEM lane quarter this warp may access
+  constexpr int LDT = BN + 4;
+  const int row = q * 32 + lane;
+  const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp moves
+  constexpr int CH = BN / 2;
+  if (has_acc) {
+#pragma unroll 1
+    for (int c = half * CH; c < (half + 1) * CH; c += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float4*>(&tile[row * LDT + c + g * 4]) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+  } else {
+    for (int c = half * CH; c < (half + 1) * CH; c += 4) *reinterpret_cast<float4*>(&tile[row * LDT + c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  constexpr int LPR = BN / 4;                // lanes per row
+  constexpr int RPW = 32 / LPR;              // rows per warp pass
+  const int ew = warp - 2;                   // 0..EPI_WARPS-1
+  const int lr = lane / LPR, lc = (lane % LPR) * 4;
+  const int n = n0 + lc;
+  constexpr int NIT = BM / (EPI_WARPS * RPW);   // rows per thread
+  constexpr int UN = 4;                      // rows whose epilogue operands are loaded before any dependent math
+  static_assert(NIT % UN == 0, "row loop must divide");
+#pragma unroll 1
+  for (int i0 = 0; i0 < NIT; i0 += UN) {
+    typename Epi::Ctx ctx[UN];
+    bool ok[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int m = m0 + ew * RPW + lr + (i0 + u) * EPI_WARPS * RPW;
+      ok[u] = m < M && n < N;
+      if (ok[u]) ctx[u] = epi.load(m, n);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int r = ew * RPW + lr + (i0 + u) * EPI_WARPS * RPW;
+      if (ok[u]) {
+        const float4 a = *reinterpret_cast<const float4*>(&tile[r * LDT + lc]);
+        const float a4[4] = {a.x, a.y, a.z, a.w};
+        epi.apply(m0 + r, n, a4, ctx[u]);
+      }
+    }
+  }
+}
 
 template <int BN, typename Epi>
 __global__ void __launch_bounds__(THREADS)
@@ -193,60 +259,133 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
       umma_commit(&s.tmem_full);              // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> shared (transpose) -> coalesced fused epilogue =====
-    // A thread owns one accumulator ROW after tcgen05.ld; global accesses of the epilogue functors want a warp
-    // on consecutive COLUMNS of one row.  The operand ring is idle once tmem_full fires, so it is reused as a
-    // [128][BN+4] fp32 staging tile (conflict-free: row stride = 4 mod 32 banks).
+    if constexpr (is_row_owner<Epi>::value) {
+      // row-owner epilogue (soft-max statistics / arg-max of the vocabulary projection): the functor stages what it needs
+      // in s.aux before the accumulator is complete, then reads TMEM itself
+      epi.prologue(s.aux, n0, N, warp, lane);
+      mbar_wait(&s.tmem_full, 0);
+      tcgen05_fence_after();
+      static_assert((size_t)BM * (BN / 2 + 8) * sizeof(float) <= sizeof(s.a) + sizeof(s.w), "row-owner scratch must fit the ring");
+      epi.template run<BN>(reinterpret_cast<uint8_t*>(&s.a[0][0]), s.aux, tmem, nkb > 0, warp, lane, m0, n0, M, N);
+    } else {
+      mbar_wait(&s.tmem_full, 0);
+      tcgen05_fence_after();
+      static_assert((size_t)BM * (BN + 4) * sizeof(float) <= sizeof(s.a) + sizeof(s.w), "staging tile must fit the ring");
+      epilogue_tile<BN, Epi>(reinterpret_cast<float*>(&s.a[0][0]), tmem, nkb > 0, warp, lane, m0, n0, M, N, epi);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+  }
+}
+
+// =============================================================================================
+// "NT" core: C[N1,N2] = sum_k A[k,n1] * B[k,n2]  -- the weight-gradient GEMMs dW = dY^T X, whose contraction runs over the
+// T*B rows of two row-major activation buffers.  Both operands are therefore MN-major for the tensor core: a TMA box of
+// {64 columns, BK rows} lands as BK 128-byte rows (128B swizzle), which is exactly the canonical MN-major SWIZZLE_128B
+// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with SBO = 1024 B (eight k rows) and LBO = BK*128 B (the next
+// 64-column box); one tcgen05.mma consumes 16 k rows = two 8-row groups, so the descriptor advances by 2048 B per MMA.
+// gridDim.z splits the k range; partials are written per z (EpiStore::zstride) and summed in fixed order by the
+// consumer (param_grads_finalize_kernel), which keeps the gradients bit-reproducible.
+// =============================================================================================
+struct MapsNT {
+  CUtensorMap a;      // A: dims {N1, Krows}, box {64, BK}
+  CUtensorMap b;      // B: dims {N2, Krows}, box {64, BK}
+};
+
+template <int BN>
+struct SmemNT {
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  alignas(1024) bf16 a[STAGES][2 * BK * 64];              // two boxes: columns n1 0..63 | 64..127, each [BK rows][64]
+  alignas(1024) bf16 b[STAGES][(BN / 64) * BK * 64];
+  alignas(8) uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+// MN-major, 128B-swizzled shared-memory matrix descriptor (see above)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(const void* p, uint32_t lbo_bytes) {
+  const uint32_t a = smem_u32(p);
+  return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+template <int BN, typename Epi>
+__global__ void __launch_bounds__(THREADS)
+gemm_nt_tc_kernel(const __grid_constant__ MapsNT maps, int N1, int N2, int Krows, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  static_assert(BN == 64 || BN == 128, "MN-major B tiles are made of 64-column boxes");
+  constexpr int STAGES = SmemNT<BN>::STAGES;
+  SmemNT<BN>& s = *reinterpret_cast<SmemNT<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb_all = (Krows + BK - 1) / BK;
+  const int kb_begin = (int)(((long)nkb_all * blockIdx.z) / gridDim.z);
+  const int kb_end = (int)(((long)nkb_all * (blockIdx.z + 1)) / gridDim.z);
+  const int nkb = kb_end - kb_begin;
+  constexpr uint32_t BOX_BYTES = BK * 64 * sizeof(bf16);
+  constexpr uint32_t STAGE_BYTES = (2 + BN / 64) * BOX_BYTES;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // both operands are activations written by predecessors
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int st = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        const int krow = (kb_begin + i) * BK;
+        mbar_wait(&s.empty[st], ph ^ 1);
+        mbar_expect_tx(&s.full[st], STAGE_BYTES);
+        tma_load_2d(&maps.a, &s.full[st], &s.a[st][0], m0, krow);
+        tma_load_2d(&maps.a, &s.full[st], &s.a[st][BK * 64], m0 + 64, krow);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_2d(&maps.b, &s.full[st], &s.b[st][j * BK * 64], n0 + 64 * j, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>() | (1u << 15) | (1u << 16);      // A and B are MN-major
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&s.full[st], ph);
+        tcgen05_fence_after();
+        const uint64_t ad = make_smem_desc_mn(&s.a[st][0], BOX_BYTES), bd = make_smem_desc_mn(&s.b[st][0], BOX_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk)      // 16 k rows = 2048 B = 128 descriptor units per MMA
+          umma(tmem, ad + 128 * kk, bd + 128 * kk, idesc, (kb | kk) != 0);
+        umma_commit(&s.empty[st]);
+      }
+      umma_commit(&s.tmem_full);
+    }
+  } else {
     mbar_wait(&s.tmem_full, 0);
     tcgen05_fence_after();
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    constexpr int LDT = BN + 4;
-    float* tile = reinterpret_cast<float*>(&s.a[0][0]);
-    static_assert((size_t)BM * LDT * sizeof(float) <= sizeof(s.a) + sizeof(s.w), "staging tile must fit the ring");
-    const int row = q * 32 + lane;
-    const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp moves
-    constexpr int CH = BN / 2;
-    if (nkb > 0) {
-#pragma unroll 1
-      for (int c = half * CH; c < (half + 1) * CH; c += 16) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<float4*>(&tile[row * LDT + c + g * 4]) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      }
-    } else {
-      for (int c = half * CH; c < (half + 1) * CH; c += 4) *reinterpret_cast<float4*>(&tile[row * LDT + c]) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    constexpr int LPR = BN / 4;                // lanes per row
-    constexpr int RPW = 32 / LPR;              // rows per warp pass
-    const int ew = warp - 2;                   // 0..EPI_WARPS-1
-    const int lr = lane / LPR, lc = (lane % LPR) * 4;
-    const int n = n0 + lc;
-    constexpr int NIT = BM / (EPI_WARPS * RPW);   // rows per thread
-    constexpr int UN = 4;                      // rows whose epilogue operands are loaded before any dependent math
-    static_assert(NIT % UN == 0, "row loop must divide");
-#pragma unroll 1
-    for (int i0 = 0; i0 < NIT; i0 += UN) {
-      typename Epi::Ctx ctx[UN];
-      bool ok[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int m = m0 + ew * RPW + lr + (i0 + u) * EPI_WARPS * RPW;
-        ok[u] = m < M && n < N;
-        if (ok[u]) ctx[u] = epi.load(m, n);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int r = ew * RPW + lr + (i0 + u) * EPI_WARPS * RPW;
-        if (ok[u]) {
-          const float4 a = *reinterpret_cast<const float4*>(&tile[r * LDT + lc]);
-          const float a4[4] = {a.x, a.y, a.z, a.w};
-          epi.apply(m0 + r, n, a4, ctx[u]);
-        }
-      }
-    }
+    static_assert((size_t)BM * (BN + 4) * sizeof(float) <= sizeof(s.a) + sizeof(s.b), "staging tile must fit the ring");
+    epilogue_tile<BN, Epi>(reinterpret_cast<float*>(&s.a[0][0]), tmem, nkb > 0, warp, lane, m0, n0, N1, N2, epi);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -307,10 +446,12 @@ static int launch_bn(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, i
   SAT_TRY(make_map(&maps.w, W, N, ktot, ldw, BN));
   auto kern = gemm_tn_tc_kernel<BN, Epi>;
   constexpr int smem = (int)sizeof(Smem<BN>) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};         // the attribute is per device
+  int dev_now = 0;
+  SAT_CUDA(cudaGetDevice(&dev_now));
+  if (!attr_set[dev_now & 63]) {
     SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[dev_now & 63] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((N + BN - 1) / BN, (M + BM - 1) / BM, splitk);
@@ -347,6 +488,75 @@ static inline int pick_splitk(int M, int N, int ktot) {
   const int nkb = (ktot + BK - 1) / BK;
   int s = 1;
   while (s < 16 && tiles * (s * 2) <= 160 && nkb / (s * 2) >= 4) s *= 2;
+  return s;
+}
+
+
+// ---- NT launchers ------------------------------------------------------------------------------------
+// 2D bf16 tensor map of a row-major [rows, cols] buffer read as {64 columns, BK rows} boxes (MN-major operand tiles)
+static int make_map_mn(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  auto enc = get_encode();
+  SAT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SAT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (MN-major) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+  return 0;
+}
+
+static inline bool nt_operands_ok(const void* A, int64_t lda, const void* B, int64_t ldb) {
+  return lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+}
+
+template <int BN, typename Epi>
+static int launch_nt_bn(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int Krows, int N1, int N2, const Epi& epi,
+                        cudaStream_t stream, int splitk) {
+  MapsNT maps;
+  SAT_TRY(make_map_mn(&maps.a, A, Krows, N1, lda));
+  SAT_TRY(make_map_mn(&maps.b, B, Krows, N2, ldb));
+  auto kern = gemm_nt_tc_kernel<BN, Epi>;
+  constexpr int smem = (int)sizeof(SmemNT<BN>) + 1024;
+  static bool attr_set[64] = {false};
+  int dev_now = 0;
+  SAT_CUDA(cudaGetDevice(&dev_now));
+  if (!attr_set[dev_now & 63]) {
+    SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev_now & 63] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((N2 + BN - 1) / BN, (N1 + BM - 1) / BM, splitk);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = sat_pdl_allowed() ? 1 : 0;
+  SAT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, N1, N2, Krows, epi));
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
+
+template <typename Epi>
+static int launch_nt(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int Krows, int N1, int N2, const Epi& epi,
+                     cudaStream_t stream, int splitk) {
+  if (N2 > 64) return launch_nt_bn<128, Epi>(A, lda, B, ldb, Krows, N1, N2, epi, stream, splitk);
+  return launch_nt_bn<64, Epi>(A, lda, B, ldb, Krows, N1, N2, epi, stream, splitk);
+}
+
+// split-K factor of a weight-gradient GEMM: enough CTAs for ~2 per SM, at least 4 k blocks each
+static inline int pick_splitk_nt(int N1, int N2, int Krows) {
+  const long tiles = (long)((N1 + BM - 1) / BM) * ((N2 + (N2 > 64 ? 127 : 63)) / (N2 > 64 ? 128 : 64));
+  const int nkb = (Krows + BK - 1) / BK;
+  int s = 1;
+  while (s < 32 && tiles * (s * 2) <= 320 && nkb / (s * 2) >= 4) s *= 2;
   return s;
 }
 

@@ -222,14 +222,16 @@ __global__ void __launch_bounds__(256) mean_L_kernel(const T* __restrict__ ann, 
 // is read row-major as [2,B,H]:  h0[b,j] = flat[b*H+j],  c0[b,j] = flat[(B+b)*H+j].
 // =============================================================================================
 template <typename T>
-__global__ void init_state_kernel(const float* __restrict__ init_out, T* __restrict__ h0, float* __restrict__ c0,
+__global__ void init_state_kernel(const float* __restrict__ init_out, int64_t ld_io, T* __restrict__ h0, float* __restrict__ c0,
                                   int64_t ld_h, int64_t ld_c, int B, int H, int ncap) {
+  // H is the module's TRUE decoder_dim (the reinterpretation mixes rows and columns, so it must not see the padding);
+  // ld_io / ld_h / ld_c are the storage pitches.  Padded state columns are zeroed by the caller.
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t BH = (int64_t)B * H;
   if (idx >= 2 * BH) return;
   const int64_t r = idx / (2 * H);          // row of the (virtual) repeated [B,2H] matrix
   const int col = (int)(idx - r * 2 * H);
-  const float v = init_out[(r / ncap) * 2 * H + col];
+  const float v = init_out[(r / ncap) * ld_io + col];
   if (idx < BH) {
     const int64_t b = idx / H;
     const int j = (int)(idx - b * H);
@@ -243,23 +245,28 @@ __global__ void init_state_kernel(const float* __restrict__ init_out, T* __restr
 }
 
 // inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i
+// (H = true decoder_dim; ld_st = storage pitch of dh0 / dc0 rows; ld_io = pitch of d_init_out, whose padding gets zeros)
 static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int ns_dh, int64_t dh_stride,
-                                             const float* __restrict__ dc0, float* __restrict__ d_init_out,
-                                             bf16* __restrict__ d_init_out16, int B, int H, int ncap) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, 2H]
+                                             const float* __restrict__ dc0, int64_t ld_st, float* __restrict__ d_init_out,
+                                             bf16* __restrict__ d_init_out16, int64_t ld_io, int B, int H, int ncap) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, ld_io]
   const int Bi = B / ncap;
-  if (idx >= (int64_t)Bi * 2 * H) return;
-  const int64_t i = idx / (2 * H);
-  const int col = (int)(idx - i * 2 * H);
+  if (idx >= (int64_t)Bi * ld_io) return;
+  const int64_t i = idx / ld_io;
+  const int col = (int)(idx - i * ld_io);
   const int64_t BH = (int64_t)B * H;
   float s = 0.0f;
-  for (int c = 0; c < ncap; ++c) {
-    const int64_t r = i * ncap + c;
-    const int64_t f = r * 2 * H + col;
-    if (f < BH) {
-      for (int sp = 0; sp < ns_dh; ++sp) s += dh0[(int64_t)sp * dh_stride + f];
-    } else {
-      s += dc0[f - BH];
+  if (col < 2 * H) {
+    for (int c = 0; c < ncap; ++c) {
+      const int64_t r = i * ncap + c;
+      const int64_t f = r * 2 * H + col;          // flat index into the [2,B,H] view
+      if (f < BH) {
+        const int64_t b = f / H, j = f - b * H;
+        for (int sp = 0; sp < ns_dh; ++sp) s += dh0[(int64_t)sp * dh_stride + b * ld_st + j];
+      } else {
+        const int64_t k = f - BH, b = k / H, j = k - b * H;
+        s += dc0[b * ld_st + j];
+      }
     }
   }
   d_init_out[idx] = s;
@@ -269,11 +276,17 @@ static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int 
 // =============================================================================================
 // previous-word ids, time-major: tok[t,b] = caps[b,t]   (teacher forcing, model.py:520)
 // =============================================================================================
-static __global__ void tok_init_kernel(const int32_t* __restrict__ caps, int32_t* __restrict__ tok, int B, int T_, int caplen) {
+static __global__ void tok_init_kernel(const int32_t* __restrict__ caps, int32_t* __restrict__ tok, int B, int T_, int caplen, int V0,
+                                       float* __restrict__ err_flag) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= T_ * B) return;
   const int t = m / B, b = m - t * B;
-  tok[m] = caps[(int64_t)b * caplen + t];
+  int w = caps[(int64_t)b * caplen + t];
+  if ((unsigned)w >= (unsigned)V0) {      // nn.Embedding would raise; here the word is fed as <PAD> and the step is flagged (out[6])
+    w = 0;
+    *err_flag = 1.0f;
+  }
+  tok[m] = w;
 }
 
 // =============================================================================================
@@ -345,7 +358,9 @@ template <typename TL, typename TD, bool kExact>
 __global__ void __launch_bounds__(256)
 ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t* __restrict__ caps,
                const int32_t* __restrict__ lens, const float* __restrict__ inv_ntok_p, float* __restrict__ row_loss,
-               int32_t* __restrict__ row_argmax, int B, int V, int caplen, float smoothing, int zero_inactive_logits) {
+               int32_t* __restrict__ row_argmax, int B, int V0, int V, int caplen, float smoothing, int zero_inactive_logits) {
+  // V0 = true vocabulary, V = storage row pitch (multiple of 8).  Padded entries hold -inf logits (bias padding): they drop
+  // out of the max / sum of exponentials by themselves, are skipped in the sum of logits, and get a zero gradient.
   extern __shared__ __align__(16) float smem[];
   float* x = smem;              // [V]
   float* scratch = x + V;       // [33]
@@ -356,34 +371,22 @@ ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t*
   const bool active = t < lens[b];
   if (!active) {
     if (zero_inactive_logits) for (int v = tid; v < V; v += 256) row[v] = from_f<TL>(0.f);
-    if (dlogits && (void*)dlogits != (void*)logits)
-      for (int v = tid; v < V; v += 256) dlogits[(int64_t)m * V + v] = from_f<TD>(0.f);
-    else if (dlogits)
-      for (int v = tid; v < V; v += 256) dlogits[(int64_t)m * V + v] = from_f<TD>(0.f);
+    if (dlogits) for (int v = tid; v < V; v += 256) dlogits[(int64_t)m * V + v] = from_f<TD>(0.f);
     if (tid == 0) { row_loss[m] = 0.0f; row_argmax[m] = -1; }
     return;
   }
-  const int y = caps[(int64_t)b * caplen + t + 1];
+  int y = caps[(int64_t)b * caplen + t + 1];
+  if ((unsigned)y >= (unsigned)V0) y = 0;      // out-of-range target ids are flagged by tok_init_kernel (out[6])
   float mx = -INFINITY, sx = 0.0f;
   int arg = 0x7fffffff;
-  const bool vec4 = (V & 3) == 0;       // 4 logits per access (rows are then 8 B (bf16) / 16 B (fp32) aligned)
-  if (vec4) {
-    for (int v = tid * 4; v < V; v += 256 * 4) {
-      const float4 q = ld4(row + v);
-      *reinterpret_cast<float4*>(x + v) = q;
-      sx += (q.x + q.y) + (q.z + q.w);
-      if (q.x > mx) { mx = q.x; arg = v; }
-      if (q.y > mx) { mx = q.y; arg = v + 1; }
-      if (q.z > mx) { mx = q.z; arg = v + 2; }
-      if (q.w > mx) { mx = q.w; arg = v + 3; }
-    }
-  } else {
-    for (int v = tid; v < V; v += 256) {
-      const float xv = to_f(row[v]);
-      x[v] = xv;
-      sx += xv;
-      if (xv > mx) { mx = xv; arg = v; }
-    }
+  for (int v = tid * 4; v < V; v += 256 * 4) {      // 4 logits per access (rows are 16 B (bf16) / 32 B (fp32) aligned)
+    const float4 q = ld4(row + v);
+    *reinterpret_cast<float4*>(x + v) = q;
+    sx += ((v < V0 ? q.x : 0.f) + (v + 1 < V0 ? q.y : 0.f)) + ((v + 2 < V0 ? q.z : 0.f) + (v + 3 < V0 ? q.w : 0.f));
+    if (q.x > mx) { mx = q.x; arg = v; }
+    if (q.y > mx) { mx = q.y; arg = v + 1; }
+    if (q.z > mx) { mx = q.z; arg = v + 2; }
+    if (q.w > mx) { mx = q.w; arg = v + 3; }
   }
   // block argmax with lowest-index tie break (torch.argmax returns the first maximal index)
   for (int o = 16; o > 0; o >>= 1) {
@@ -397,44 +400,36 @@ ce_rows_kernel(TL* __restrict__ logits, TD* __restrict__ dlogits, const int32_t*
   for (int w = 1; w < 8; ++w)
     if (s_val[w] > mx || (s_val[w] == mx && s_arg[w] < arg)) { mx = s_val[w]; arg = s_arg[w]; }
   float se = 0.0f;
-  if (vec4) {
-    for (int v = tid * 4; v < V; v += 256 * 4) {
-      const float4 q = *reinterpret_cast<const float4*>(x + v);
-      se += (sat_exp<kExact>(q.x - mx) + sat_exp<kExact>(q.y - mx)) + (sat_exp<kExact>(q.z - mx) + sat_exp<kExact>(q.w - mx));
-    }
-  } else {
-    for (int v = tid; v < V; v += 256) se += sat_exp<kExact>(x[v] - mx);
+  for (int v = tid * 4; v < V; v += 256 * 4) {
+    const float4 q = *reinterpret_cast<const float4*>(x + v);
+    se += (sat_exp<kExact>(q.x - mx) + sat_exp<kExact>(q.y - mx)) + (sat_exp<kExact>(q.z - mx) + sat_exp<kExact>(q.w - mx));
   }
   se = block_sum(se, scratch);
   sx = block_sum(sx, scratch);
   const float lse = mx + (kExact ? logf(se) : __logf(se));
   if (tid == 0) {
     const float nll = lse - x[y];
-    const float smooth = lse - sx / (float)V;
+    const float smooth = lse - sx / (float)V0;
     row_loss[m] = (1.0f - smoothing) * nll + smoothing * smooth;
     row_argmax[m] = arg;
   }
   if (dlogits) {
     const float inv_ntok = *inv_ntok_p;
-    const float sv = smoothing / (float)V;
-    if (vec4) {
-      TD* drow = dlogits + (int64_t)m * V;
-      for (int v = tid * 4; v < V; v += 256 * 4) {
-        const float4 q = *reinterpret_cast<const float4*>(x + v);
-        float p0 = sat_exp<kExact>(q.x - lse) - sv, p1 = sat_exp<kExact>(q.y - lse) - sv;
-        float p2 = sat_exp<kExact>(q.z - lse) - sv, p3 = sat_exp<kExact>(q.w - lse) - sv;
-        if (y == v) p0 -= (1.0f - smoothing);
-        if (y == v + 1) p1 -= (1.0f - smoothing);
-        if (y == v + 2) p2 -= (1.0f - smoothing);
-        if (y == v + 3) p3 -= (1.0f - smoothing);
-        st4(drow + v, make_float4(p0 * inv_ntok, p1 * inv_ntok, p2 * inv_ntok, p3 * inv_ntok));
-      }
-    } else {
-      for (int v = tid; v < V; v += 256) {
-        float p = sat_exp<kExact>(x[v] - lse) - sv;
-        if (v == y) p -= (1.0f - smoothing);
-        dlogits[(int64_t)m * V + v] = from_f<TD>(p * inv_ntok);
-      }
+    const float sv = smoothing / (float)V0;
+    TD* drow = dlogits + (int64_t)m * V;
+    for (int v = tid * 4; v < V; v += 256 * 4) {
+      const float4 q = *reinterpret_cast<const float4*>(x + v);
+      float p0 = sat_exp<kExact>(q.x - lse) - sv, p1 = sat_exp<kExact>(q.y - lse) - sv;
+      float p2 = sat_exp<kExact>(q.z - lse) - sv, p3 = sat_exp<kExact>(q.w - lse) - sv;
+      if (y == v) p0 -= (1.0f - smoothing);
+      if (y == v + 1) p1 -= (1.0f - smoothing);
+      if (y == v + 2) p2 -= (1.0f - smoothing);
+      if (y == v + 3) p3 -= (1.0f - smoothing);
+      if (v >= V0) p0 = 0.f;
+      if (v + 1 >= V0) p1 = 0.f;
+      if (v + 2 >= V0) p2 = 0.f;
+      if (v + 3 >= V0) p3 = 0.f;
+      st4(drow + v, make_float4(p0 * inv_ntok, p1 * inv_ntok, p2 * inv_ntok, p3 * inv_ntok));
     }
   }
 }

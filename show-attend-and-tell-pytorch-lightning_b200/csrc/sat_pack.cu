@@ -88,44 +88,48 @@ struct Builder {
 extern "C" int sat_pack_weights(const SatDims* d, const SatMasterWeights* m, const SatWeights* w, void* stream) {
   SAT_REQUIRE(d && m && w, "sat_pack_weights: NULL struct");
   SAT_REQUIRE(d->dtype == SAT_F32 || d->dtype == SAT_BF16, "unknown dtype %d", d->dtype);
+  // storage (padded) dims address the destinations, the module's true dims (D0 ..) the fp32 sources; the destinations'
+  // padding is zero-filled once by the owner of the buffers (and -inf for the padded entries of the vocabulary bias)
   const int D = d->D, A = d->A, E = d->E, H = d->H, V = d->V;
+  const int D0 = d->D0 ? d->D0 : D, A0 = d->A0 ? d->A0 : A, E0 = d->E0 ? d->E0 : E, H0 = d->H0 ? d->H0 : H, V0 = d->V0 ? d->V0 : V;
+  SAT_REQUIRE(D0 <= D && A0 <= A && E0 <= E && H0 <= H && V0 <= V, "sat_pack_weights: true dims exceed the storage dims");
   const int NH3 = A + D + 4 * H, NH4 = NH3 + E;
   SAT_REQUIRE(m->embedding && m->w_ih && m->w_hh && m->b_ih && m->b_hh && m->enc_att && m->dec_att && m->f_att && m->beta_w &&
                   m->beta_b && m->out_hidden && m->out_w && m->fact_w && m->fact_b && m->init_w && m->init_b,
               "sat_pack_weights: missing master parameter");
   Builder b;
-  // forward layouts
-  b.add(m->enc_att, nullptr, w->Wa, A, D, D, D, 0, 0, 0, 0, 0);
-  b.add(m->dec_att, nullptr, w->Whcat, A, H, H, H, 0, 0, 0, 0, 0);
-  b.add(m->beta_w, nullptr, w->Whcat, D, H, H, H, A, 0, 0, 0, 0);
-  b.add(m->w_hh, nullptr, w->Whcat, 4 * H, H, H, H, A + D, 0, H, 0, 0);
-  b.add(m->out_hidden, nullptr, w->Whcat, E, H, H, H, NH3, 0, 0, 0, 0);
-  b.add(m->beta_b, nullptr, w->bhcat, 1, D, D, NH4, 0, A, 0, 0, 1);
-  b.add(m->w_ih + E, nullptr, w->Wihz, 4 * H, D, E + D, D, 0, 0, H, 0, 0);
-  b.add(m->w_ih, nullptr, w->Wihe, 4 * H, E, E + D, E, 0, 0, H, 0, 0);
-  b.add(m->b_ih, m->b_hh, w->bg, 4 * H, 1, 1, 1, 0, 0, H, 0, 1);
-  b.add(m->out_hidden, nullptr, w->Whozo, E, H, H, H + D, 0, 0, 0, 0, 0);
-  b.add(m->out_context, nullptr, w->Whozo, E, D, D, H + D, 0, H, 0, 0, 0);
-  b.add(m->out_w, nullptr, w->Wo, V, E, E, E, 0, 0, 0, 0, 0);
-  b.add(m->out_b, nullptr, w->bo, 1, V, V, V, 0, 0, 0, 0, 1);
-  b.add(m->f_att, nullptr, w->wf, 1, A, A, A, 0, 0, 0, 0, 1);
-  if (w->Emb != w->Wo) b.add(m->embedding, nullptr, w->Emb, V, E, E, E, 0, 0, 0, 0, 0);
-  b.add(m->fact_w, nullptr, w->Wfact, E, D, D, D, 0, 0, 0, 0, 0);
-  b.add(m->fact_b, nullptr, w->bfact, 1, E, E, E, 0, 0, 0, 0, 1);
-  b.add(m->init_w, nullptr, w->Winit, 2 * H, E, E, E, 0, 0, 0, 0, 0);
-  b.add(m->init_b, nullptr, w->binit, 1, 2 * H, 2 * H, 2 * H, 0, 0, 0, 0, 1);
+  // forward layouts                     rows    cols  src_ld   dst_ld  r0       c0 inter tr f32
+  b.add(m->enc_att, nullptr, w->Wa,      A0,     D0,   D0,      D,      0,       0, 0,  0, 0);
+  b.add(m->dec_att, nullptr, w->Whcat,   A0,     H0,   H0,      H,      0,       0, 0,  0, 0);
+  b.add(m->beta_w, nullptr, w->Whcat,    D0,     H0,   H0,      H,      A,       0, 0,  0, 0);
+  b.add(m->w_hh, nullptr, w->Whcat,      4 * H0, H0,   H0,      H,      A + D,   0, H0, 0, 0);
+  b.add(m->out_hidden, nullptr, w->Whcat, E0,    H0,   H0,      H,      NH3,     0, 0,  0, 0);
+  b.add(m->beta_b, nullptr, w->bhcat,    1,      D0,   D0,      NH4,    0,       A, 0,  0, 1);
+  b.add(m->w_ih + E0, nullptr, w->Wihz,  4 * H0, D0,   E0 + D0, D,      0,       0, H0, 0, 0);
+  b.add(m->w_ih, nullptr, w->Wihe,       4 * H0, E0,   E0 + D0, E,      0,       0, H0, 0, 0);
+  b.add(m->b_ih, m->b_hh, w->bg,         4 * H0, 1,    1,       1,      0,       0, H0, 0, 1);
+  b.add(m->out_hidden, nullptr, w->Whozo, E0,    H0,   H0,      H + D,  0,       0, 0,  0, 0);
+  b.add(m->out_context, nullptr, w->Whozo, E0,   D0,   D0,      H + D,  0,       H, 0,  0, 0);
+  b.add(m->out_w, nullptr, w->Wo,        V0,     E0,   E0,      E,      0,       0, 0,  0, 0);
+  b.add(m->out_b, nullptr, w->bo,        1,      V0,   V0,      V,      0,       0, 0,  0, 1);
+  b.add(m->f_att, nullptr, w->wf,        1,      A0,   A0,      A,      0,       0, 0,  0, 1);
+  if (w->Emb != w->Wo) b.add(m->embedding, nullptr, w->Emb, V0, E0, E0, E, 0, 0, 0, 0, 0);
+  b.add(m->fact_w, nullptr, w->Wfact,    E0,     D0,   D0,      D,      0,       0, 0,  0, 0);
+  b.add(m->fact_b, nullptr, w->bfact,    1,      E0,   E0,      E,      0,       0, 0,  0, 1);
+  b.add(m->init_w, nullptr, w->Winit,    2 * H0, E0,   E0,      E,      0,       0, 0,  0, 0);
+  b.add(m->init_b, nullptr, w->binit,    1,      2 * H0, 2 * H0, 2 * H, 0,       0, 0,  0, 1);
   // transposed copies for the backward GEMMs (skipped when the destination pointers are NULL)
-  b.add(m->out_w, nullptr, w->WoT, V, E, E, V, 0, 0, 0, 1, 0);
-  b.add(m->out_hidden, nullptr, w->WhozoT, E, H, H, E, 0, 0, 0, 1, 0);
-  b.add(m->out_context, nullptr, w->WhozoT, E, D, D, E, H, 0, 0, 1, 0);
-  b.add(m->w_ih + E, nullptr, w->WihzT, 4 * H, D, E + D, 4 * H, 0, 0, H, 1, 0);
-  b.add(m->w_ih, nullptr, w->WiheT, 4 * H, E, E + D, 4 * H, 0, 0, H, 1, 0);
-  b.add(m->dec_att, nullptr, w->WhcatT, A, H, H, NH3, 0, 0, 0, 1, 0);
-  b.add(m->beta_w, nullptr, w->WhcatT, D, H, H, NH3, 0, A, 0, 1, 0);
-  b.add(m->w_hh, nullptr, w->WhcatT, 4 * H, H, H, NH3, 0, A + D, H, 1, 0);
-  b.add(m->enc_att, nullptr, w->WaT, A, D, D, A, 0, 0, 0, 1, 0);
-  b.add(m->init_w, nullptr, w->WinitT, 2 * H, E, E, 2 * H, 0, 0, 0, 1, 0);
-  b.add(m->fact_w, nullptr, w->WfactT, E, D, D, E, 0, 0, 0, 1, 0);
+  b.add(m->out_w, nullptr, w->WoT,       V0,     E0,   E0,      V,      0,       0, 0,  1, 0);
+  b.add(m->out_hidden, nullptr, w->WhozoT, E0,   H0,   H0,      E,      0,       0, 0,  1, 0);
+  b.add(m->out_context, nullptr, w->WhozoT, E0,  D0,   D0,      E,      H,       0, 0,  1, 0);
+  b.add(m->w_ih + E0, nullptr, w->WihzT, 4 * H0, D0,   E0 + D0, 4 * H,  0,       0, H0, 1, 0);
+  b.add(m->w_ih, nullptr, w->WiheT,      4 * H0, E0,   E0 + D0, 4 * H,  0,       0, H0, 1, 0);
+  b.add(m->dec_att, nullptr, w->WhcatT,  A0,     H0,   H0,      NH3,    0,       0, 0,  1, 0);
+  b.add(m->beta_w, nullptr, w->WhcatT,   D0,     H0,   H0,      NH3,    0,       A, 0,  1, 0);
+  b.add(m->w_hh, nullptr, w->WhcatT,     4 * H0, H0,   H0,      NH3,    0,       A + D, H0, 1, 0);
+  b.add(m->enc_att, nullptr, w->WaT,     A0,     D0,   D0,      A,      0,       0, 0,  1, 0);
+  b.add(m->init_w, nullptr, w->WinitT,   2 * H0, E0,   E0,      2 * H,  0,       0, 0,  1, 0);
+  b.add(m->fact_w, nullptr, w->WfactT,   E0,     D0,   D0,      E,      0,       0, 0,  1, 0);
   SAT_REQUIRE(b.ok, "sat_pack_weights: job table overflow");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == SAT_F32) pack_kernel<float><<<b.tiles, 256, 0, st>>>(b.t);

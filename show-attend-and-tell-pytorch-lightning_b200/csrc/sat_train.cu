@@ -13,6 +13,7 @@
 #include "sat_gemm.cuh"
 #include "sat_attention_pipe.cuh"
 #include "sat_kernels.cuh"
+#include "sat_vocab_ce.cuh"
 
 namespace {
 
@@ -36,8 +37,13 @@ static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void
                            EpiStore<TS>{(TS*)f1, E, w.bfact, nullptr, 0}, st)));
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(f1, E, E), (const TS*)w.Winit, E, Bi, 2 * H,
                            EpiStore<float>{init_out, 2 * H, w.binit, nullptr, 0}, st)));
-  const int64_t n = 2 * (int64_t)B * H;
-  init_state_kernel<TS><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(init_out, (TS*)h0, c0, H, H, B, H, d.ncap);
+  const int H0 = d.H0 ? d.H0 : H;      // the [B,2H] -> [2,B,H] reinterpretation works on the module's true decoder_dim
+  if (H0 != H) {                        // padded state columns start (and stay) at zero
+    SAT_CUDA(cudaMemsetAsync(h0, 0, sizeof(TS) * (size_t)B * H, st));
+    SAT_CUDA(cudaMemsetAsync(c0, 0, sizeof(float) * (size_t)B * H, st));
+  }
+  const int64_t n = 2 * (int64_t)B * H0;
+  init_state_kernel<TS><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(init_out, 2 * H, (TS*)h0, c0, H, H, B, H0, d.ncap);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   return 0;
@@ -49,13 +55,19 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   const int NH3 = A + D + 4 * H;
   const int caplen = T + 1;
   const bool tc = d.use_tc != 0;
+  const int V0 = d.V0 ? d.V0 : V;
   const TS* ann = (const TS*)b.ann;
+  // fused vocabulary projection + cross entropy (tensor-core mode): the logits are never written
+  const bool fuse_ce = b.ce_stats != nullptr && b.row_lse != nullptr && b.row_xt != nullptr && std::is_same<TS, bf16>::value && tc && !kExact &&
+                       b.sampled == nullptr && tc::operands_ok(gemm_a1(b.Xo, E, E), w.Wo, E);
+  SAT_REQUIRE(fuse_ce || b.logits != nullptr, "sat_train_forward: logits buffer missing (only the fused tensor-core path can do without)");
 
   // ---- once per image ------------------------------------------------------------------------
   SAT_TRY((prepare_images_impl<TS>(d, w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st, b.dropout_p, b.dropout_seed)));
 
   // ---- hoisted: embeddings of the (teacher-forced) previous words and their gate projection ---
-  tok_init_kernel<<<(T * B + 255) / 256, 256, 0, st>>>(b.caps, b.tok, B, T, caplen);
+  SAT_CUDA(cudaMemsetAsync(b.out + 6, 0, sizeof(float), st));
+  tok_init_kernel<<<(T * B + 255) / 256, 256, 0, st>>>(b.caps, b.tok, B, T, caplen, V0, b.out + 6);
   SAT_COUNT_LAUNCH();
   embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.tok, (TS*)b.Xe, E, 0, b.emb_dropout_p, b.dropout_seed);
   SAT_COUNT_LAUNCH();
@@ -113,34 +125,49 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
                            EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr, d.plain_output, b.dropout_p, b.dropout_seed, 0}, st)));
-  SAT_PROF(3, st);
-  if (b.logits_f32) {
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
-                             EpiStore<float>{(float*)b.logits, V, w.bo, nullptr, 0}, st)));
-  } else {
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
-                             EpiStore<TS>{(TS*)b.logits, V, w.bo, nullptr, 0}, st)));
-  }
-
-  SAT_PROF(3, st);
-
-  // ---- loss ------------------------------------------------------------------------------------
   ntok_kernel<<<1, 256, 0, st>>>(b.lens, B, b.out);
   SAT_COUNT_LAUNCH();
-  const size_t ce_smem = sizeof(float) * (size_t)(V + 40);
-  if (b.logits_f32) {
-    auto k = ce_rows_kernel<float, TS, kExact>;
-    if (ce_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem));
-    k<<<T * B, 256, ce_smem, st>>>((float*)b.logits, (TS*)b.dlogits, b.caps, b.lens, b.out + 4, b.row_loss, b.row_argmax, B,
-                                   V, caplen, b.label_smoothing, 1);
+  SAT_PROF(3, st);
+  if (fuse_ce) {
+    // pass 1: per-tile soft-max statistics in the GEMM epilogue; finish per row; pass 2 (training only): recompute the tiles
+    // into dlogits.  HBM traffic of the stage: one bf16 [T*B, V] write instead of write + read + write.
+    tc::VocabArgs va{};
+    va.bias = w.bo; va.V0 = V0; va.NT = (V + 127) / 128; va.stats = reinterpret_cast<float4*>(b.ce_stats);
+    va.caps = b.caps; va.lens = b.lens; va.B = B; va.caplen = caplen; va.row_xt = b.row_xt; va.row_lse = b.row_lse;
+    va.inv_ntok_p = b.out + 4; va.smoothing = b.label_smoothing; va.dlogits = (bf16*)b.dlogits; va.ldd = V;
+    SAT_TRY((tc::launch_vocab<tc::VOCAB_STATS>(gemm_a1(b.Xo, E, E), (const bf16*)w.Wo, E, T * B, V, va, st)));
+    SAT_CUDA(sat_launch_pdl(tc::ce_finalize_kernel, dim3((T * B + 7) / 8), dim3(256), 0, st, (const float4*)va.stats, va.NT,
+                            (const float*)b.row_xt, b.lens, B, T * B, V0, b.label_smoothing, b.row_lse, b.row_loss, b.row_argmax));
+    SAT_COUNT_LAUNCH();
+    if (b.dlogits != nullptr) SAT_TRY((tc::launch_vocab<tc::VOCAB_DLOGITS>(gemm_a1(b.Xo, E, E), (const bf16*)w.Wo, E, T * B, V, va, st)));
+    SAT_PROF(3, st);
   } else {
-    auto k = ce_rows_kernel<TS, TS, kExact>;
-    if (ce_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem));
-    k<<<T * B, 256, ce_smem, st>>>((TS*)b.logits, (TS*)b.dlogits, b.caps, b.lens, b.out + 4, b.row_loss, b.row_argmax, B, V,
-                                   caplen, b.label_smoothing, 1);
+    if (b.logits_f32) {
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
+                               EpiStore<float>{(float*)b.logits, V, w.bo, nullptr, 0}, st)));
+    } else {
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.Xo, E, E), (const TS*)w.Wo, E, T * B, V,
+                               EpiStore<TS>{(TS*)b.logits, V, w.bo, nullptr, 0}, st)));
+    }
+    SAT_PROF(3, st);
+    // ---- loss ----------------------------------------------------------------------------------
+    const size_t ce_smem = sizeof(float) * (size_t)(V + 40);
+    SAT_REQUIRE(ce_smem <= 227 * 1024, "vocabulary of %d words needs %zu bytes of shared memory per row in the unfused cross-entropy "
+                "kernel (limit 227 KB): use the fused tensor-core path (bf16) for vocabularies this large", V, ce_smem);
+    if (b.logits_f32) {
+      auto k = ce_rows_kernel<float, TS, kExact>;
+      if (ce_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem));
+      k<<<T * B, 256, ce_smem, st>>>((float*)b.logits, (TS*)b.dlogits, b.caps, b.lens, b.out + 4, b.row_loss, b.row_argmax, B,
+                                     V0, V, caplen, b.label_smoothing, 1);
+    } else {
+      auto k = ce_rows_kernel<TS, TS, kExact>;
+      if (ce_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ce_smem));
+      k<<<T * B, 256, ce_smem, st>>>((TS*)b.logits, (TS*)b.dlogits, b.caps, b.lens, b.out + 4, b.row_loss, b.row_argmax, B, V0, V,
+                                     caplen, b.label_smoothing, 1);
+    }
+    SAT_COUNT_LAUNCH();
+    SAT_LAUNCH_OK();
   }
-  SAT_COUNT_LAUNCH();
-  SAT_LAUNCH_OK();
   // per-CTA partials of sum (1-S)^2 live in the (by now dead) hp scratch buffer
   const int nparts = (B * L + 255) / 256;
   SAT_REQUIRE((int64_t)nparts <= (int64_t)B * NH3, "reduction scratch too small");
@@ -161,7 +188,11 @@ int check_dims(const SatDims* d) {
   SAT_REQUIRE(d->L > 0 && d->T >= 0, "bad L=%d T=%d", d->L, d->T);
   SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0 && d->D > 0 && d->A > 0 &&
                   d->E > 0 && d->H > 0 && d->V > 0,
-              "D=%d A=%d E=%d H=%d V=%d must be positive multiples of 8", d->D, d->A, d->E, d->H, d->V);
+              "storage dims D=%d A=%d E=%d H=%d V=%d must be positive multiples of 8 (pad the module's dims: SatDims.D0 ..)", d->D, d->A,
+              d->E, d->H, d->V);
+  SAT_REQUIRE(d->D0 >= 0 && d->D0 <= d->D && d->A0 >= 0 && d->A0 <= d->A && d->E0 >= 0 && d->E0 <= d->E && d->H0 >= 0 && d->H0 <= d->H &&
+                  d->V0 >= 0 && d->V0 <= d->V,
+              "true dims D0=%d A0=%d E0=%d H0=%d V0=%d must not exceed the storage dims", d->D0, d->A0, d->E0, d->H0, d->V0);
   return 0;
 }
 
@@ -223,7 +254,7 @@ int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b,
   SAT_REQUIRE(w && b, "sat_train_forward: NULL struct");
   SAT_REQUIRE(d->T > 0, "sat_train_forward: T must be > 0");
   SAT_REQUIRE(b->ann && b->caps && b->lens && b->tok && b->P && b->meanv && b->f1 && b->init_out && b->Xe && b->Gx && b->Hs && b->Cs &&
-                  b->hp && b->Q && b->alphas && b->Z && b->GZ && b->Beta && b->Gates && b->Xo && b->logits && b->row_loss &&
+                  b->hp && b->Q && b->alphas && b->Z && b->GZ && b->Beta && b->Gates && b->Xo && b->row_loss &&
                   b->row_argmax && b->S && b->out,
               "sat_train_forward: NULL forward buffer");
   cudaStream_t st = (cudaStream_t)stream;

@@ -98,8 +98,9 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   }
   // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
   const bool init_tc = tc && !std::is_same<TS, float>::value && b.d_init_out16 != nullptr && b.df116 != nullptr;
-  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, b.d_init_out,
-                                                                  init_tc ? (bf16*)b.d_init_out16 : (bf16*)nullptr, B, H, d.ncap);
+  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, H, b.d_init_out,
+                                                                  init_tc ? (bf16*)b.d_init_out16 : (bf16*)nullptr, 2 * H, B,
+                                                                  d.H0 ? d.H0 : H, d.ncap);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   if (init_tc) {

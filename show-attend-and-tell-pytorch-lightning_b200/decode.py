@@ -23,7 +23,7 @@ class DecodeWeights:
         self.pw = PackedWeights(W, dtype=dtype, device=device, backward=False)
         dm = self.pw.dims
         self.exact, self.use_tc = exact, use_tc
-        d = decoder.make_dims(1, 1, 1, dm["D"], dm["A"], dm["E"], dm["H"], dm["V"], 1, dtype, exact, use_tc, self.pw.plain_output)
+        d = decoder.make_dims(1, 1, 1, self.pw, 1, dtype, exact, use_tc)
         self.GxV = torch.empty(dm["V"], 4 * dm["H"], dtype=torch.float32, device=device)
         _lib.check(_lib.lib().sat_decode_prepare_weights(C.byref(d), self.pw.ref(), _lib.ptr(self.GxV), _lib.stream_ptr()),
                    "sat_decode_prepare_weights")
@@ -38,10 +38,16 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     n_img, L, D = ann_bld.shape
     dm = dw.pw.dims
     A, E, H, V = dm["A"], dm["E"], dm["H"], dm["V"]
+    if D != dm["D"]:                      # encoder_dim that is not a multiple of 8: zero-padded channels
+        assert D == dw.pw.dims0["D"], "annotation width %d != encoder_dim %d" % (D, dw.pw.dims0["D"])
+        ann_bld = torch.nn.functional.pad(ann_bld, (0, dm["D"] - D)).contiguous()
+        D = dm["D"]
     S = int(max_gen_length)
     R = n_img * k
     dtype = dw.pw.dtype
-    d = decoder.make_dims(R, n_img, L, D, A, E, H, V, S + 1, dtype, dw.exact, dw.use_tc, dw.pw.plain_output)
+    d = decoder.make_dims(R, n_img, L, dw.pw, S + 1, dtype, dw.exact, dw.use_tc)
+    # greedy on the tensor cores: per-tile soft-max statistics replace the [R,V] logits
+    fuse_greedy = k == 1 and dw.use_tc and dtype == torch.bfloat16 and not dw.exact
     f, s, i32 = torch.float32, dtype, torch.int32
     _n = [0]
 
@@ -51,7 +57,7 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
 
     t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * H), f),
              h=mk((R, H), s), c=mk((R, H), f), hn=mk((R, H), s), cn=mk((R, H), f), hp=mk((R, A + D + 4 * H), f),
-             z=mk((R, D), s), gz=mk((R, D), s), xo=mk((R, E), s), logits=mk((R, V), f), alpha_all=mk((S + 1, R, L), f),
+             z=mk((R, D), s), gz=mk((R, D), s), xo=mk((R, E), s), alpha_all=mk((S + 1, R, L), f),
              cand_val=mk((R, k), f), cand_idx=mk((R, k), i32), tok_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev),
              asrc_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev), top_scores=mk((R,), f), cur_tok=mk((R,), i32),
              src_row=torch.zeros((R,), dtype=i32, device=dev), alive=mk((R,), i32), kcur=mk((n_img,), i32),
@@ -59,6 +65,10 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
              fin_asrc=torch.zeros((n_img, k, S + 1), dtype=i32, device=dev), fin_len=mk((n_img, k), i32),
              fin_score=torch.full((n_img, k), float("-inf"), dtype=f, device=dev), fin_ppl=mk((n_img, k), f),
              fin_count=mk((n_img,), i32))
+    if fuse_greedy:
+        t["topk_stats"] = mk((R, (V + 127) // 128, 4), f)
+    else:
+        t["logits"] = mk((R, V), f)
     temps = temperature if isinstance(temperature, (list, tuple)) else [temperature]
     temps_arr = (C.c_float * (S + 1))(*[float(temps[i % len(temps)]) for i in range(S + 1)])
     b = _lib.SatDecodeBuffers()
@@ -161,22 +171,3 @@ def caption_from_annotations(model, ann, beamk, max_gen_length, temperature, res
     vocab = dict(PAD=model.stoi("<PAD>"), START=model.stoi("<START>"), END=model.stoi("<END>"), UNK=model.stoi("<UNK>"))
     t = decode_annotations(dw, bld, int(beamk), max_gen_length, temperature, rescore_method, rescore_reward, vocab)
     return assemble(t, hw, return_all=return_all)
-
-
-def smoke():
-    """tiny greedy + beam decode on cuda:0 checked against the CPU oracle (called by __graft_entry__.smoke)."""
-    from oracle import sat_oracle as O
-    D, A, E, H, V = 64, 32, 32, 64, 128
-    W = O.random_weights(D, A, E, H, V, seed=5, sharpen=True)
-    W["output.output.bias"][V - 1] = 3.0
-    g = torch.Generator().manual_seed(6)
-    ann = torch.randn(4, D, 4, 4, generator=g)
-    vocab = dict(PAD=0, UNK=V - 3, START=V - 2, END=V - 1)
-    dw = DecodeWeights(W, torch.float32, torch.device("cuda"), True, False)
-    for k in (1, 3):
-        ref = O.caption(W, ann, vocab, beamk=k, max_gen_length=10, rescore_method="LN")
-        t = decode_annotations(dw, decoder.annotations_as_bld(ann.cuda(), torch.float32), k, 10, 1.0, "LN", 0.5, vocab)
-        caps, scores, _, _ = assemble(t, (4, 4))
-        assert caps == ref[0], (k, caps, ref[0])
-        assert max(abs(a - b) for a, b in zip(scores, ref[1])) < 1e-4
-    print("decode smoke ok: greedy and beam token ids match the CPU oracle")

@@ -148,18 +148,28 @@ def _as_bld(annotations, dtype):
     return decoder.annotations_as_bld(annotations, dtype), annotations.shape[2:]
 
 
+def _pad8(x, dims):
+    """zero-pad the given dims of x up to multiples of 8 (the kernels' storage granularity)."""
+    pads = []
+    for dim in range(x.dim() - 1, -1, -1):
+        n = x.shape[dim]
+        pads += [0, ((n + 7) // 8 * 8 - n) if (dim in dims or dim - x.dim() in dims) else 0]
+    return torch.nn.functional.pad(x, pads) if any(pads) else x
+
+
 def _linear(x, weight, bias=None):
-    """x [M,K] fp32 cuda, weight [N,K] -> [M,N] through libsat_b200's GEMM core (sat_linear)."""
+    """x [M,K] fp32 cuda, weight [N,K] -> [M,N] through libsat_b200's GEMM core (sat_linear); any K, N (zero-padded to 8s)."""
     import ctypes as C
-    x = x.contiguous().float()
-    w = weight.detach().contiguous().float()
+    N0 = weight.shape[0]
+    x = _pad8(x.float(), (-1,)).contiguous()
+    w = _pad8(weight.detach().float(), (0, 1)).contiguous()
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty(M, N, dtype=torch.float32, device=x.device)
-    b = bias.detach().contiguous().float() if bias is not None else None
+    b = _pad8(bias.detach().float(), (0,)).contiguous() if bias is not None else None
     _lib.check(_lib.lib().sat_linear(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(out), N, M, N, K,
                                      _lib.SAT_F32, 1, 0, _lib.stream_ptr()), "sat_linear")
-    return out
+    return out[:, :N0] if N0 != N else out
 
 
 class InitLSTM(nn.Module):
@@ -196,19 +206,24 @@ class SoftAttention(nn.Module):
         """-> (z [B,D], alpha [B,h,w])  (alpha [B,L] for 3-D annotations)."""
         import ctypes as C
         bld, hw = _as_bld(annotations, torch.float32)
+        D0 = bld.shape[2]
+        bld = _pad8(bld, (-1,)).contiguous()                      # storage dims are multiples of 8: zero channels / units add nothing
         B, L, D = bld.shape
-        A = self.encoder_att.weight.shape[0]
-        P = _linear(bld.reshape(B * L, D), self.encoder_att.weight).reshape(B, L, A)
+        Wa = _pad8(self.encoder_att.weight.detach().float(), (0, 1))
+        A = Wa.shape[0]
+        P = _linear(bld.reshape(B * L, D), Wa).reshape(B, L, A)
         hp = torch.zeros(B, A + D, dtype=torch.float32, device=bld.device)
-        hp[:, :A] = _linear(decoder_hidden, self.decoder_att.weight)
-        d = decoder.make_dims(B, B, L, D, A, 8, decoder_hidden.shape[1], 8, 1, torch.float32, True, False)
+        hp[:, :self.decoder_att.weight.shape[0]] = _linear(decoder_hidden, self.decoder_att.weight)
+        up8 = lambda n: (n + 7) // 8 * 8
+        d = decoder.make_dims(B, B, L, dict(D=D, A=A, E=8, H=up8(decoder_hidden.shape[1]), V=8), 1, torch.float32, True, False)
         alpha = torch.empty(B, L, dtype=torch.float32, device=bld.device)
         z = torch.empty(B, D, dtype=torch.float32, device=bld.device)
         gz = torch.empty_like(z)
-        wf = self.f_att.weight.detach().reshape(-1).contiguous().float()
+        wf = _pad8(self.f_att.weight.detach().reshape(-1).float(), (0,)).contiguous()
         _lib.check(_lib.lib().sat_attention_step_fwd(C.byref(d), _lib.ptr(bld), _lib.ptr(P), _lib.ptr(wf), _lib.ptr(hp),
                                                      A + D, None, 0, _lib.ptr(alpha), L, _lib.ptr(z), _lib.ptr(gz), None, D,
                                                      _lib.stream_ptr()), "sat_attention_step_fwd")
+        z = z[:, :D0] if D0 != D else z
         return z, (alpha.reshape(B, *hw) if hw is not None else alpha)
 
 
@@ -276,7 +291,7 @@ class _FusedTrainLoss(torch.autograd.Function):
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, cfg["label_smoothing"], cfg["att_gamma"], exact=cfg["exact"],
                                     use_tc=cfg["use_tc"], logits_f32=False, backward=True, keep_logits=False,
-                                    sampled=cfg.get("sampled"), dropout=cfg.get("dropout", (0.0, 0.0, 0)))
+                                    sampled=cfg.get("sampled"), dropout=cfg.get("dropout", (0.0, 0.0, 0)), fuse_ce=True)
         ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
         ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
         ctx.have = [p is not None for p in params]
@@ -311,13 +326,17 @@ class _TrainLogits(torch.autograd.Function):
         ctx.pw, ctx.buf, ctx.cfg = pw, buf, cfg
         ctx.ann_shape, ctx.ann_dtype = ann.shape, ann.dtype
         ctx.have = [p is not None for p in params]
-        logits = buf.t["logits"].permute(1, 0, 2).contiguous()          # [B,T,V] fp32 (model.py:504)
+        V0 = pw.dims0["V"]
+        logits = buf.t["logits"][:, :, :V0].permute(1, 0, 2).contiguous()          # [B,T,V] fp32 (model.py:504)
         return logits, buf.t["alphas"].clone()
 
     @staticmethod
     def backward(ctx, glogits, galphas):
         cfg, buf = ctx.cfg, ctx.buf
-        buf.t["dlogits"].copy_(glogits.permute(1, 0, 2))
+        V0 = ctx.pw.dims0["V"]
+        if V0 != ctx.pw.dims["V"]:
+            buf.t["dlogits"].zero_()
+        buf.t["dlogits"][:, :, :V0].copy_(glogits.permute(1, 0, 2))
         saved_gamma = buf.c.att_gamma
         buf.c.att_gamma = 0.0
         G, d_ann = decoder.train_backward(ctx.pw, buf, None, pad_idx=cfg["pad_idx"], weight_tying=cfg["weight_tying"],

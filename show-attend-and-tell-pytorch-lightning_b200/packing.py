@@ -44,10 +44,17 @@ class PackedWeights:
     def __init__(self, W, dtype=torch.float32, device="cuda", backward=True):
         self.dtype = dtype
         dev = self.device = torch.device(device)
-        V, E = W["embedding.weight"].shape
-        H = W["lstm.weight_hh_l0"].shape[1]
-        A, D = W["attention.encoder_att.weight"].shape
+        V0, E0 = W["embedding.weight"].shape
+        H0 = W["lstm.weight_hh_l0"].shape[1]
+        A0, D0 = W["attention.encoder_att.weight"].shape
+        # The kernels work on storage dims that are multiples of 8 (16-byte vectors, TMA rows).  A module with other sizes
+        # (V = words above min_count + 4, 100/300-d GloVe embeddings ...) is zero-padded here: zero weights keep the padded
+        # lanes exactly zero through forward and backward, the padded vocabulary entries get a bias of -inf.
+        up8 = lambda n: (int(n) + 7) // 8 * 8
+        V, E, H, D, A = up8(V0), up8(E0), up8(H0), up8(D0), up8(A0)
         self.dims = dict(V=V, E=E, H=H, D=D, A=A)
+        self.dims0 = dict(V=int(V0), E=int(E0), H=int(H0), D=int(D0), A=int(A0))
+        self.padded = self.dims != self.dims0
         # DeepOutput(deep=False) has no context projection (model.py:120-121): its slots stay zero, plain epilogues
         self.plain_output = W.get("output.context.weight", None) is None
         NH3, NH4 = A + D + 4 * H, A + D + 4 * H + E
@@ -62,7 +69,10 @@ class PackedWeights:
         t["bg"] = z((4 * H,), f)
         t["Whozo"] = z((E, H + D), dtype)
         t["Wo"] = z((V, E), dtype)
-        t["bo"] = z((V,), f) if W.get("output.output.bias", None) is not None else None
+        self.has_out_bias = W.get("output.output.bias", None) is not None
+        t["bo"] = z((V,), f) if (self.has_out_bias or V != V0) else None
+        if t["bo"] is not None and V != V0:
+            t["bo"][V0:] = float("-inf")           # padded words never win a max, add nothing to a soft-max
         t["wf"] = z((A,), f)
         t["Emb"] = z((V, E), dtype)
         t["Wfact"] = z((E, D), dtype)
@@ -84,6 +94,7 @@ class PackedWeights:
         self._d = _lib.SatDims()
         self._d.B = self._d.Bi = self._d.ncap = 1
         self._d.L, self._d.D, self._d.A, self._d.E, self._d.H, self._d.V, self._d.T = 1, D, A, E, H, V, 1
+        self._d.D0, self._d.A0, self._d.E0, self._d.H0, self._d.V0 = int(D0), int(A0), int(E0), int(H0), int(V0)
         self._d.dtype = _lib.dtype_code(dtype)
         self.repack(W)
 

@@ -31,7 +31,7 @@ alpha = torch.empty(B, L, device="cuda")
 z = torch.empty(B, D, device="cuda", dtype=dt)
 gz = torch.empty_like(z)
 beta = torch.empty_like(z)
-d = decoder.make_dims(B, B, L, D, A, 8, 8, 8, 1, dt, args.fp32, False)
+d = decoder.make_dims(B, B, L, dict(D=D, A=A, E=8, H=8, V=8), 1, dt, args.fp32, False)
 lib = _lib.lib()
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda") if args.flush else None
 

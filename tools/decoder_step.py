@@ -16,6 +16,7 @@ ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--no-tc", action="store_true")
 ap.add_argument("--decode", type=int, default=0, help="run batched decode with this beam width instead of training")
 ap.add_argument("--dims", type=str, default="", help="D,A,E,H,V,T,L override, e.g. 2048,128,256,1024,6400,20,196 (configs[2])")
+ap.add_argument("--no-fuse-ce", action="store_true", help="unfused vocabulary GEMM + ce_rows_kernel")
 ap.add_argument("--profile", type=int, default=0, help="also report the in-situ per-launch time of kernel kind 1 (att fwd) / 2 (att bwd) / 3 (vocab GEMM)")
 args = ap.parse_args()
 
@@ -59,7 +60,7 @@ else:
     pw = PackedWeights(W, dtype=dtype, device="cuda", backward=True)
     for it in range(args.iters):
         ev0.record()
-        buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True)
+        buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True, fuse_ce=not args.no_fuse_ce)
         G, d_ann = decoder.train_backward(pw, buf)
         ev1.record()
         torch.cuda.synchronize()
@@ -68,7 +69,7 @@ else:
         from sat_b200 import _lib
         _lib.profile_begin(args.profile)
         for it in range(3):
-            buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True)
+            buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True, fuse_ce=not args.no_fuse_ce)
             G, d_ann = decoder.train_backward(pw, buf)
         torch.cuda.synchronize()
         ms, n = _lib.profile_end()
