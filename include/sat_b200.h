@@ -236,7 +236,8 @@ unsigned long long sat_launch_count(void);
 int sat_pack_weights(const SatDims* d, const SatMasterWeights* m, const SatWeights* w, void* stream);
 
 /* Kernel timing for bench.py's roofline entry: while enabled, every launch of the selected kernel kind
- * (1 = attention step forward, 2 = attention step backward, 3 = vocabulary GEMM) is bracketed by CUDA
+ * (1 = attention step forward, 2 = attention step backward, 3 = vocabulary projection stage (GEMM, or the fused
+ * statistics pass + row finalize + dlogits pass), 4 = gate GEMM + LSTM cell of the training forward) is bracketed by CUDA
  * events on its own stream.  sat_profile_end synchronises, returns the summed device time and count. */
 int sat_profile_begin(int kind);
 int sat_profile_end(float* total_ms, int* count);

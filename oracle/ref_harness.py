@@ -16,7 +16,12 @@ import types
 import torch
 from torch import nn
 
-REFERENCE_DIR = os.environ.get("SAT_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference exists in the build container only.  __graft_entry__.build() copies the reference's model.py / util.py
+# UNMODIFIED into the git-ignored oracle/_ref/ (it travels to the GPU box like the built .so), so that bench.py's
+# `--impl reference` arm can time the real reference there.  Nothing under oracle/_ref is ever committed.
+_CANDIDATES = [os.environ.get("SAT_REFERENCE_DIR", ""), "/root/reference", os.path.join(_HERE, "_ref")]
+REFERENCE_DIR = next((d for d in _CANDIDATES if d and os.path.isfile(os.path.join(d, "model.py"))), "/root/reference")
 
 
 class _HParams(dict):
@@ -32,11 +37,37 @@ class _HParams(dict):
         self[k] = v
 
 
+class _NullExperiment:
+    def add_scalar(self, *a, **k):
+        pass
+
+
+class _NullLogger:
+    experiment = _NullExperiment()
+
+
+class _NullTrainer:
+    global_step = 0
+
+
 class _LightningModule(nn.Module):
+    """what the reference's SAT needs from pl.LightningModule: hparams capture, device, and -- for
+    training_step / the epoch hooks -- logger, trainer, optimizers(), log(), current_epoch, global_step."""
+    current_epoch = 0
+    global_step = 0
+    logger = _NullLogger()
+    trainer = _NullTrainer()
+
     def save_hyperparameters(self):
         frame = inspect.currentframe().f_back
         kwargs = frame.f_locals.get("kwargs", {})
         object.__setattr__(self, "_hparams", _HParams(kwargs))
+
+    def optimizers(self):
+        return getattr(self, "_optimizer", None)
+
+    def log(self, *a, **k):
+        pass
 
     @property
     def hparams(self):
@@ -123,7 +154,10 @@ def default_hparams(**over):
               mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225], embed_dim=256, embed_norm=None,
               attention_dim=128, decoder_dim=512, decoder_layers=1, dropout=0.0, embedding_dropout=0.0,
               label_smoothing=0.0, weight_tying=False, deep_output=True, vocab_size=6400,
-              pretrained_embedding=None, att_gamma=1.0, decoder_tf="always")
+              pretrained_embedding=None, att_gamma=1.0, decoder_tf="always",
+              # read by training_step / configure_optimizers (model.py:608-617,720-817)
+              lr_warmup_steps=0, scheduler=None, opt="adam", adam_b1=0.9, adam_b2=0.999, decoder_lr=4e-4, embedding_lr=4e-4,
+              encoder_lr=1e-4, weight_decay=0.0, encoder_finetune_after=-1)
     hp.update(over)
     stoi, itos = make_vocab(hp["vocab_size"])
     hp.setdefault("vocab_stoi", stoi)

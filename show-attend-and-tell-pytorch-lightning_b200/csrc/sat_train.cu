@@ -118,7 +118,9 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
     EpiLstm<TS, kExact> epi{b.Gx + (int64_t)t * B * 4 * H, 4 * H, b.hp + A + D, NH3, h_t, c_t,
                             (TS*)b.Hs + (int64_t)(t + 1) * B * H, b.Cs + (int64_t)(t + 1) * B * H, H, H,
                             (TS*)b.Gates + (int64_t)t * B * 4 * H, 4 * H, b.lens, t, nullptr};
+    SAT_PROF(4, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(gz_t, D, D), (const TS*)w.Wihz, D, B, 4 * H, epi, st)));
+    SAT_PROF(4, st);
   }
 
   // ---- hoisted: deep output (model.py:127) and vocabulary projection (model.py:130) over all T*B rows

@@ -71,3 +71,99 @@ class FlatGradBuckets:
         inv = 1.0 / world_size
         for f in self.flat:
             f.mul_(inv)
+
+
+class OverlappedGradReducer:
+    """Gradient averaging overlapped with the backward pass (what PL's DDP does for the reference, train.py:272).
+
+    Bucket 0 holds the decoder parameters: their gradients are all final when the fused decoder backward returns, i.e.
+    BEFORE the encoder backward starts, so its all-reduce travels over NVLink while cuDNN runs the trunk's backward.  The
+    encoder parameters follow in REVERSE order (autograd produces the last layers' gradients first) in buckets of
+    ~`bucket_bytes`; a post-accumulate-grad hook per parameter counts a bucket down and issues its asynchronous
+    all-reduce (ReduceOp.AVG on NCCL: no separate scaling pass) the moment its last gradient has landed.  `.grad` of every
+    parameter is a view into its bucket, zeroed by prepare() so that autograd accumulates in place.
+
+        reducer.prepare(); loss.backward(); reducer.finish(); optimizer.step()
+    """
+
+    def __init__(self, dec_params, enc_params, bucket_bytes=32 << 20, group=None):
+        self.group = group
+        dec = [p for p in dec_params if p.requires_grad]
+        enc = [p for p in enc_params if p.requires_grad][::-1]
+        self.buckets = [dec] if dec else []
+        cur, cur_n = [], 0
+        for p in enc:
+            n = p.numel()
+            if cur and (cur_n + n) * 4 > bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += n
+        if cur:
+            self.buckets.append(cur)
+        self.flat, self.views = [], []
+        for b in self.buckets:
+            flat = torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
+            views, off = [], 0
+            for p in b:
+                views.append(FlatGradBuckets._view(flat, off, p))
+                off += p.numel()
+            self.flat.append(flat)
+            self.views.append(views)
+        self._pending = [0] * len(self.buckets)
+        self._handles = [None] * len(self.buckets)
+        self._hooks = []
+        self._armed = False
+        backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        self._avg = backend == "nccl"
+        self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+        for bi, b in enumerate(self.buckets):
+            for p in b:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _make_hook(self, bi):
+        def hook(param):
+            if not self._armed:
+                return
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        if self._handles[bi] is not None or self._world <= 1:
+            return
+        # a parameter whose .grad was re-assigned (not accumulated in place) is copied back into its bucket slot first
+        for p, v in zip(self.buckets[bi], self.views[bi]):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._handles[bi] = dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True)
+
+    def prepare(self):
+        """before backward(): zero the buckets (autograd accumulates into the views) and arm the hooks"""
+        for bi, (b, flat, views) in enumerate(zip(self.buckets, self.flat, self.views)):
+            flat.zero_()
+            for p, v in zip(b, views):
+                p.grad = v
+            self._pending[bi] = len(b)
+            self._handles[bi] = None
+        self._armed = True
+
+    def finish(self):
+        """after backward(): reduce buckets whose hooks did not all fire (unused parameters), wait for every all-reduce"""
+        self._armed = False
+        for bi in range(len(self.buckets)):
+            if self._handles[bi] is None:
+                self._launch(bi)
+        for bi, h in enumerate(self._handles):
+            if h is not None:
+                h.wait()
+                if not self._avg:
+                    self.flat[bi].mul_(1.0 / self._world)
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

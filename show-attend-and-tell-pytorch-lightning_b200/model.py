@@ -378,6 +378,11 @@ class SAT(_Base):
         self.special_idxs = [self.stoi("<PAD>"), self.stoi("<START>"), self.stoi("<END>")]
         # module construction order follows model.py:154-195 so that a seeded default init is identical
         self.encoder = get_encoder(hp)
+        if self._dtype() == torch.bfloat16 and hp.get("cudnn_batchnorm", True):
+            # encoder boundary: PyTorch does not route bf16 batch-norm to cuDNN (ATen's channels_last kernels are 3-4x slower
+            # on B200); same parameters / buffers / state_dict keys, training-mode NHWC half-precision inputs go to cuDNN
+            from .cudnn_bn import convert_batchnorm
+            convert_batchnorm(self.encoder)
         self.embedding = nn.Embedding(num_embeddings=hp.vocab_size, embedding_dim=hp.embed_dim, max_norm=hp.embed_norm,
                                       padding_idx=self.stoi("<PAD>"))
         self.embedding_dropout = nn.Dropout(p=hp.embedding_dropout)

@@ -49,3 +49,47 @@ def test_flat_bucket_allreduce_mean_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _worker_overlap(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import sat_b200  # noqa: F401
+    from sat_b200.dist import OverlappedGradReducer
+    torch.manual_seed(0)
+    dec = [torch.nn.Parameter(torch.randn(s)) for s in [(7, 5), (11,)]]
+    enc = [torch.nn.Parameter(torch.randn(s)) for s in [(3, 4, 2), (1,), (6, 6), (9,)]]
+    unused = torch.nn.Parameter(torch.randn(4))                  # never receives a gradient: its bucket is reduced by finish()
+    red = OverlappedGradReducer(dec, enc + [unused], bucket_bytes=100)
+    assert len(red.buckets) >= 3 and red.buckets[0] == dec
+    launched = []
+    orig = red._launch
+    red._launch = lambda bi: (launched.append(bi), orig(bi))[1]
+    ok = True
+    for step in range(2):                                         # two steps: buckets are re-zeroed, hooks re-armed
+        red.prepare()
+        params = dec + enc
+        loss = sum(((rank + 1) * (i + 1) * (step + 1)) * p.sum() for i, p in enumerate(params))
+        loss.backward()
+        n_in_backward = len(launched)
+        red.finish()
+        for i, p in enumerate(params):
+            expect = sum((r + 1) * (i + 1) * (step + 1) for r in range(world)) / world
+            ok = ok and torch.allclose(p.grad, torch.full_like(p, expect))
+        ok = ok and bool((unused.grad == 0).all())
+        ok = ok and n_in_backward >= len(red.buckets) - 1          # every bucket but the unused one started inside backward()
+        launched.clear()
+    red.close()
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_overlap, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
