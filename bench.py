@@ -460,7 +460,7 @@ def run_train(args, D, name):
     clk = clocks.stop()
     launches = (_lib.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     value = B * world * args.steps / (tot_ms * 1e-3)
-    e2e_ms, _ = timed(D, step_e2e, args.steps, max(1, args.warmup // 2), drain=drain_e2e)
+    e2e_ms, _ = timed(D, step_e2e, args.steps, args.warmup, drain=drain_e2e)
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
     h2d = img_h.numel() * 4 + caps_h.numel() * 8 + lens_h.numel() * 8
 

@@ -62,54 +62,80 @@ __global__ void __launch_bounds__(256) ncap_sum_kernel(const TI* __restrict__ in
   st4(out + i4, acc);
 }
 
-// ---- embedding gradient: dEmb[v, :] = sum over the rows m (ascending) with tok[m] == v of dXe[m, :] ------------------
-// One warp per vocabulary entry; the CTA's 8 warps share the token list through shared memory.  Rows are added in row
-// order, so the result does not depend on scheduling (index_add_ with float atomics does).  The <PAD> row stays zero
-// (nn.Embedding(padding_idx), model.py:162).
-constexpr int EG_CHUNK = 2048;
+// ---- embedding gradient: dEmb[v, :] = sum over the rows m with tok[m] == v of dXe[m, :] ------------------------------
+// A CTA owns EG_TPC consecutive vocabulary entries.  The token list is staged in shared memory chunk by chunk; for every
+// owned word the CTA's 8 warps split the chunk's rows into 8 contiguous ranges, each warp walks its range 32 token ids at
+// a time (ballot) and adds the matching rows of dXe in ascending row order, four rows in flight (independent loads, ordered
+// adds); the 8 partial sums are added in warp order at the end.  The order of additions is fixed by (row, warp) alone: no
+// atomics, no sort, bit-identical from run to run (index_add_ with float atomics is not).  A frequent word (<START> feeds
+// every caption's first step) is spread over 8 warps x 4 loads in flight instead of one serial chain.  The <PAD> row stays
+// zero (nn.Embedding(padding_idx), model.py:162).
+constexpr int EG_TPC = 4;                // words per CTA
+constexpr int EG_COLS = 256;             // columns per pass: 32 lanes x 2 float4
+constexpr int EG_CHUNK = 4096;           // token ids staged per chunk (8 warps x 512 rows)
 __global__ void __launch_bounds__(256)
 embed_grad_kernel(const int32_t* __restrict__ tok, const float* __restrict__ dXe, int64_t ld_dxe, int M, int V0, int E0, int pad_idx,
                   float* __restrict__ dEmb) {
   __shared__ int32_t s_tok[EG_CHUNK];
+  __shared__ __align__(16) float part[8][EG_COLS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int v = blockIdx.x * 8 + warp;
-  const bool mine = v < V0 && v != pad_idx;
-  for (int e0 = 0; e0 < E0; e0 += 1024) {                       // 32 lanes x 8 x float4 columns per pass
-    float4 acc[8];
+  const int v0 = blockIdx.x * EG_TPC;
+  for (int e0 = 0; e0 < E0; e0 += EG_COLS) {
+    float4 acc[EG_TPC][2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < EG_TPC; ++k) acc[k][0] = acc[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int mb = 0; mb < M; mb += EG_CHUNK) {
       const int nm = min(EG_CHUNK, M - mb);
       __syncthreads();
       for (int i = threadIdx.x; i < nm; i += 256) s_tok[i] = tok[mb + i];
       __syncthreads();
-      if (!mine) continue;
-      for (int i = 0; i < nm; i += 32) {
-        const int t = (i + lane) < nm ? s_tok[i + lane] : -1;
-        unsigned hit = __ballot_sync(0xffffffffu, t == v);
-        while (hit) {
-          const int j0 = __ffs(hit) - 1;
-          hit &= hit - 1;
-          const float* row = dXe + (int64_t)(mb + i + j0) * ld_dxe + e0;
+      const int wb = warp * (EG_CHUNK / 8), we = min(nm, wb + EG_CHUNK / 8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int e = lane * 4 + 128 * j;                   // ld_dxe is a multiple of 4: whole float4s stay inside the row
-            if (e0 + e < E0) {
-              const float4 x = *reinterpret_cast<const float4*>(row + e);
-              acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
+      for (int k = 0; k < EG_TPC; ++k) {
+        const int v = v0 + k;
+        if (v >= V0 || v == pad_idx) continue;
+        for (int i = wb; i < we; i += 32) {
+          const int t = (i + lane) < we ? s_tok[i + lane] : -1;
+          unsigned hit = __ballot_sync(0xffffffffu, t == v);
+          while (hit) {
+            int r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              r[u] = hit ? mb + i + __ffs(hit) - 1 : -1;
+              hit &= hit - 1;                                    // 0 stays 0
+            }
+            float4 x[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int e = e0 + lane * 4 + 128 * j;           // ld_dxe is a multiple of 4: whole float4s stay inside the row
+                x[u][j] = (r[u] >= 0 && e < E0) ? *reinterpret_cast<const float4*>(dXe + (int64_t)r[u] * ld_dxe + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                        // rows are added in ascending order
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                acc[k][j].x += x[u][j].x; acc[k][j].y += x[u][j].y; acc[k][j].z += x[u][j].z; acc[k][j].w += x[u][j].w;
+              }
             }
           }
         }
       }
     }
-    if (v < V0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int e = e0 + lane * 4 + 128 * j;
-        const float a4[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+    for (int k = 0; k < EG_TPC; ++k) {
+      __syncthreads();
+      *reinterpret_cast<float4*>(&part[warp][lane * 4]) = acc[k][0];
+      *reinterpret_cast<float4*>(&part[warp][lane * 4 + 128]) = acc[k][1];
+      __syncthreads();
+      const int v = v0 + k, c = threadIdx.x;
+      if (v < V0 && e0 + c < E0) {
+        float sum = 0.0f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (e + u < E0) dEmb[(int64_t)v * E0 + e + u] = a4[u];
+        for (int w2 = 0; w2 < 8; ++w2) sum += part[w2][c];
+        dEmb[(int64_t)v * E0 + e0 + c] = sum;
       }
     }
   }
@@ -134,19 +160,43 @@ struct FinTable {
 };
 
 __global__ void __launch_bounds__(256) param_grads_finalize_kernel(const __grid_constant__ FinTable tab, const float* __restrict__ gscale) {
+  // a thread finishes 4 consecutive columns of one destination row: 16-byte loads from every split (the partials' pitches
+  // are multiples of 8 floats), 32-bit index arithmetic
   int j = 0;
   while (j + 1 < tab.njobs && (int)blockIdx.x >= tab.job[j + 1].blk0) ++j;
   const FinJob& J = tab.job[j];
-  const int64_t idx = (int64_t)(blockIdx.x - J.blk0) * 256 + threadIdx.x;
-  if (idx >= (int64_t)J.rows * J.cols) return;
-  const int rd = (int)(idx / J.cols), c = (int)(idx - (int64_t)rd * J.cols);
+  const unsigned cols4 = (unsigned)(J.cols + 3) >> 2;
+  const unsigned idx = (unsigned)(blockIdx.x - J.blk0) * 256u + threadIdx.x;
+  if (idx >= (unsigned)J.rows * cols4) return;
+  const int rd = (int)(idx / cols4), c = (int)(idx - (unsigned)rd * cols4) * 4;
   const int rs = J.inter_h > 0 ? 4 * (rd % J.inter_h) + rd / J.inter_h : rd;
   const float* p = J.src + (int64_t)rs * J.src_ld + J.src_c0 + c;
-  float s = 0.0f;
-  for (int z = 0; z < J.nsplit; ++z) s += p[(int64_t)z * J.split_stride];
-  if (J.scale_g && gscale) s *= *gscale;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec = c + 4 <= J.cols && (((uintptr_t)p | (uintptr_t)(J.split_stride * 4)) & 15) == 0;
+  if (vec) {
+    int z = 0;
+    for (; z + 4 <= J.nsplit; z += 4) {      // four splits in flight; the sum order stays z = 0, 1, 2, ...
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const float4*>(p + (int64_t)(z + u) * J.split_stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s[0] += q[u].x; s[1] += q[u].y; s[2] += q[u].z; s[3] += q[u].w; }
+    }
+    for (; z < J.nsplit; ++z) {
+      const float4 q = *reinterpret_cast<const float4*>(p + (int64_t)z * J.split_stride);
+      s[0] += q.x; s[1] += q.y; s[2] += q.z; s[3] += q.w;
+    }
+  } else {
+    for (int z = 0; z < J.nsplit; ++z)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u < J.cols) s[u] += p[(int64_t)z * J.split_stride + u];
+  }
+  const float g = (J.scale_g && gscale) ? *gscale : 1.0f;
   float* o = J.dst + (int64_t)rd * J.dst_ld + J.dst_c0 + c;
-  *o = J.accumulate ? *o + s : s;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (c + u < J.cols) o[u] = J.accumulate ? o[u] + s[u] * g : s[u] * g;
 }
 
 struct FinBuilder {
@@ -161,7 +211,7 @@ struct FinBuilder {
     j.src = src; j.dst = dst; j.split_stride = split_stride; j.src_ld = src_ld; j.dst_ld = dst_ld; j.nsplit = nsplit;
     j.src_c0 = src_c0; j.dst_c0 = dst_c0; j.rows = rows; j.cols = cols; j.inter_h = inter_h; j.scale_g = scale_g;
     j.accumulate = accumulate; j.blk0 = blocks;
-    blocks += (int)(((int64_t)rows * cols + 255) / 256);
+    blocks += (int)(((int64_t)rows * ((cols + 3) / 4) + 255) / 256);
   }
 };
 
@@ -289,7 +339,7 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   SAT_TRY(launch_colsum<float>(b.df1, E, Bi, E, ws + p.cs_off[C_FACT], st));
   // embedding: segment sum of dXe by the word that was fed
   if (g.embedding) {
-    embed_grad_kernel<<<(V0 + 7) / 8, 256, 0, st>>>(b.tok, b.dXe, E, M, V0, E0, g.pad_idx, g.embedding);
+    embed_grad_kernel<<<(V0 + EG_TPC - 1) / EG_TPC, 256, 0, st>>>(b.tok, b.dXe, E, M, V0, E0, g.pad_idx, g.embedding);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
   }

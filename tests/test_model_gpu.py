@@ -21,8 +21,9 @@ def build(seed=0, **over):
     m = SAT(**hp)
     m.encoder = nn.Identity()
     with torch.no_grad():
-        m.attention.f_att.weight *= 10
-    return m.cuda()
+        m.attention.f_att.weight *= 6        # non-uniform attention (softmax backward is exercised).  The scores' rounding error is
+    return m.cuda()                          # amplified by this factor: x10 sat on the 1e-5 tolerance (1.8e-5 on one GPU host, whose
+                                             # CPU runs the fp32 oracle's GEMMs in a different order)
 
 
 def batch(seed, Bi=5, ncap=2, T=7, V=128, D=64, hw=(4, 3)):
