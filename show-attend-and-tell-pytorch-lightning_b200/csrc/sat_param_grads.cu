@@ -275,6 +275,7 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   const bool bf = std::is_same<TS, bf16>::value;
   const bool tc = d.use_tc != 0 && bf;
   const Plan p = make_plan(d);
+  SAT_PROF(7, st);                 // 7 = the whole parameter-gradient stage (closing mark after the finalize kernel)
   SatNoPdlScope first_launch;      // the operands were written by the caller's previous launches (sat_train_backward)
 
   // one weight-gradient GEMM: partials [sk][n1][n2] at ws + off
@@ -339,7 +340,9 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   SAT_TRY(launch_colsum<float>(b.df1, E, Bi, E, ws + p.cs_off[C_FACT], st));
   // embedding: segment sum of dXe by the word that was fed
   if (g.embedding) {
+    SAT_PROF(5, st);
     embed_grad_kernel<<<(V0 + EG_TPC - 1) / EG_TPC, 256, 0, st>>>(b.tok, b.dXe, E, M, V0, E0, g.pad_idx, g.embedding);
+    SAT_PROF(5, st);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
   }
@@ -378,10 +381,13 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   cj(C_FACT, 0, g.fact_b, E0, 0);
   SAT_REQUIRE(f.ok, "sat_train_param_grads: finalize job table overflow");
   if (f.blocks > 0) {
+    SAT_PROF(6, st);
     param_grads_finalize_kernel<<<f.blocks, 256, 0, st>>>(f.t, b.gscale);
+    SAT_PROF(6, st);
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
   }
+  SAT_PROF(7, st);
   return 0;
 }
 

@@ -68,6 +68,26 @@ except Exception:  # pragma: no cover - exercised in this image
         def optimizers(self):
             return getattr(self, "_optimizer", None)
 
+        def freeze(self):
+            for p in self.parameters():
+                p.requires_grad = False
+            self.eval()
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **overrides):
+            """Loads a PyTorch-Lightning checkpoint file (what `SAT.load_from_checkpoint` does in evaluate.ipynb cell 2,
+            visualize.ipynb cell 1, temperature_scaling.py:17): a torch-pickled dict with `hyper_parameters` (the
+            constructor kwargs captured by save_hyperparameters) and `state_dict`."""
+            ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+            hp = dict(ckpt.get("hyper_parameters", ckpt.get("hparams", {})))
+            hp.update(overrides)
+            hp["pretrained"] = False                      # the weights come from the checkpoint, not from a download
+            model = cls(**hp)
+            model.load_state_dict(ckpt["state_dict"], strict=strict)
+            model.current_epoch = int(ckpt.get("epoch", 0))
+            model.global_step = int(ckpt.get("global_step", 0))
+            return model
+
 
 def _hp(args, name, default=None):
     try:
@@ -368,7 +388,8 @@ class SAT(_Base):
         for k, v in (("decoder_layers", 1), ("dropout", 0.0), ("embedding_dropout", 0.0), ("label_smoothing", 0.0),
                      ("weight_tying", False), ("deep_output", False), ("embed_norm", None), ("pretrained_embedding", None),
                      ("att_gamma", 1.0), ("decoder_tf", None), ("encoder_size", None), ("precision", "fp32"),
-                     ("encoder_finetune_after", -1), ("lr_warmup_steps", 0)):
+                     ("encoder_finetune_after", -1), ("lr_warmup_steps", 0), ("scheduler", None), ("val_beamk", 3), ("val_max_len", 32),
+                     ("save_monitor", None), ("early_stop_monitor", None), ("plateau_monitor", None)):
             if k not in hp:
                 hp[k] = v
         assert 0 <= hp.label_smoothing < (hp.vocab_size - 1) / hp.vocab_size
@@ -532,7 +553,110 @@ class SAT(_Base):
         if logger is not None and getattr(logger, "experiment", None) is not None:
             for k, v in metrics.items():
                 logger.experiment.add_scalar("{}/train".format(k), float(v), global_step=self.global_step)
+        self._step_lr_schedule()
         return metrics
+
+    def _trainer_step(self):
+        tr = getattr(self, "trainer", None)
+        return int(getattr(tr, "global_step", self.global_step)) if tr is not None else int(self.global_step)
+
+    def _step_lr_schedule(self):
+        """learning-rate warm-up and the schedulers that step every batch (model.py:608-617; host-side)."""
+        opt = self.optimizers() if callable(getattr(self, "optimizers", None)) else None
+        if opt is None or self.opt_init_lr is None:
+            return
+        step, warm = self._trainer_step(), int(self.hparams.lr_warmup_steps or 0)
+        if step < warm:
+            lr_scale = min(1, float(step + 1) / warm)
+            for pg, init_lr in zip(opt.param_groups, self.opt_init_lr):
+                pg["lr"] = lr_scale * init_lr
+        elif step > 0 and type(self.scheduler) in (torch.optim.lr_scheduler.CosineAnnealingWarmRestarts, torch.optim.lr_scheduler.OneCycleLR):
+            self.scheduler.step()
+
+    def training_epoch_end(self, outputs):
+        """epoch means to the logger, learning rate, per-epoch schedulers (model.py:621-635)."""
+        logger = getattr(self, "logger", None)
+        exp = getattr(logger, "experiment", None) if logger is not None else None
+        if outputs and exp is not None:
+            for k in outputs[0].keys():
+                vals = [float(x[k]) for x in outputs]
+                exp.add_scalar("{}/train_epoch".format(k), sum(vals) / len(vals) if vals else 0, global_step=self.current_epoch + 1)
+            opt = self.optimizers()
+            if opt is not None:
+                exp.add_scalar("Learning Rate", opt.param_groups[0]["lr"], global_step=self.current_epoch + 1)
+        if type(self.scheduler) in (torch.optim.lr_scheduler.MultiStepLR, torch.optim.lr_scheduler.ExponentialLR):
+            self.scheduler.step()
+
+    # ---- validation (model.py:646-718) -----------------------------------------------------------
+    def score_captions(self, captions, encoded_captions, lengths, perplexities=None):
+        """corpus BLEU-1..4 / GLEU of the generated captions against the references and the best cosine similarity of
+        mean word embeddings (model.py:646-682).  BLEU / GLEU: sat_b200/metrics.py (nltk is not needed); the embedding
+        means are batched on the device instead of one small launch per reference."""
+        from . import metrics as M
+        enc = encoded_captions.tolist()
+        lens = lengths.tolist() if torch.is_tensor(lengths) else lengths
+        references = [[c[1:l] for c, l in zip(refs, lens[i])] for i, refs in enumerate(enc)]
+        out = {"bleu1": M.corpus_bleu(references, captions, weights=(1, 0, 0, 0)),
+               "bleu2": M.corpus_bleu(references, captions, weights=(0.5, 0.5, 0, 0)),
+               "bleu3": M.corpus_bleu(references, captions, weights=(0.33, 0.33, 0.33, 0)),
+               "bleu4": M.corpus_bleu(references, captions, weights=(0.25, 0.25, 0.25, 0.25))}
+        gleu = M.corpus_gleu(references, captions)
+        W = self.embedding.weight.detach()
+        dev = W.device
+        with torch.no_grad():
+            def mean_embed(seqs):                       # [n, E]: mean embedding of each id list (nan for an empty one, like .mean(0))
+                n = len(seqs)
+                mx = max(1, max((len(q) for q in seqs), default=1))
+                ids = torch.zeros(n, mx, dtype=torch.long)
+                msk = torch.zeros(n, mx)
+                for i, q in enumerate(seqs):
+                    if len(q):
+                        ids[i, :len(q)] = torch.as_tensor(q, dtype=torch.long)
+                        msk[i, :len(q)] = 1
+                ids, msk = ids.to(dev), msk.to(dev)
+                return (W[ids].float() * msk.unsqueeze(-1)).sum(1) / msk.sum(1, keepdim=True)
+            cv = mean_embed(list(captions))                                         # [B, E]
+            flat = [r for refs in references for r in refs]
+            rv = mean_embed(flat).reshape(len(references), -1, W.shape[1])         # [B, ncap, E]
+            cos = torch.nn.functional.cosine_similarity(rv, cv.unsqueeze(1), dim=2)
+            cosine_similarity = cos.max(dim=1).values.mean()
+        out["cosine_similarity"] = cosine_similarity.item()
+        out["gleu"] = gleu
+        if type(perplexities) == list:
+            out["perplexity"] = sum(perplexities) / len(perplexities)
+        return out
+
+    def val_batch(self, batch, beamk=3, max_gen_length=32, temperature=0.5, sample_method="beam", sample_topk=3, decoder_noise=None,
+                  rescore_method=None, rescore_reward=0.5):
+        img, encoded_captions, lengths = batch
+        captions, scores, alphas, perplexities = self.caption(img, beamk, max_gen_length, temperature, sample_method, sample_topk,
+                                                              decoder_noise, rescore_method, rescore_reward, return_all=False)
+        return self.score_captions(captions, encoded_captions, lengths, perplexities)
+
+    def validation_step(self, batch, batch_idx):
+        return self.val_batch(batch, beamk=self.hparams.val_beamk, max_gen_length=self.hparams.val_max_len, temperature=1.0,
+                              rescore_method="LN")
+
+    def validation_epoch_end(self, outputs):
+        hp = self.hparams
+        logger = getattr(self, "logger", None)
+        exp = getattr(logger, "experiment", None) if logger is not None else None
+        plateau_val = None
+        for k in (outputs[0].keys() if outputs else []):
+            vals = [x[k] for x in outputs]
+            try:
+                val = sum(vals) / len(vals)
+            except Exception:
+                val = 0
+            if self.current_epoch != 0 and exp is not None:
+                exp.add_scalar("{}/val_epoch".format(k), val, global_step=self.current_epoch + 1)
+            if k == hp.save_monitor or k == hp.early_stop_monitor:
+                self.log(k, val)
+            if k == hp.plateau_monitor:
+                plateau_val = val
+        if self._trainer_step() >= int(hp.lr_warmup_steps or 0) and type(self.scheduler) is torch.optim.lr_scheduler.ReduceLROnPlateau \
+                and plateau_val is not None:
+            self.scheduler.step(plateau_val)
 
     # ---- inference (model.py:214-472) ---------------------------------------------------------
     @torch.no_grad()
@@ -611,6 +735,9 @@ class SAT(_Base):
         params = groups([self.init_lstm, self.lstm, self.attention, self.beta, self.output], wd, lr)
         if _hp(hp, "embedding_lr", lr) > 0 and not hp.weight_tying:
             params += [{"params": self.embedding.parameters(), "lr": _hp(hp, "embedding_lr", lr), "weight_decay": 0.0}]
+        # the reference adds the encoder group when encoder_finetune_after > 0 and encoder_lr > 0 (model.py:744); a trunk that
+        # trains from scratch (pretrained=False: every parameter requires grad, model.py:23-25) is included as well, otherwise
+        # its gradients would be computed and never applied
         if _hp(hp, "encoder_lr", 0.0) > 0 and (_hp(hp, "encoder_finetune_after", -1) > 0 or not hp.pretrained):
             params += groups([self.encoder], wd, hp.encoder_lr)
         opt = _hp(hp, "opt", "adam")
@@ -622,4 +749,34 @@ class SAT(_Base):
             optimizer = torch.optim.Adam(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)))
         self.opt_init_lr = [pg["lr"] for pg in optimizer.param_groups]
         self._optimizer = optimizer
+        self.scheduler = self._build_scheduler(optimizer)
         return optimizer
+
+    def _build_scheduler(self, optimizer):
+        """the five schedules of model.py:765-815 on stock torch schedulers"""
+        hp = self.hparams
+        S = torch.optim.lr_scheduler
+        kind = _hp(hp, "scheduler", None)
+        if kind == "step":
+            return S.MultiStepLR(optimizer, milestones=hp.milestones, gamma=hp.lr_gamma)
+        if kind == "plateau":
+            return S.ReduceLROnPlateau(optimizer, mode="max", factor=hp.lr_gamma, patience=hp.plateau_patience, min_lr=hp.min_lr)
+        if kind == "exp":
+            return S.ExponentialLR(optimizer, gamma=hp.lr_gamma)
+        if kind == "cosine":
+            # restarts sized so that the last cycle ends with the run (model.py:785-805)
+            adj_steps = hp.epochs * hp.train_loader_len - hp.lr_warmup_steps
+            t0, tm, acc = hp.cosine_iterations, hp.cosine_multi, _hp(hp, "accumulate", 1)
+            if tm != 1:
+                restarts = math.floor(math.log(1 - (adj_steps * (1 - tm) / t0)) / math.log(tm))
+                t0 = adj_steps + acc if restarts == 0 else math.ceil((adj_steps + acc) / ((1 - tm ** restarts) / (1 - tm)))
+            else:
+                restarts = math.floor(adj_steps / t0)
+                t0 = adj_steps + acc if restarts == 0 else math.ceil((adj_steps + acc) / restarts)
+            return S.CosineAnnealingWarmRestarts(optimizer, T_0=int(t0), T_mult=int(tm), eta_min=hp.min_lr)
+        if kind == "one_cycle":
+            hp.lr_warmup_steps = 0
+            return S.OneCycleLR(optimizer, self.opt_init_lr, epochs=hp.epochs, steps_per_epoch=hp.train_loader_len,
+                                pct_start=hp.one_cycle_pct, cycle_momentum=False, div_factor=hp.one_cycle_div,
+                                final_div_factor=hp.one_cycle_fdiv)
+        return None
