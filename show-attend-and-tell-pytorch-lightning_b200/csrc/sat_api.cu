@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "sat_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -23,6 +25,32 @@ void sat_prof_mark(cudaStream_t st) {
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, st);
   g_prof_events.push_back(e);
+}
+
+// L2 persistence carve-out, opt-in with SAT_ATT_L2=1.  Measured on B200 at BASELINE configs[1] (annotations 51 MB of the
+// 126 MB L2, pinned for the time loop): attention forward 20.6 vs 20.3 us, backward 25.1 vs 24.1 us, decoder step 2.30 vs
+// 2.20 ms WITH vs without the window -- the kernels are latency-bound at this batch, not DRAM-bound, and the persisting
+// carve-out takes L2 away from everything else.  Off by default.
+size_t sat_l2_persist_limit() {
+  static size_t limit[64];
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  dev &= 63;
+  if (!done[dev]) {
+    done[dev] = true;
+    limit[dev] = 0;
+    const char* e = getenv("SAT_ATT_L2");
+    if (e != nullptr && atoi(e) != 0) {
+      int maxp = 0, maxw = 0;
+      cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      if (maxp > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp) == cudaSuccess)
+        limit[dev] = (size_t)(maxp < maxw || maxw == 0 ? maxp : maxw);
+      cudaGetLastError();
+    }
+  }
+  return limit[dev];
 }
 
 extern "C" {

@@ -64,9 +64,9 @@ __global__ void __launch_bounds__(256) ncap_sum_kernel(const TI* __restrict__ in
 
 // ---- embedding gradient: dEmb[v, :] = sum over the rows m with tok[m] == v of dXe[m, :] ------------------------------
 // A CTA owns EG_TPC consecutive vocabulary entries.  The token list is staged in shared memory chunk by chunk; for every
-// owned word the CTA's 8 warps split the chunk's rows into 8 contiguous ranges, each warp walks its range 32 token ids at
-// a time (ballot) and adds the matching rows of dXe in ascending row order, four rows in flight (independent loads, ordered
-// adds); the 8 partial sums are added in warp order at the end.  The order of additions is fixed by (row, warp) alone: no
+// owned word the chunk's 32-row windows are dealt round-robin to the CTA's 8 warps; a warp tests its window with a ballot
+// and adds the matching rows of dXe in ascending row order, four rows in flight (independent loads, ordered adds); the 8
+// partial sums are added in warp order at the end.  The order of additions is fixed by (row, warp) alone: no
 // atomics, no sort, bit-identical from run to run (index_add_ with float atomics is not).  A frequent word (<START> feeds
 // every caption's first step) is spread over 8 warps x 4 loads in flight instead of one serial chain.  The <PAD> row stays
 // zero (nn.Embedding(padding_idx), model.py:162).
@@ -89,13 +89,14 @@ embed_grad_kernel(const int32_t* __restrict__ tok, const float* __restrict__ dXe
       __syncthreads();
       for (int i = threadIdx.x; i < nm; i += 256) s_tok[i] = tok[mb + i];
       __syncthreads();
-      const int wb = warp * (EG_CHUNK / 8), we = min(nm, wb + EG_CHUNK / 8);
 #pragma unroll
       for (int k = 0; k < EG_TPC; ++k) {
         const int v = v0 + k;
         if (v >= V0 || v == pad_idx) continue;
-        for (int i = wb; i < we; i += 32) {
-          const int t = (i + lane) < we ? s_tok[i + lane] : -1;
+        // 32-row windows are dealt round-robin to the warps: rows are time-major, so the rows that feed one word cluster
+        // (every caption's first step feeds <START>: B consecutive rows) and contiguous ranges would leave them to one warp
+        for (int i = warp * 32; i < nm; i += 8 * 32) {
+          const int t = (i + lane) < nm ? s_tok[i + lane] : -1;
           unsigned hit = __ballot_sync(0xffffffffu, t == v);
           while (hit) {
             int r[4];

@@ -77,6 +77,15 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
 
   // ---- recurrence ------------------------------------------------------------------------------
   const float scale = (float)(1.0 / sqrt((double)L));
+  // The attention kernels re-read the same annotations at every step: when they fit the persisting part of the L2 they are
+  // pinned there for the time loop (read from HBM once per step sequence instead of T times)
+  struct L2Scope {
+    L2Scope(const void* p, size_t n) {
+      const size_t lim = sat_l2_persist_limit();
+      if (lim > 0 && n > 0) { sat_l2_window().ptr = p; sat_l2_window().bytes = n < lim ? n : lim; sat_l2_window().hit_ratio = n <= lim ? 1.0f : (float)lim / (float)n; }
+    }
+    ~L2Scope() { sat_l2_window().ptr = nullptr; sat_l2_window().bytes = 0; }
+  } l2scope(b.ann, sizeof(TS) * (size_t)Bi * L * D);
   for (int t = 0; t < T; ++t) {
     if (b.sampled != nullptr && t > 0 && b.sampled[t]) {
       // scheduled sampling (model.py:518-523): this step's input word is argmax_v logits[t-1]; compute the output of

@@ -52,6 +52,13 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   const int att_threads = att_pipe ? ATTP_BWD_CW * 32 + 32 : ATT_THREADS;
   if (att_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(att_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
 
+  struct L2Scope {
+    L2Scope(const void* p, size_t n) {
+      const size_t lim = sat_l2_persist_limit();
+      if (lim > 0 && n > 0) { sat_l2_window().ptr = p; sat_l2_window().bytes = n < lim ? n : lim; sat_l2_window().hit_ratio = n <= lim ? 1.0f : (float)lim / (float)n; }
+    }
+    ~L2Scope() { sat_l2_window().ptr = nullptr; sat_l2_window().bytes = 0; }
+  } l2scope(b.ann, sizeof(TS) * (size_t)Bi * L * D);
   for (int t = T - 1; t >= 0; --t) {
     TS* DY_t = (TS*)b.DY + (int64_t)t * B * NH3;
     const float* dHZ_t = b.dHZ + (int64_t)t * B * (H + D);

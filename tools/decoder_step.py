@@ -16,6 +16,7 @@ ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--no-tc", action="store_true")
 ap.add_argument("--decode", type=int, default=0, help="run batched decode with this beam width instead of training")
 ap.add_argument("--dims", type=str, default="", help="D,A,E,H,V,T,L override, e.g. 2048,128,256,1024,6400,20,196 (configs[2])")
+ap.add_argument("--rand-start", action="store_true", help="random word instead of <START> in column 0 (no heavy word)")
 ap.add_argument("--no-fuse-ce", action="store_true", help="unfused vocabulary GEMM + ce_rows_kernel")
 ap.add_argument("--profile", type=int, default=0, help="also report the in-situ per-launch time of kernel kind 1 (att fwd) / 2 (att bwd) / 3 (vocab GEMM)")
 args = ap.parse_args()
@@ -33,7 +34,8 @@ g = torch.Generator(device="cuda").manual_seed(0)
 B = args.batch
 ann = torch.randn(B, L, D, device="cuda", generator=g).to(dtype)
 caps = torch.randint(1, V - 3, (B, T + 1), device="cuda", generator=g)
-caps[:, 0] = V - 2
+if not args.rand_start:
+    caps[:, 0] = V - 2
 lens = torch.full((B,), T, device="cuda")
 use_tc = (not args.fp32) and (not args.no_tc)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
