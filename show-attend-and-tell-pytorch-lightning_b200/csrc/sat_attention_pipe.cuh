@@ -1133,6 +1133,289 @@ attention_step_fwd_group_tcr_kernel(const bf16* __restrict__ ann, const bf16* __
   }
 }
 
+// =============================================================================================
+// K1 pair: one caption row per 2-CTA CLUSTER (bf16, one row per image, D <= 512).  At BASELINE configs[1] the per-row kernel
+// above is a single wave of 256 CTAs whose run time is the critical path of ONE row (prologue -> scores -> softmax -> context
+// -> gate): latency-, not bandwidth-bound.  Here two CTAs share a row and halve that path:
+//   * scores: CTA r streams the P rows of its half of the locations and computes their scores; every score is written to
+//     both CTAs' shared memory (local store + st.shared::cluster to the peer), completion is signalled with a remote
+//     mbarrier arrive, so each CTA ends up with all L scores and runs the (cheap) softmax redundantly;
+//   * context: CTA r owns the column half [r*D/2, (r+1)*D/2) of z for ALL locations: the annotation tile is streamed as
+//     32-row x D/2-column boxes by 2-D TMA; no reduction across the pair is needed, each CTA gates and stores its half.
+// 4 CTAs (36 warps) per SM instead of 2 (18): twice the warps hide the same latencies.  Same arithmetic as the per-row
+// kernel up to the order of the softmax / context sums.
+// =============================================================================================
+constexpr int ATTC_CW = 8;          // consumer warps
+constexpr int ATTC_NST = 3;         // 3 x 16 KB ring -> ~50 KB per CTA, 4 CTAs per SM
+constexpr int ATTC_BOX_ROWS = 32;
+
+struct AttPairSmem {
+  uint64_t full[ATTC_NST];
+  uint64_t empty[ATTC_NST];
+  uint64_t xbar;                    // the peer's scores have landed (remote arrive, one per consumer warp of the peer)
+  float red_a[ATTC_CW];
+  float red_b[ATTC_CW];
+};
+
+__device__ __forceinline__ uint32_t sat_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t sat_mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void sat_st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sat_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sat_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sat_mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void sat_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = sat_smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <bool kExact, int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, 4)
+attention_step_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_ann, const bf16* __restrict__ P, const float* __restrict__ wf,
+                               const float* __restrict__ hp, int64_t ldhp, const int32_t* __restrict__ lens, int t, int ncap, int L,
+                               int D, int A, float scale, float* __restrict__ alpha, int64_t ld_alpha, float* __restrict__ qsave,
+                               bf16* __restrict__ z, bf16* __restrict__ gz, bf16* __restrict__ beta, int64_t ld_z, int lens_dyn) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  typedef bf16 T;
+  constexpr int CONSUMERS = CW * 32, THREADS = CW * 32 + 32;
+  SAT_PDL_TRIGGER();
+  if (lens_dyn) SAT_PDL_WAIT();         // decode: lens (= alive) is rewritten every step by beam_update_kernel
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = sat_cluster_ctarank();
+  const int b = blockIdx.x >> 1;
+  const int Dh = D >> 1, d0 = (int)rank * Dh;
+  AttPairSmem* hd = reinterpret_cast<AttPairSmem*>(smem_raw);
+  const int L4 = (L + 3) & ~3;
+  float* e = reinterpret_cast<float*>(smem_raw + sizeof(AttPairSmem));      // [L4] all scores, then alpha
+  const uint32_t stage_off = (uint32_t)((sizeof(AttPairSmem) + sizeof(float) * (size_t)L4 + 127) & ~(size_t)127);
+  uint8_t* stages = smem_raw + stage_off;
+  float* red = reinterpret_cast<float*>(stages);                             // [CW][Dh], after the ring is drained
+
+  const bool active = lens == nullptr || t < lens[b];                        // the same value in both CTAs of the pair
+  if (!active) {                        // no cluster traffic at all for a finished row: both CTAs just write their zeros
+    SAT_PDL_WAIT();
+    float* alpha_b = alpha + (int64_t)b * ld_alpha;
+    if (rank == 0) {
+      for (int l = tid; l < L; l += THREADS) alpha_b[l] = 0.0f;
+      if (qsave) for (int a = tid; a < A; a += THREADS) qsave[(int64_t)b * A + a] = 0.0f;
+    }
+    for (int d = tid; d < Dh; d += THREADS) {
+      z[(int64_t)b * ld_z + d0 + d] = from_f<T>(0.f);
+      gz[(int64_t)b * ld_z + d0 + d] = from_f<T>(0.f);
+      if (beta) beta[(int64_t)b * ld_z + d0 + d] = from_f<T>(0.f);
+    }
+    return;
+  }
+  const int img = b / ncap;
+  const int Ls = min(L, (((L + 1) >> 1) + 3) & ~3);      // locations [0, Ls) belong to CTA 0, [Ls, L) to CTA 1
+  const int l0 = rank ? Ls : 0, l1 = rank ? L : Ls, nl = l1 - l0;
+  const int RCP = ATTP_STAGE_BYTES / (A * (int)sizeof(T));                   // P rows per stage
+  const int nP = (nl + RCP - 1) / RCP, nA = (L + ATTC_BOX_ROWS - 1) / ATTC_BOX_ROWS;
+  const uint32_t box_bytes = (uint32_t)(ATTC_BOX_ROWS * Dh * (int)sizeof(T));
+
+  if (tid == 0) {
+    for (int i = 0; i < ATTC_NST; ++i) {
+      sat_mbar_init(&hd->full[i], 1);
+      sat_mbar_init(&hd->empty[i], CW);
+    }
+    sat_mbar_init(&hd->xbar, CW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  sat_cluster_arrive();                 // both CTAs are running and their barriers exist before any remote access (waited below)
+
+  if (warp == CW) {
+    // ===== producer: the CTA's P rows (1-D bulk copies), then the annotation boxes of its column half (2-D TMA) =====
+    if (lane == 0) {
+      const T* Pb = P + ((int64_t)img * L + l0) * A;
+      for (int i = 0; i < nP + nA; ++i) {
+        const int st = i % ATTC_NST;
+        const uint32_t ph = (uint32_t)(i / ATTC_NST) & 1u;
+        sat_mbar_wait(&hd->empty[st], ph ^ 1u);
+        uint8_t* dst = stages + (size_t)st * ATTP_STAGE_BYTES;
+        if (i < nP) {
+          const int r0 = i * RCP, rows = min(RCP, nl - r0);
+          const uint32_t bytes = (uint32_t)(rows * A * (int)sizeof(T));
+          sat_mbar_expect_tx(&hd->full[st], bytes);
+          sat_bulk_g2s(dst, Pb + (int64_t)r0 * A, bytes, &hd->full[st]);
+        } else {
+          sat_mbar_expect_tx(&hd->full[st], box_bytes);
+          tc::tma_load_2d(&tm_ann, &hd->full[st], dst, d0, img * L + (i - nP) * ATTC_BOX_ROWS);
+        }
+      }
+    }
+    __syncwarp();
+    sat_cluster_wait();                 // pairs with the arrive above (every thread arrives and waits exactly once)
+    return;
+  }
+
+  // ===== consumers =====
+  SAT_PDL_WAIT();
+  const float* hp_b = hp + (int64_t)b * ldhp;
+  float qreg[ATTP_KA][4], wreg[ATTP_KA][4];
+#pragma unroll
+  for (int k = 0; k < ATTP_KA; ++k) {
+    const int a = lane * 4 + 128 * k;
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = q4;
+    if (a < A) {
+      q4 = *reinterpret_cast<const float4*>(hp_b + a);
+      w4 = *reinterpret_cast<const float4*>(wf + a);
+      if (qsave && rank == 0 && warp == 0) *reinterpret_cast<float4*>(qsave + (int64_t)b * A + a) = q4;
+    }
+    qreg[k][0] = q4.x; qreg[k][1] = q4.y; qreg[k][2] = q4.z; qreg[k][3] = q4.w;
+    wreg[k][0] = w4.x; wreg[k][1] = w4.y; wreg[k][2] = w4.z; wreg[k][3] = w4.w;
+  }
+  const float bpre = tid < Dh ? hp_b[A + d0 + tid] : 0.0f;                  // beta_pre of the column this thread finalises
+  sat_cluster_wait();                                                       // the peer's shared memory and barriers are live
+  const uint32_t e_remote = sat_mapa(sat_smem_u32(e), rank ^ 1u);
+  int it = 0;
+  for (int i = 0; i < nP; ++i, ++it) {
+    const int st = it % ATTC_NST;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTC_NST) & 1u);
+    const T* Ps = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
+    const int r0 = i * RCP, rows = min(RCP, nl - r0);
+    for (int lr = warp * 4; lr < rows; lr += CW * 4) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < ATTP_KA; ++k) {
+        const int a = lane * 4 + 128 * k;
+        if (a < A) {
+          float4 p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            p[u] = (lr + u) < rows ? ld4(Ps + (size_t)(lr + u) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            s4[u] = fmaf(wreg[k][0], sat_tanh<kExact>(p[u].x + qreg[k][0]), s4[u]);
+            s4[u] = fmaf(wreg[k][1], sat_tanh<kExact>(p[u].y + qreg[k][1]), s4[u]);
+            s4[u] = fmaf(wreg[k][2], sat_tanh<kExact>(p[u].z + qreg[k][2]), s4[u]);
+            s4[u] = fmaf(wreg[k][3], sat_tanh<kExact>(p[u].w + qreg[k][3]), s4[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s4[u] += __shfl_xor_sync(0xffffffffu, s4[u], o);
+      }
+      if (lane < 4 && (lr + lane) < rows) {
+        const float sv = (lane == 0 ? s4[0] : (lane == 1 ? s4[1] : (lane == 2 ? s4[2] : s4[3]))) * scale;
+        const int l = l0 + r0 + lr + lane;
+        e[l] = sv;
+        sat_st_cluster_f32(e_remote + (uint32_t)l * 4u, sv);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  // this warp's scores are in both CTAs: tell the peer (release at cluster scope orders the remote stores before the arrive)
+  __syncwarp();
+  if (lane == 0) sat_mbar_arrive_remote(sat_mapa(sat_smem_u32(&hd->xbar), rank ^ 1u));
+  sat_named_bar(1, CONSUMERS);                                              // own half complete (local stores)
+  sat_mbar_wait_cluster(&hd->xbar, 0);                                      // the peer's half has landed
+  // softmax over all L locations (both CTAs compute it; it is ~L exps)
+  float mx = -INFINITY;
+  for (int l = tid; l < L; l += CONSUMERS) mx = fmaxf(mx, e[l]);
+  mx = warp_max(mx);
+  if (lane == 0) hd->red_a[warp] = mx;
+  sat_named_bar(1, CONSUMERS);
+  mx = hd->red_a[0];
+#pragma unroll
+  for (int w2 = 1; w2 < CW; ++w2) mx = fmaxf(mx, hd->red_a[w2]);
+  float sum = 0.0f;
+  for (int l = tid; l < L; l += CONSUMERS) {
+    const float pe = sat_exp<kExact>(e[l] - mx);
+    e[l] = pe;
+    sum += pe;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) hd->red_b[warp] = sum;
+  sat_named_bar(1, CONSUMERS);
+  sum = 0.0f;
+#pragma unroll
+  for (int w2 = 0; w2 < CW; ++w2) sum += hd->red_b[w2];
+  float* alpha_b = alpha + (int64_t)b * ld_alpha;
+  for (int l = tid; l < L; l += CONSUMERS) {
+    const float al = e[l] / sum;
+    e[l] = al;
+    if (l >= l0 && l < l1) alpha_b[l] = al;                                 // each CTA stores the weights of its own locations
+  }
+  sat_named_bar(1, CONSUMERS);
+
+  // context for the columns [d0, d0 + Dh): a warp takes rows w, w + CW, .. of every 32-row box, a lane one 16-byte vector
+  constexpr int VN = 8;
+  const int NV = Dh / VN;                                                   // <= 32
+  float acc[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
+  const bool worker = lane < NV;
+  for (int j = 0; j < nA; ++j, ++it) {
+    const int st = it % ATTC_NST;
+    sat_mbar_wait(&hd->full[st], (uint32_t)(it / ATTC_NST) & 1u);
+    const T* As = reinterpret_cast<const T*>(stages + (size_t)st * ATTP_STAGE_BYTES);
+    const int r0 = j * ATTC_BOX_ROWS, rows = min(ATTC_BOX_ROWS, L - r0);
+    if (worker) {
+      float v[ATTC_BOX_ROWS / CW][VN];
+      float al[ATTC_BOX_ROWS / CW];
+#pragma unroll
+      for (int u = 0; u < ATTC_BOX_ROWS / CW; ++u) {
+        const int rr = warp + u * CW;                                       // rows past the image's last location carry weight 0
+        al[u] = rr < rows ? e[r0 + rr] : 0.0f;
+        Vec16<T>::load_shared(As + (size_t)rr * Dh + lane * VN, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < ATTC_BOX_ROWS / CW; ++u) {
+#pragma unroll
+        for (int i2 = 0; i2 < VN; ++i2) acc[i2] = fmaf(al[u], v[u][i2], acc[i2]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sat_mbar_arrive(&hd->empty[st]);
+  }
+  sat_named_bar(1, CONSUMERS);          // the ring is drained: red[] may overwrite it
+  if (worker) {
+#pragma unroll
+    for (int i = 0; i < VN; ++i) red[warp * Dh + lane * VN + i] = acc[i];
+  }
+  sat_named_bar(1, CONSUMERS);
+  if (tid < Dh) {
+    float zs = 0.0f;
+#pragma unroll
+    for (int w2 = 0; w2 < CW; ++w2) zs += red[w2 * Dh + tid];
+    const float bt = sat_sigmoid<kExact>(bpre);
+    z[(int64_t)b * ld_z + d0 + tid] = from_f<T>(zs);
+    gz[(int64_t)b * ld_z + d0 + tid] = from_f<T>(bt * zs);
+    if (beta) beta[(int64_t)b * ld_z + d0 + tid] = from_f<T>(bt);
+  }
+}
+
+static inline size_t attention_fwd_pair_smem(int L) {
+  return ((sizeof(AttPairSmem) + sizeof(float) * (size_t)((L + 3) & ~3) + 127) & ~(size_t)127) + 128 + (size_t)ATTC_NST * ATTP_STAGE_BYTES;
+}
+
 // stage geometry of the row-streamed kernel: 8 or 16 padded rows per stage, as many stages as fit ~97 KB (<= ATTP_NST)
 struct AttTcrGeom { int rows, nst, stage_bytes; size_t smem; };
 static inline AttTcrGeom attention_fwd_group_tcr_geom(int L, int D, int A) {
@@ -1186,6 +1469,37 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
     SAT_COUNT_LAUNCH();
     SAT_LAUNCH_OK();
     return 0;
+  }
+  // one row per image, bf16, small grids: a 2-CTA cluster per row halves the row's critical path (SAT_ATT_PAIR=0/1 forces
+  // the choice; by default up to 3 rows per SM, where the per-row kernel is a single latency-bound wave)
+  if constexpr (std::is_same<T, bf16>::value && !kExact) {
+    // Measured on B200 at BASELINE configs[1] (B = 256): 18.1-18.6 us (ncu) / 20.3 us (in situ) against 18.6 / 20.1 us for the
+    // per-row kernel -- halving the row's critical path changes nothing, the launch is bounded by DRAM streaming plus fixed
+    // launch / fill / drain costs, not by the path of one row.  Kept as an opt-in variant (SAT_ATT_PAIR=1), off by default.
+    static const int pair_mode = getenv("SAT_ATT_PAIR") ? atoi(getenv("SAT_ATT_PAIR")) : 0;
+    const int Dh = D / 2;
+    const bool pair_fit = ncap == 1 && D % 16 == 0 && Dh <= 256 && Dh * 2 * ATTC_BOX_ROWS <= ATTP_STAGE_BYTES && A <= 128 * ATTP_KA && A % 4 == 0 &&
+                          L >= 8 && ldhp % 4 == 0 && (reinterpret_cast<uintptr_t>(hp) & 15) == 0;
+    if (pair_fit && (pair_mode == 1 || (pair_mode != 0 && rows <= 3 * 148))) {
+      static thread_local CUtensorMap tmp;
+      static thread_local const void* tmp_ptr = nullptr;
+      static thread_local int64_t tmp_rows = 0, tmp_d = 0;
+      static thread_local int tmp_dev = -1;
+      const int64_t n_rows = (int64_t)rows * L;            // ncap == 1: one image per row
+      int dev_now = 0;
+      SAT_CUDA(cudaGetDevice(&dev_now));
+      if (tmp_ptr != (const void*)ann || tmp_rows != n_rows || tmp_d != D || tmp_dev != dev_now) {
+        SAT_TRY(tc::make_map_plain(&tmp, ann, n_rows, D, D, Dh, ATTC_BOX_ROWS));
+        tmp_ptr = ann; tmp_rows = n_rows; tmp_d = D; tmp_dev = dev_now;
+      }
+      auto kern = attention_step_fwd_pair_kernel<kExact, ATTC_CW>;
+      const size_t smem = attention_fwd_pair_smem(L);
+      SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SAT_CUDA(sat_launch_cluster_pdl(kern, dim3(2 * rows), dim3(ATTC_CW * 32 + 32), smem, 2, st, tmp, P, wf, hp, ldhp, lens, t, ncap, L, D, A,
+                                      scale, alpha, ld_alpha, qsave, z, gz, beta, ld_z, lens_dyn));
+      SAT_COUNT_LAUNCH();
+      return 0;
+    }
   }
   // several caption rows per image (beams / captions): one CTA per image streams the tiles once for all of them when
   // the per-image tile is large enough for the shared stream to pay (SAT_ATT_GROUP=0/1 forces the choice)

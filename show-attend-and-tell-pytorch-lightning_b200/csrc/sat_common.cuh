@@ -109,6 +109,32 @@ static inline cudaError_t sat_launch_pdl(Kern kern, dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// same, for kernels that run as thread-block clusters of `cluster_x` CTAs along x (distributed shared memory between the CTAs)
+template <typename Kern, typename... Args>
+static inline cudaError_t sat_launch_cluster_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, unsigned cluster_x, cudaStream_t st,
+                                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = cluster_x;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (sat_pdl_allowed()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ---- typed loads / stores ------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

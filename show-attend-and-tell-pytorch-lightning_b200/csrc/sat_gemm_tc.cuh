@@ -33,6 +33,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
@@ -266,7 +269,7 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
       mbar_wait(&s.tmem_full, 0);
       tcgen05_fence_after();
       static_assert((size_t)BM * (BN / 2 + 8) * sizeof(float) <= sizeof(s.a) + sizeof(s.w), "row-owner scratch must fit the ring");
-      epi.template run<BN>(reinterpret_cast<uint8_t*>(&s.a[0][0]), s.aux, tmem, nkb > 0, warp, lane, m0, n0, M, N);
+      epi.template run<BN, EPI_WARPS>(reinterpret_cast<uint8_t*>(&s.a[0][0]), s.aux, tmem, nkb > 0, warp, lane, m0, n0, M, N, (int)blockIdx.x);
     } else {
       mbar_wait(&s.tmem_full, 0);
       tcgen05_fence_after();
@@ -278,6 +281,148 @@ gemm_tn_tc_kernel(const __grid_constant__ Maps maps, int M, int N, int k0, int k
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+  }
+}
+
+// =============================================================================================
+// Persistent variant for row-owner epilogues (the vocabulary projection: M = T*B rows, N = V, only K = E <= 256 deep).  One
+// CTA per SM owns a CONTIGUOUS run of output tiles in m-major order (n fastest), so that
+//   * the A row block of the run (128 rows x K, <= 64 KB) is loaded ONCE and stays resident in shared memory while the W
+//     tiles stream through a 6-stage ring: half the L2 -> SM traffic of reloading both operands per tile (this GEMM is
+//     bound by that traffic, not by the tensor pipe: 2000 tiles x 128 KB per pass at BASELINE configs[1]);
+//   * TWO accumulator buffers in tensor memory let the MMA warp fill one while the 16 epilogue warps drain the other;
+//   * launch, barrier-init and TMEM-allocation latency is paid once per CTA instead of once per 128x128 tile.
+// =============================================================================================
+constexpr int PERS_WSTAGES = 6;
+constexpr int PERS_AKB = 4;                   // resident A: up to 4 k-blocks of 64 (K <= 256)
+constexpr int PERS_EPI_WARPS = 16;            // four per scheduler: the row-owner epilogues are chains of dependent ALU / MUFU ops
+constexpr int PERS_THREADS = 64 + PERS_EPI_WARPS * 32;
+struct SmemPers {
+  alignas(1024) bf16 a[PERS_AKB][BM * BK];
+  alignas(1024) bf16 w[PERS_WSTAGES][128 * BK];
+  alignas(1024) uint8_t scratch[BM * (128 / 2 + 8) * sizeof(float)];   // row-owner epilogue scratch (not aliased with the ring here): 36 KB
+  alignas(8) uint64_t full[PERS_WSTAGES];
+  uint64_t empty[PERS_WSTAGES];
+  uint64_t a_full, a_empty;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  alignas(16) float aux[AUX_FLOATS];
+};
+
+template <typename Epi>
+__global__ void __launch_bounds__(PERS_THREADS, 1)
+gemm_tn_tc_persistent_kernel(const __grid_constant__ Maps maps, int M, int N, int K, Epi epi) {
+  static_assert(is_row_owner<Epi>::value, "the persistent kernel runs row-owner epilogues");
+  constexpr int BN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  SmemPers& s = *reinterpret_cast<SmemPers*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + BK - 1) / BK;                                  // <= PERS_AKB (checked by the launcher)
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+  const int ntiles = tiles_n * tiles_m;
+  const int t0 = (int)(((long)ntiles * blockIdx.x) / gridDim.x), t1 = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+  constexpr uint32_t W_BYTES = BN * BK * sizeof(bf16), A_KB_BYTES = BM * BK * sizeof(bf16);
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PERS_WSTAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(&s.a_full, 1);
+    mbar_init(&s.a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      mbar_init(&s.tmem_empty[i], PERS_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+  }
+  if (warp == 1) {   // two accumulator buffers of BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, aload = 0;                        // W k-block counter across tiles, number of A loads so far
+      int cur_mb = -1;
+      for (int tile = t0; tile < t1; ++tile) {
+        const int mb = tile / tiles_n, n0 = (tile - mb * tiles_n) * BN;
+        if (mb != cur_mb) {                               // new row block: (re)load the resident A operand
+          mbar_wait(&s.a_empty, (aload & 1) ^ 1);         // every MMA that read the previous block has retired
+          mbar_expect_tx(&s.a_full, A_KB_BYTES * (uint32_t)nkb);
+          for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&maps.a[0], &s.a_full, s.a[kb], kb * BK, mb * BM);
+          ++aload;
+          cur_mb = mb;
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % PERS_WSTAGES;
+          const uint32_t ph = (it / PERS_WSTAGES) & 1;
+          mbar_wait(&s.empty[st], ph ^ 1);
+          mbar_expect_tx(&s.full[st], W_BYTES);
+          tma_load_2d(&maps.w, &s.full[st], s.w[st], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      uint32_t it = 0, lt = 0, aload = 0;
+      int cur_mb = -1;
+      for (int tile = t0; tile < t1; ++tile, ++lt) {
+        const int mb = tile / tiles_n;
+        if (mb != cur_mb) {
+          mbar_wait(&s.a_full, aload & 1);
+          ++aload;
+          cur_mb = mb;
+        }
+        const uint32_t buf = lt & 1;
+        mbar_wait(&s.tmem_empty[buf], ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this buffer (free at first use)
+        tcgen05_fence_after();
+        const uint32_t acc = tmem + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % PERS_WSTAGES;
+          const uint32_t ph = (it / PERS_WSTAGES) & 1;
+          mbar_wait(&s.full[st], ph);
+          tcgen05_fence_after();
+          const uint64_t ad = make_smem_desc(s.a[kb]), bd = make_smem_desc(s.w[st]);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) umma(acc, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+          umma_commit(&s.empty[st]);
+        }
+        umma_commit(&s.tmem_full[buf]);
+        if (tile + 1 >= t1 || (tile + 1) / tiles_n != mb) umma_commit(&s.a_empty);   // last tile of this row block
+      }
+    }
+  } else {
+    uint32_t lt = 0;
+    for (int tile = t0; tile < t1; ++tile, ++lt) {
+      const int mb = tile / tiles_n, nt = tile - mb * tiles_n;
+      const int m0 = mb * BM, n0 = nt * BN;
+      const uint32_t buf = lt & 1;
+      epi.prologue(s.aux, n0, N, warp, lane);
+      mbar_wait(&s.tmem_full[buf], (lt >> 1) & 1);
+      tcgen05_fence_after();
+      epi.template run<BN, PERS_EPI_WARPS>(s.scratch, s.aux, tmem + buf * BN, nkb > 0, warp, lane, m0, n0, M, N, nt);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&s.tmem_empty[buf]);          // this warp no longer reads the buffer
+      asm volatile("bar.sync 1, %0;" ::"n"(PERS_EPI_WARPS * 32) : "memory");   // scratch / aux are reused by the next tile
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN));
   }
 }
 
@@ -423,6 +568,22 @@ static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t k, 
   return 0;
 }
 
+// generic 2D bf16 tensor map of a row-major [rows, cols] buffer: box {box_cols, box_rows}, no swizzle, OOB -> 0
+static int make_map_plain(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  auto enc = get_encode();
+  SAT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SAT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (plain) failed (%d) rows=%lld cols=%lld box=%dx%d", (int)r, (long long)rows,
+              (long long)cols, box_cols, box_rows);
+  return 0;
+}
+
 static inline bool operands_ok(const GemmOperandA& A, const void* W, int64_t ldw) {
   if (A.nseg < 1 || A.nseg > 2) return false;
   for (int i = 0; i < A.nseg; ++i) {
@@ -491,6 +652,43 @@ static inline int pick_splitk(int M, int N, int ktot) {
   return s;
 }
 
+
+// persistent launcher (row-owner epilogues, single A segment of K <= 256, BN = 128)
+static inline bool persistent_ok(const GemmOperandA& A) { return A.nseg == 1 && A.k[0] <= PERS_AKB * BK; }
+
+template <typename Epi>
+static int launch_persistent(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const Epi& epi, cudaStream_t stream) {
+  Maps maps;
+  SAT_TRY(make_map(&maps.a[0], A.p[0], M, A.k[0], A.ld[0], BM));
+  maps.a[1] = maps.a[0];
+  SAT_TRY(make_map(&maps.w, W, N, A.k[0], ldw, 128));
+  auto kern = gemm_tn_tc_persistent_kernel<Epi>;
+  constexpr int smem = (int)sizeof(SmemPers) + 1024;
+  static bool attr_set[64] = {false};
+  static int n_sm[64] = {0};
+  int dev_now = 0;
+  SAT_CUDA(cudaGetDevice(&dev_now));
+  if (!attr_set[dev_now & 63]) {
+    SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SAT_CUDA(cudaDeviceGetAttribute(&n_sm[dev_now & 63], cudaDevAttrMultiProcessorCount, dev_now));
+    attr_set[dev_now & 63] = true;
+  }
+  const int ntiles = ((N + 127) / 128) * ((M + BM - 1) / BM);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ntiles < n_sm[dev_now & 63] ? ntiles : n_sm[dev_now & 63]);
+  cfg.blockDim = dim3(PERS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = sat_pdl_allowed() ? 1 : 0;
+  SAT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, M, N, A.k[0], epi));
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
+  return 0;
+}
 
 // ---- NT launchers ------------------------------------------------------------------------------------
 // 2D bf16 tensor map of a row-major [rows, cols] buffer read as {64 columns, BK rows} boxes (MN-major operand tiles)

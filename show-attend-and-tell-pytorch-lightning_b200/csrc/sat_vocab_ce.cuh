@@ -10,6 +10,8 @@
 // After tcgen05.ld a thread holds one accumulator row, so all of these reductions are thread-local; the two column halves
 // of a tile (two warps per TMEM lane quarter) are combined through the drained operand ring.
 #pragma once
+#include <stdlib.h>
+
 #include "sat_gemm_tc.cuh"
 
 namespace tc {
@@ -42,6 +44,7 @@ struct VocabArgs {
   const int32_t* alive;
   float inv_temp;
   int tokPAD, tokSTART, tokEND, tokUNK, step0;
+  int debug;                // timing experiments only (SAT_VOCAB_DEBUG): 1 = no epilogue math, 2 = no TMEM reads either
 };
 
 template <int MODE>
@@ -60,14 +63,18 @@ struct EpiVocab {
     (void)N;
   }
 
-  template <int BN>
+  // NW epilogue warps (8: one-tile-per-CTA kernel, 16: persistent kernel): warp w reads TMEM lane quarter w & 3 (rows) and the
+  // column part (w - 2) >> 2 of the tile, 128 / (NW / 4) columns.
+  template <int BN, int NW>
   __device__ __forceinline__ void run(uint8_t* scratch, const float* aux, uint32_t tmem, bool has_acc, int warp, int lane, int m0,
-                                      int n0, int M, int N) const {
+                                      int n0, int M, int N, int tile_n) const {
     static_assert(BN == 128, "the vocabulary epilogues work on 128-column tiles");
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    static_assert(NW == 8 || NW == 16, "two or four column parts");
+    constexpr int PARTS = NW / 4, PCOLS = BN / PARTS, NCH = PCOLS / 16;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int r = q * 32 + lane, m = m0 + r;
-    const int cbase = half * 64;                                   // first tile column of this thread
-    asm volatile("bar.sync 1, 256;" ::: "memory");                 // bias tile staged by prologue()
+    const int cbase = part * PCOLS;                                // first tile column of this thread
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");     // bias tile staged by prologue()
     bool active = m < M;
     int y = -1;
     if (MODE == VOCAB_GREEDY) {
@@ -78,15 +85,29 @@ struct EpiVocab {
       if (active) y = a.caps[(int64_t)b * a.caplen + t + 1];
     }
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
+    const bool tile_full = n0 + BN <= a.V0;                        // no padded / out-of-range column in this tile (CTA-uniform)
+    if (a.debug) {                                                 // timing experiments: wrong results by design
+      float acc0 = 0.f;
+      if (a.debug == 1) {
+        for (int ch = 0; ch < NCH; ++ch) {
+          float v[16];
+          tmem_ld16(taddr + ch * 16, v);
+          acc0 += v[0];
+        }
+      }
+      if (acc0 == 123.456f) a.row_xt[0] = acc0;
+      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+      return;
+    }
 
     if (MODE == VOCAB_DLOGITS) {
       // ---- pass 2: dlogits tile, staged as bf16 [128][128 + 8] and written out with whole rows per half warp ----
       constexpr int PITCH = (BN + 8) * 2;                          // bytes; 272: quarter-warp 16-byte stores hit distinct banks
-      const float lse = active ? a.row_lse[m] : 0.0f;
-      const float inv_ntok = *a.inv_ntok_p;
+      const float nlse = active ? -a.row_lse[m] * LOG2E_F : -INFINITY;     // finished rows: exp2(-inf) = 0, no overflow
+      const float inv_ntok = active ? *a.inv_ntok_p : 0.0f;        // finished rows: all-zero gradient
       const float sv = a.smoothing / (float)a.V0, conf = 1.0f - a.smoothing;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
         float v[16];
         if (has_acc) tmem_ld16(taddr + ch * 16, v);
         else {
@@ -94,6 +115,7 @@ struct EpiVocab {
           for (int j = 0; j < 16; ++j) v[j] = 0.0f;
         }
         const int c0 = cbase + ch * 16;
+        const int jy = y - (n0 + c0);                              // target column inside this chunk, or out of [0,16)
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
@@ -101,9 +123,9 @@ struct EpiVocab {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const float x = v[j + u] + aux[c0 + j + u];
-            float p = ex2_fast((x - lse) * LOG2E_F) - sv;
-            if (n0 + c0 + j + u == y) p -= conf;
-            p2[u] = (active && x > -INFINITY) ? p * inv_ntok : 0.0f;
+            float p = ex2_fast(fmaf(x, LOG2E_F, nlse)) - sv;       // softmax - s/V   (x = -inf: -s/V, zeroed below)
+            if (j + u == jy) p -= conf;
+            p2[u] = (tile_full || x > -INFINITY) ? p * inv_ntok : 0.0f;
           }
           const __nv_bfloat162 h = __floats2bfloat162_rn(p2[0], p2[1]);
           pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
@@ -112,11 +134,11 @@ struct EpiVocab {
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
       const int ew = warp - 2;
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 16 + ew * 2 + (lane >> 4);
+      for (int it = 0; it < BM / (NW * 2); ++it) {
+        const int rr = it * (NW * 2) + ew * 2 + (lane >> 4);
         const int cc = (lane & 15) * 8;
         const int mm = m0 + rr, n = n0 + cc;
         if (mm < M && n < N)
@@ -125,12 +147,12 @@ struct EpiVocab {
       return;
     }
 
-    // ---- STATS / GREEDY: running soft-max statistics of this thread's 64 columns ----
+    // ---- STATS / GREEDY: running soft-max statistics of this thread's columns (short dependency chains: pairwise trees) ----
     float mx = -INFINITY, se = 0.0f, sx = 0.0f, xt = 0.0f, bestv = -INFINITY;
     int arg = 0x7fffffff, has_xt = 0;
     const float xs = MODE == VOCAB_GREEDY ? a.inv_temp : 1.0f;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < NCH; ++ch) {
       float v[16];
       if (has_acc) tmem_ld16(taddr + ch * 16, v);
       else {
@@ -138,25 +160,39 @@ struct EpiVocab {
         for (int j = 0; j < 16; ++j) v[j] = 0.0f;
       }
       const int c0 = cbase + ch * 16, col0 = n0 + c0;
-      const float old = mx;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (v[j] + aux[c0 + j]) * xs;
+      // chunk arg-max as a tree of (value, index) pairs; a tie keeps the lower index (torch.argmax / topk order)
+      float cv[16];
+      int ci[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float x = (v[j] + aux[c0 + j]) * xs;
-        v[j] = x;
-        mx = fmaxf(mx, x);
-      }
-      if (MODE == VOCAB_GREEDY) {
-        // candidate set: <START>, <PAD> never; <END>, <UNK> not at step 0 (model.py:333,340); first index wins ties
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        cv[j] = v[j];
+        ci[j] = j;
+        if (MODE == VOCAB_GREEDY) {
+          // candidate set: <START>, <PAD> never; <END>, <UNK> not at step 0 (model.py:333,340)
           const int col = col0 + j;
-          const bool masked = col == a.tokSTART || col == a.tokPAD || (a.step0 && (col == a.tokEND || col == a.tokUNK));
-          if (!masked && v[j] > bestv) { bestv = v[j]; arg = col; }
+          if (col == a.tokSTART || col == a.tokPAD || (a.step0 && (col == a.tokEND || col == a.tokUNK))) cv[j] = -INFINITY;
         }
-      } else {
+      }
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (v[j] > bestv) { bestv = v[j]; arg = col0 + j; }      // arg-max over every word (model.py:596)
+      for (int w = 1; w < 16; w <<= 1) {
+#pragma unroll
+        for (int j = 0; j + w < 16; j += 2 * w) {
+          const bool keep = cv[j] >= cv[j + w];
+          cv[j] = keep ? cv[j] : cv[j + w];
+          ci[j] = keep ? ci[j] : ci[j + w];
+        }
+      }
+      if (cv[0] > bestv) { bestv = cv[0]; arg = col0 + ci[0]; }    // strictly greater: earlier chunks win ties
+      float cm;                                                    // chunk max over EVERY column (soft-max statistics ignore the masks)
+      if (MODE == VOCAB_GREEDY) {
+        float t8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t8[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+        cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
+      } else {
+        cm = cv[0];
         if ((unsigned)(y - col0) < 16u) {
           const int jy = y - col0;
 #pragma unroll
@@ -165,42 +201,49 @@ struct EpiVocab {
           has_xt = 1;
         }
       }
-      if (mx > -INFINITY) {
-        if (mx > old) se *= ex2_fast((old - mx) * LOG2E_F);        // old = -inf: se is still 0
-        float s0 = 0.0f, s1 = 0.0f, t0 = 0.0f, t1 = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          s0 += ex2_fast((v[j] - mx) * LOG2E_F);
-          s1 += ex2_fast((v[j + 1] - mx) * LOG2E_F);
-          t0 += v[j] > -INFINITY ? v[j] : 0.0f;
-          t1 += v[j + 1] > -INFINITY ? v[j + 1] : 0.0f;
+      if (cm > -INFINITY) {
+        if (cm > mx) {
+          se *= ex2_fast((mx - cm) * LOG2E_F);                     // mx = -inf: se is still 0
+          mx = cm;
         }
-        se += s0 + s1;
-        sx += t0 + t1;
+        const float nm = -mx * LOG2E_F;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          s4[j & 3] += ex2_fast(fmaf(v[j], LOG2E_F, nm));
+          if (MODE != VOCAB_GREEDY) t4[j & 3] += (tile_full || v[j] > -INFINITY) ? v[j] : 0.0f;
+        }
+        se += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        sx += (t4[0] + t4[1]) + (t4[2] + t4[3]);
       }
     }
-    // combine the two column halves of the tile (same row, warps w and w + 4) through the drained ring
+    // combine the column parts of the tile (same row, warps w, w + 4, ..) through shared memory, lower columns first
     float* xch = reinterpret_cast<float*>(scratch);
-    if (half == 1) {
-      float* o = xch + r * 8;
+    if (part > 0) {
+      float* o = xch + ((part - 1) * BM + r) * 8;
       o[0] = mx; o[1] = se; o[2] = sx; o[3] = bestv; o[4] = __int_as_float(arg); o[5] = xt; o[6] = __int_as_float(has_xt);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (half == 0 && active) {
-      const float* o = xch + r * 8;
-      const float mx1 = o[0], se1 = o[1], sx1 = o[2], bv1 = o[3];
-      const int arg1 = __float_as_int(o[4]);
-      const float mm = fmaxf(mx, mx1);
-      float s = 0.0f;
-      if (mx > -INFINITY) s += se * ex2_fast((mx - mm) * LOG2E_F);
-      if (mx1 > -INFINITY) s += se1 * ex2_fast((mx1 - mm) * LOG2E_F);
-      if (bv1 > bestv) { bestv = bv1; arg = arg1; }                // ties keep the lower columns (half 0)
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    if (part == 0 && active) {
+#pragma unroll
+      for (int p2 = 1; p2 < PARTS; ++p2) {
+        const float* o = xch + ((p2 - 1) * BM + r) * 8;
+        const float mx1 = o[0], se1 = o[1], bv1 = o[3];
+        const float mm = fmaxf(mx, mx1);
+        float s = 0.0f;
+        if (mx > -INFINITY) s += se * ex2_fast((mx - mm) * LOG2E_F);
+        if (mx1 > -INFINITY) s += se1 * ex2_fast((mx1 - mm) * LOG2E_F);
+        mx = mm;
+        se = s;
+        sx += o[2];
+        if (bv1 > bestv) { bestv = bv1; arg = __float_as_int(o[4]); }   // ties keep the lower columns
+        if (__float_as_int(o[6]) != 0) { xt = o[5]; has_xt = 1; }
+      }
       if (MODE == VOCAB_GREEDY) {
-        a.stats[(int64_t)m * a.NT + blockIdx.x] = make_float4(mm, s, bestv, __int_as_float(arg));
+        a.stats[(int64_t)m * a.NT + tile_n] = make_float4(mx, se, bestv, __int_as_float(arg));
       } else {
-        a.stats[(int64_t)m * a.NT + blockIdx.x] = make_float4(mm, s, sx + sx1, __int_as_float(arg));
+        a.stats[(int64_t)m * a.NT + tile_n] = make_float4(mx, se, sx, __int_as_float(arg));
         if (has_xt) a.row_xt[m] = xt;
-        else if (__float_as_int(o[6]) != 0) a.row_xt[m] = o[5];
       }
     }
     (void)N;
@@ -291,6 +334,13 @@ greedy_finalize_kernel(const float4* __restrict__ stats, int NT, const int32_t* 
 template <int MODE>
 static int launch_vocab(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const VocabArgs& va, cudaStream_t stream) {
   EpiVocab<MODE> epi{va};
+  static const int dbg = getenv("SAT_VOCAB_DEBUG") ? atoi(getenv("SAT_VOCAB_DEBUG")) : 0;
+  epi.a.debug = dbg;
+  // persistent kernel (one CTA per SM, double-buffered tensor memory) at every size, so that a row's statistics do not depend
+  // on the batch it is computed in (the two kernels split a tile's columns differently); SAT_VOCAB_PERSIST=0 forces the
+  // one-tile-per-CTA kernel (A/B timing)
+  static const int pers_mode = getenv("SAT_VOCAB_PERSIST") ? atoi(getenv("SAT_VOCAB_PERSIST")) : 1;
+  if (pers_mode != 0 && persistent_ok(A)) return launch_persistent<EpiVocab<MODE>>(A, W, ldw, M, N, epi, stream);
   return launch_bn<128, EpiVocab<MODE>>(A, W, ldw, M, N, epi, stream);
 }
 
