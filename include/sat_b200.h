@@ -202,8 +202,10 @@ typedef struct SatDecodeBuffers {
   float* alpha_all;      /* [S+1,R,L]  alpha of every step and row (histories hold row indices)    */
   float* topk_stats;     /* [R, ceil(V/128), 4] or NULL: greedy (k = 1) tensor-core decode keeps per-tile soft-max statistics
                                          and the best word instead of writing the logits                       */
-  float* cand_val;       /* [R,k]                                                                 */
-  int32_t* cand_idx;     /* [R,k]                                                                 */
+  float* cand_val;       /* [R,kcap]   per-row candidates: score (log-prob + parent score)        */
+  int32_t* cand_idx;     /* [R,kcap]   word                                                       */
+  float* cand_key;       /* [R,kcap]   sampling key (multinomial sampler), NULL for beam search   */
+  void* h_noisy;         /* [R,H] s    h + noise, operand of the recurrent projection (decoder_noise != 0), else NULL */
   int32_t* tok_hist;     /* [2,R,S+1]  generated words per live beam (ping-pong)                   */
   int32_t* asrc_hist;    /* [2,R,S+1]  row of alpha_all[step] that belongs to the beam's ancestry  */
   float* top_scores;     /* [R]                                                                   */
@@ -221,6 +223,13 @@ typedef struct SatDecodeBuffers {
   int32_t k, max_gen_length, rescore;   /* rescore: 0 none, 1 LN, 2 WR, 3 BAR                      */
   float reward;
   int32_t tokPAD, tokSTART, tokEND, tokUNK;
+  /* sampling decoders (model.py:360-379) and decoder noise (model.py:322-324); all zero = plain beam search */
+  int32_t sample_method; /* 0 "beam", 1 "multinomial" (kc draws without replacement from softmax(20*seq_scores/step)), 2 "topk"
+                            (kc draws from the softmax(score/step) of every beam's sample_topk best words); Gumbel-top-k      */
+  int32_t sample_topk;   /* candidates per beam of the "topk" sampler (<= 32)                      */
+  int32_t kcap;          /* row pitch of cand_*: >= max(k, sample_topk); 0 = k                     */
+  float decoder_noise;   /* base std-dev of the Gaussian noise added to h before the LSTM cell, scaled by 1/(step+1) */
+  uint64_t sample_seed;  /* the sampling / noise draws are a pure function of (seed, step, row, word) */
 } SatDecodeBuffers;
 
 int sat_version(void);

@@ -46,10 +46,12 @@ class SatTrainBuffers(C.Structure):
 class SatDecodeBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "P", "meanv", "f1", "init_out", "GxV", "h", "c", "hn", "cn", "hp", "z", "gz", "xo", "logits",
-                 "alpha_all", "topk_stats", "cand_val", "cand_idx", "tok_hist", "asrc_hist", "top_scores", "cur_tok", "src_row", "alive",
+                 "alpha_all", "topk_stats", "cand_val", "cand_idx", "cand_key", "h_noisy", "tok_hist", "asrc_hist", "top_scores", "cur_tok", "src_row", "alive",
                  "kcur", "fin_tokens", "fin_asrc", "fin_len", "fin_score", "fin_ppl", "fin_count", "temps")] + \
                [("k", C.c_int32), ("max_gen_length", C.c_int32), ("rescore", C.c_int32), ("reward", C.c_float),
-                ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32)]
+                ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32),
+                ("sample_method", C.c_int32), ("sample_topk", C.c_int32), ("kcap", C.c_int32), ("decoder_noise", C.c_float),
+                ("sample_seed", C.c_uint64)]
 
 
 class SatParamGrads(C.Structure):

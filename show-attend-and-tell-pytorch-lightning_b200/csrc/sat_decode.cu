@@ -47,22 +47,46 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   const int V0 = d.V0 ? d.V0 : V;
   // greedy on the tensor cores: soft-max statistics and the best word come out of the vocabulary GEMM's epilogue
   const bool fuse_greedy = k == 1 && b.topk_stats != nullptr && std::is_same<TS, bf16>::value && tc && !kExact &&
-                           tc::operands_ok(gemm_a1(b.xo, E, E), w.Wo, E);
+                           b.sample_method == 0 && tc::operands_ok(gemm_a1(b.xo, E, E), w.Wo, E);
   SAT_REQUIRE(fuse_greedy || topk_smem <= 227 * 1024, "vocabulary of %d words needs %zu bytes of shared memory per row in the top-k kernel "
               "(limit 227 KB)", V, topk_smem);
   // candidate selection: threshold kernel (SAT_TOPK_MODE=0 forces the plain scan kernel for A/B runs)
   static const int topk_mode = getenv("SAT_TOPK_MODE") ? atoi(getenv("SAT_TOPK_MODE")) : 1;
   auto topk_k = (topk_mode == 0 || k == 1) ? row_topk_kernel : row_topk_thresh_kernel;      // greedy: one scan is already minimal
   if (topk_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(topk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
-  BeamParams bp{k, V, S, b.tokEND, b.rescore, b.reward, S + 1};
+  // sampling decoders (sample_method "multinomial" / "topk", model.py:360-379) and decoder noise (model.py:322-324)
+  const int sample = b.sample_method;
+  const int kcap = b.kcap > 0 ? b.kcap : k;
+  const int kk_req = sample == SAT_SAMPLE_TOPK ? b.sample_topk : 0;
+  const bool noisy = b.decoder_noise != 0.0f;
+  SAT_REQUIRE(sample == SAT_SAMPLE_BEAM || (b.cand_key != nullptr || sample == SAT_SAMPLE_TOPK), "sat_decode: cand_key buffer missing");
+  SAT_REQUIRE(!noisy || b.h_noisy != nullptr, "sat_decode: h_noisy buffer missing");
+  const size_t samp_smem = sizeof(float) * (size_t)(2 * V + 40);
+  if (sample == SAT_SAMPLE_MULTINOMIAL) {
+    SAT_REQUIRE(samp_smem <= 227 * 1024, "vocabulary of %d words is too large for the multinomial sampler's shared memory", V);
+    if (samp_smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(row_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samp_smem));
+  }
+  BeamParams bp{k, V, S, b.tokEND, b.rescore, b.reward, S + 1, kcap, sample, b.sample_topk, b.sample_seed};
   const int64_t hist_sz = (int64_t)R * (S + 1);
 
   // k == 1 (greedy): a live row always continues from itself, so the post-LSTM state is used in place (buffer ping-pong)
   // instead of being gathered by source row
   void* h_cur = b.h; float* c_cur = b.c; void* h_nxt = b.hn; float* c_nxt = b.cn;
   for (int step = 0; step <= S; ++step) {
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
-                             st)));
+    if (!noisy) {
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
+                               st)));
+    } else {
+      // decoder noise: attention and the beta gate read the clean state, the recurrent projection W_hh (h + noise) the noisy one
+      const int64_t nh = (int64_t)R * H;
+      SAT_CUDA(sat_launch_pdl(noisy_state_kernel<TS>, dim3((unsigned)((nh + 255) / 256)), dim3(256), 0, st, (const TS*)h_cur, (TS*)b.h_noisy, nh,
+                              b.decoder_noise / (float)(step + 1), b.sample_seed, step));
+      SAT_COUNT_LAUNCH();
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, A + D, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
+                               st)));
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.h_noisy, H, H), (const TS*)w.Whcat + (int64_t)(A + D) * H, H, R, 4 * H,
+                               EpiStore<float>{b.hp + A + D, NH3, nullptr, nullptr, 0}, st)));
+    }
     SAT_PROF(1, st);
     SAT_TRY((launch_attention_fwd<TS, kExact>(ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, R, k, L, D, A, scale,
                                               b.alpha_all + (int64_t)step * R * L, L, nullptr, (TS*)b.z, (TS*)b.gz,
@@ -87,13 +111,19 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     } else {
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.xo, E, E), (const TS*)w.Wo, E, R, V, EpiStore<float>{b.logits, V, w.bo, nullptr, 0}, st)));
       SAT_PROF(3, st);
-      SAT_CUDA(sat_launch_pdl(topk_k, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
-                              (const int32_t*)b.kcur, k, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK, b.cand_val,
-                              b.cand_idx));
+      if (sample == SAT_SAMPLE_MULTINOMIAL && step > 0) {
+        SAT_CUDA(sat_launch_pdl(row_sample_kernel, dim3(R), dim3(256), samp_smem, st, (const float*)b.logits, (const float*)b.top_scores,
+                                (const int32_t*)b.kcur, k, kcap, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.sample_seed, b.cand_key,
+                                b.cand_val, b.cand_idx));
+      } else {
+        SAT_CUDA(sat_launch_pdl(topk_k, dim3(R), dim3(256), topk_smem, st, (const float*)b.logits, (const float*)b.top_scores,
+                                (const int32_t*)b.kcur, k, kcap, kk_req, V, step, b.temps[step], b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK,
+                                b.cand_val, b.cand_idx));
+      }
       SAT_COUNT_LAUNCH();
     }
     const int in = step & 1, out = in ^ 1;
-    SAT_CUDA(sat_launch_pdl(beam_update_kernel, dim3(n_img), dim3(32), 0, st, bp, step, (const float*)b.cand_val,
+    SAT_CUDA(sat_launch_pdl(beam_update_kernel, dim3(n_img), dim3(32), 0, st, bp, step, (const float*)b.cand_val, (const float*)b.cand_key,
                             (const int32_t*)b.cand_idx, b.kcur, b.top_scores, b.cur_tok, b.src_row, b.alive,
                             (const int32_t*)(b.tok_hist + in * hist_sz), (const int32_t*)(b.asrc_hist + in * hist_sz),
                             b.tok_hist + out * hist_sz, b.asrc_hist + out * hist_sz, b.fin_tokens, b.fin_asrc, b.fin_len, b.fin_score,
@@ -136,6 +166,10 @@ int sat_decode(const SatDims* d, const SatWeights* w, SatDecodeBuffers* b, void*
   SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0, "storage dims must be multiples of 8");
   SAT_REQUIRE(d->H0 >= 0 && d->H0 <= d->H && d->V0 >= 0 && d->V0 <= d->V, "true dims must not exceed the storage dims");
   SAT_REQUIRE(b->max_gen_length >= 1 && b->temps, "sat_decode: max_gen_length >= 1 and temps required");
+  SAT_REQUIRE(b->sample_method >= 0 && b->sample_method <= 2, "sat_decode: unknown sample_method %d", b->sample_method);
+  SAT_REQUIRE(b->sample_method != 2 || (b->sample_topk >= 1 && b->sample_topk <= 32 && b->kcap >= b->sample_topk && b->kcap >= b->k),
+              "sat_decode: the topk sampler needs 1 <= sample_topk <= 32 and kcap >= max(k, sample_topk)");
+  SAT_REQUIRE(b->kcap == 0 || b->kcap >= b->k, "sat_decode: kcap %d < k %d", b->kcap, b->k);
   SAT_REQUIRE(b->k + 4 <= (d->V0 ? d->V0 : d->V), "sat_decode: beam width %d too large for vocab %d", b->k, d->V0 ? d->V0 : d->V);
   SAT_REQUIRE(b->ann && b->P && b->meanv && b->f1 && b->init_out && b->GxV && b->h && b->c && b->hn && b->cn && b->hp && b->z &&
                   b->gz && b->xo && (b->logits || b->topk_stats) && b->alpha_all && b->cand_val && b->cand_idx && b->tok_hist && b->asrc_hist &&

@@ -36,7 +36,7 @@ __global__ void init_state_decode_kernel(const float* __restrict__ init_out, int
 // for the sum of exponentials) and only the winners are converted: score = (x - max) - log(sum exp(x - max)) + parent.
 __global__ void __launch_bounds__(256)
 row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur,
-                int k, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
+                int k, int kcap, int kk_req, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
                 float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
   SAT_PDL_TRIGGER();
   SAT_PDL_WAIT();
@@ -70,7 +70,7 @@ row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_
   se = block_sum(se, scratch);
   const float lse = logf(se);
   const float base = s0 ? 0.0f : top_scores[r];
-  const int kk = s0 ? k : kc;
+  const int kk = s0 ? k : (kk_req > 0 ? kk_req : kc);      // kk_req: the "topk" sampler asks for sample_topk candidates per row (pitch kcap)
   float pv = INFINITY;
   int pi = -1;
   for (int i = 0; i < kk; ++i) {
@@ -94,8 +94,8 @@ row_topk_kernel(const float* __restrict__ logits, const float* __restrict__ top_
       if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
     if (tid == 0) {
       const float lp = (bv - mx) - lse;                            // -inf stays -inf
-      cand_val[(int64_t)r * k + i] = s0 ? lp : lp + base;
-      cand_idx[(int64_t)r * k + i] = bi;
+      cand_val[(int64_t)r * kcap + i] = s0 ? lp : lp + base;
+      cand_idx[(int64_t)r * kcap + i] = bi;
     }
     pv = bv; pi = bi;
   }
@@ -111,7 +111,7 @@ __device__ __forceinline__ bool topk_before(float av, int ai, float bv, int bi) 
 
 __global__ void __launch_bounds__(256)
 row_topk_thresh_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur,
-                       int k, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
+                       int k, int kcap, int kk_req, int V, int step, float temp, int tokPAD, int tokSTART, int tokEND, int tokUNK,
                        float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
   SAT_PDL_TRIGGER();
   SAT_PDL_WAIT();
@@ -148,7 +148,7 @@ row_topk_thresh_kernel(const float* __restrict__ logits, const float* __restrict
   se = block_sum(se, scratch);          // (its barriers also publish c_val / s_cnt)
   const float lse = logf(se);
   const float base = s0 ? 0.0f : top_scores[r];
-  const int kk = s0 ? k : kc;
+  const int kk = s0 ? k : (kk_req > 0 ? kk_req : kc);      // kk_req: the "topk" sampler asks for sample_topk candidates per row (pitch kcap)
   if (warp == 0) {                      // T = kk-th largest thread maximum (with multiplicity)
     float m8[8];
 #pragma unroll
@@ -211,8 +211,8 @@ row_topk_thresh_kernel(const float* __restrict__ logits, const float* __restrict
       }
       if (lane == 0) {
         const float lp = (bv - mx) - lse;                            // -inf stays -inf
-        cand_val[(int64_t)r * k + i] = s0 ? lp : lp + base;
-        cand_idx[(int64_t)r * k + i] = bi;
+        cand_val[(int64_t)r * kcap + i] = s0 ? lp : lp + base;
+        cand_idx[(int64_t)r * kcap + i] = bi;
       }
     }
     return;
@@ -241,11 +241,124 @@ row_topk_thresh_kernel(const float* __restrict__ logits, const float* __restrict
       if (topk_before(c_val[w], c_idx[w], bv, bi)) { bv = c_val[w]; bi = c_idx[w]; }
     if (tid == 0) {
       const float lp = (bv - mx) - lse;
-      cand_val[(int64_t)r * k + i] = s0 ? lp : lp + base;
-      cand_idx[(int64_t)r * k + i] = bi;
+      cand_val[(int64_t)r * kcap + i] = s0 ? lp : lp + base;
+      cand_idx[(int64_t)r * kcap + i] = bi;
     }
     pv = bv; pi = bi;
   }
+}
+
+// ---- sampling decoders (model.py:360-379) --------------------------------------------------------------------------------
+// torch.multinomial(p, n) without replacement draws a Plackett-Luce ordering of the entries; taking the n largest of
+// log p_i + G_i with independent standard Gumbel G_i draws from exactly that distribution (Gumbel-top-k), and it runs on
+// the same per-row candidate / per-image merge structure as beam search.  The noise is a pure function of (seed, step, row,
+// word), so a decode is reproducible under its seed; it is not the reference's torch RNG stream (not parity-checkable).
+enum { SAT_SAMPLE_BEAM = 0, SAT_SAMPLE_MULTINOMIAL = 1, SAT_SAMPLE_TOPK = 2 };
+
+__device__ __forceinline__ float sat_uniform01(uint64_t seed, uint32_t stream, uint64_t idx) {      // in (0, 1)
+  return ((float)(sat_hash32(seed, stream, idx) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float sat_gumbel(uint64_t seed, uint32_t stream, uint64_t idx) {
+  return -logf(-logf(sat_uniform01(seed, stream, idx)));
+}
+
+// sample_method = "multinomial" (model.py:360-364), steps > 0: the reference draws kc flat indices from
+// softmax(20 * seq_scores / step, dim=1).reshape(-1).  Per row: key_v = y_v - logsumexp(y) + Gumbel, y = 20 * log_softmax(x)_v / step
+// (the parent score is constant inside a row and cancels in the row's softmax); the row's kc largest keys are emitted in
+// descending order together with the candidates' scores (log-prob + parent score); beam_update_kernel merges the rows by key.
+__global__ void __launch_bounds__(256)
+row_sample_kernel(const float* __restrict__ logits, const float* __restrict__ top_scores, const int32_t* __restrict__ kcur, int k,
+                  int kcap, int V, int step, float temp, int tokPAD, int tokSTART, uint64_t seed, float* __restrict__ cand_key,
+                  float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
+  extern __shared__ __align__(16) float smem[];
+  float* x = smem;            // [V] scaled logits (masked entries -inf)
+  float* key = x + V;         // [V] sampling keys
+  float* scratch = key + V;   // [33]
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const int r = blockIdx.x, n = r / k, j = r - n * k, tid = threadIdx.x;
+  const int kc = kcur[n];
+  if (j >= kc) return;
+  const float* row = logits + (int64_t)r * V;
+  float mx = -INFINITY;
+  for (int v = tid * 4; v < V; v += 256 * 4) {
+    float4 q = *reinterpret_cast<const float4*>(row + v);
+    q.x = q.x / temp; q.y = q.y / temp; q.z = q.z / temp; q.w = q.w / temp;
+    *reinterpret_cast<float4*>(x + v) = q;
+    mx = fmaxf(fmaxf(mx, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+  }
+  mx = block_max(mx, scratch);
+  float se = 0.0f;
+  for (int v = tid; v < V; v += 256) {
+    se += expf(x[v] - mx);
+    if (v == tokSTART || v == tokPAD) x[v] = -INFINITY;            // model.py:333
+  }
+  se = block_sum(se, scratch);
+  const float lse = logf(se);
+  const float sharp = 20.0f / (float)step;                          // model.py:363
+  float my = -INFINITY;
+  for (int v = tid; v < V; v += 256) {
+    const float y = sharp * ((x[v] - mx) - lse);                    // -inf for masked / padded words
+    key[v] = y;
+    my = fmaxf(my, y);
+  }
+  my = block_max(my, scratch);
+  float se2 = 0.0f;
+  for (int v = tid; v < V; v += 256) se2 += expf(key[v] - my);
+  se2 = block_sum(se2, scratch);
+  const float lse2 = my + logf(se2);
+  for (int v = tid; v < V; v += 256) {
+    const float y = key[v];
+    key[v] = y > -INFINITY ? (y - lse2) + sat_gumbel(seed, (uint32_t)step, (uint64_t)r * (uint64_t)V + v) : -INFINITY;
+  }
+  __syncthreads();
+  const float base = top_scores[r];
+  float pv = INFINITY;
+  int pi = -1;
+  for (int i = 0; i < kc; ++i) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = tid; v < V; v += 256) {
+      const float kv = key[v];
+      const bool after = (kv < pv) || (kv == pv && v > pi);
+      if (after && (kv > bv || (kv == bv && v < bi))) { bv = kv; bi = v; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    bv = s_val[0]; bi = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+    if (tid == 0) {
+      const bool ok = bi != 0x7fffffff && bv > -INFINITY;
+      cand_key[(int64_t)r * kcap + i] = ok ? bv : -INFINITY;
+      cand_val[(int64_t)r * kcap + i] = ok ? ((x[bi] - mx) - lse) + base : -INFINITY;
+      cand_idx[(int64_t)r * kcap + i] = ok ? bi : 0;
+    }
+    pv = bv; pi = bi;
+  }
+}
+
+// decoder_noise (model.py:322-324): h += randn * noise / (step + 1) right before the LSTM cell -- only the recurrent
+// projection W_hh h sees it (attention and the beta gate were computed from the clean state).  Box-Muller on the stateless hash.
+template <typename T>
+__global__ void __launch_bounds__(256) noisy_state_kernel(const T* __restrict__ h, T* __restrict__ h_noisy, int64_t n, float sigma,
+                                                          uint64_t seed, int step) {
+  SAT_PDL_TRIGGER();
+  SAT_PDL_WAIT();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float u1 = sat_uniform01(seed, 0x40000000u + (uint32_t)step, 2 * (uint64_t)i);
+  const float u2 = sat_uniform01(seed, 0x40000000u + (uint32_t)step, 2 * (uint64_t)i + 1);
+  const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  h_noisy[i] = from_f<T>(to_f(h[i]) + sigma * g);
 }
 
 struct BeamParams {
@@ -254,11 +367,16 @@ struct BeamParams {
   int rescore;                 // SAT_RESCORE_*
   float reward;
   int hist_ld;                 // S + 1 entries per slot
+  int kcap;                    // candidates stored per row (row pitch of cand_*): max(k, sample_topk)
+  int sample;                  // SAT_SAMPLE_*
+  int sample_topk;             // candidates per row of the "topk" sampler
+  uint64_t seed;
 };
 
 // One warp per image.  Lane 0 performs the (tiny) merge; all lanes copy histories.
 __global__ void __launch_bounds__(32)
-beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, const float* __restrict__ cand_key,
+                   const int32_t* __restrict__ cand_idx,
                    int32_t* __restrict__ kcur, float* __restrict__ top_scores, int32_t* __restrict__ cur_tok,
                    int32_t* __restrict__ src_row, int32_t* __restrict__ alive, const int32_t* __restrict__ tok_in,
                    const int32_t* __restrict__ asrc_in, int32_t* __restrict__ tok_out, int32_t* __restrict__ asrc_out,
@@ -277,24 +395,51 @@ beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, c
   const int64_t r0 = (int64_t)n * k;
   if (lane == 0) {
     int nnew;
+    const int cp = p.kcap;                                 // candidates per row in cand_* (row pitch)
     if (step == 0) {
       nnew = k;
-      for (int i = 0; i < k; ++i) { nval[i] = cand_val[r0 * k + i]; nword[i] = cand_idx[r0 * k + i]; nsrc[i] = i; }
+      for (int i = 0; i < k; ++i) { nval[i] = cand_val[r0 * cp + i]; nword[i] = cand_idx[r0 * cp + i]; nsrc[i] = i; }
+    } else if (p.sample == SAT_SAMPLE_TOPK) {
+      // "topk" sampler (model.py:365-379): every live beam offers its sample_topk best words; kc of these kc * sample_topk
+      // candidates are drawn without replacement with probability softmax(score / step): Gumbel-top-k over the candidates
+      nnew = kc;
+      const int tk = p.sample_topk;
+      unsigned long long taken[KMAX * KMAX / 64 + 1];
+      for (int w = 0; w < KMAX * KMAX / 64 + 1; ++w) taken[w] = 0ull;
+      for (int i = 0; i < kc; ++i) {
+        int bj = -1, bc = 0;
+        float bkey = -INFINITY;
+        for (int j = 0; j < kc; ++j) {
+          for (int c = 0; c < tk; ++c) {
+            const int f = j * tk + c;
+            if ((taken[f >> 6] >> (f & 63)) & 1ull) continue;
+            const float v = cand_val[(r0 + j) * cp + c];
+            if (!(v > -INFINITY)) continue;
+            const float key = v / (float)step + sat_gumbel(p.seed, 0x20000000u + (uint32_t)step, (uint64_t)(r0 + j) * (uint64_t)cp + c);
+            if (bj < 0 || key > bkey) { bj = j; bc = c; bkey = key; }
+          }
+        }
+        if (bj < 0) { bj = 0; bc = 0; }
+        const int f = bj * tk + bc;
+        taken[f >> 6] |= 1ull << (f & 63);
+        nval[i] = cand_val[(r0 + bj) * cp + bc]; nword[i] = cand_idx[(r0 + bj) * cp + bc]; nsrc[i] = bj;
+      }
     } else {
+      // beam search: top-kc of the flattened [kc*V] scores (model.py:359); "multinomial": the kc largest sampling keys.  Every
+      // row's candidates are sorted by that criterion, so this is a kc-way merge.
+      const float* ckey = (p.sample == SAT_SAMPLE_MULTINOMIAL && cand_key != nullptr) ? cand_key : cand_val;
       nnew = kc;
       int ptr[KMAX];
       for (int j = 0; j < kc; ++j) ptr[j] = 0;
-      for (int i = 0; i < kc; ++i) {                   // top-kc of the flattened [kc*V] scores (model.py:359)
+      for (int i = 0; i < kc; ++i) {
         int bj = -1;
         float bv = 0.f;
-        int bw = 0;
         for (int j = 0; j < kc; ++j) {
           if (ptr[j] >= kc) continue;
-          const float v = cand_val[(r0 + j) * k + ptr[j]];
-          const int w = cand_idx[(r0 + j) * k + ptr[j]];
-          if (bj < 0 || v > bv) { bj = j; bv = v; bw = w; }   // j ascending => lower flat index wins ties
+          const float v = ckey[(r0 + j) * cp + ptr[j]];
+          if (bj < 0 || v > bv) { bj = j; bv = v; }       // j ascending => lower flat index wins ties
         }
-        nval[i] = bv; nword[i] = bw; nsrc[i] = bj;
+        nval[i] = cand_val[(r0 + bj) * cp + ptr[bj]]; nword[i] = cand_idx[(r0 + bj) * cp + ptr[bj]]; nsrc[i] = bj;
         ++ptr[bj];
       }
     }

@@ -44,7 +44,6 @@ struct VocabArgs {
   const int32_t* alive;
   float inv_temp;
   int tokPAD, tokSTART, tokEND, tokUNK, step0;
-  int debug;                // timing experiments only (SAT_VOCAB_DEBUG): 1 = no epilogue math, 2 = no TMEM reads either
 };
 
 template <int MODE>
@@ -86,20 +85,6 @@ struct EpiVocab {
     }
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
     const bool tile_full = n0 + BN <= a.V0;                        // no padded / out-of-range column in this tile (CTA-uniform)
-    if (a.debug) {                                                 // timing experiments: wrong results by design
-      float acc0 = 0.f;
-      if (a.debug == 1) {
-        for (int ch = 0; ch < NCH; ++ch) {
-          float v[16];
-          tmem_ld16(taddr + ch * 16, v);
-          acc0 += v[0];
-        }
-      }
-      if (acc0 == 123.456f) a.row_xt[0] = acc0;
-      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-      return;
-    }
-
     if (MODE == VOCAB_DLOGITS) {
       // ---- pass 2: dlogits tile, staged as bf16 [128][128 + 8] and written out with whole rows per half warp ----
       constexpr int PITCH = (BN + 8) * 2;                          // bytes; 272: quarter-warp 16-byte stores hit distinct banks
@@ -334,8 +319,6 @@ greedy_finalize_kernel(const float4* __restrict__ stats, int NT, const int32_t* 
 template <int MODE>
 static int launch_vocab(const GemmOperandA& A, const bf16* W, int64_t ldw, int M, int N, const VocabArgs& va, cudaStream_t stream) {
   EpiVocab<MODE> epi{va};
-  static const int dbg = getenv("SAT_VOCAB_DEBUG") ? atoi(getenv("SAT_VOCAB_DEBUG")) : 0;
-  epi.a.debug = dbg;
   // persistent kernel (one CTA per SM, double-buffered tensor memory) at every size, so that a row's statistics do not depend
   // on the batch it is computed in (the two kernels split a tile's columns differently); SAT_VOCAB_PERSIST=0 forces the
   // one-tile-per-CTA kernel (A/B timing)

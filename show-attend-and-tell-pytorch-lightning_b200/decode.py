@@ -14,6 +14,7 @@ from . import _lib, _redzone, decoder
 from .packing import PackedWeights
 
 RESCORE = {None: 0, "LN": 1, "WR": 2, "BAR": 3}
+SAMPLE = {"beam": 0, "multinomial": 1, "topk": 2}
 
 
 class DecodeWeights:
@@ -30,9 +31,10 @@ class DecodeWeights:
 
 
 def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_method=None, rescore_reward=0.5,
-                       vocab=None):
+                       vocab=None, sample_method="beam", sample_topk=3, decoder_noise=None, seed=None):
     """ann_bld [n_img,L,D] (dw.pw.dtype, cuda).  Returns dict of device tensors (fin_* + alpha_all) after
-    enqueueing the whole decode; nothing is synchronised here."""
+    enqueueing the whole decode; nothing is synchronised here.  sample_method "multinomial" / "topk" and decoder_noise
+    (model.py:322-324,360-379) draw their randomness from `seed` (default: one draw from torch's CPU generator)."""
     L_ = _lib.lib()
     dev = ann_bld.device
     n_img, L, D = ann_bld.shape
@@ -46,8 +48,13 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     R = n_img * k
     dtype = dw.pw.dtype
     d = decoder.make_dims(R, n_img, L, dw.pw, S + 1, dtype, dw.exact, dw.use_tc)
+    method = SAMPLE[sample_method]
+    noise = float(decoder_noise) if decoder_noise else 0.0
+    kcap = max(k, int(sample_topk)) if method == 2 else k
+    if (method != 0 or noise != 0.0) and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     # greedy on the tensor cores: per-tile soft-max statistics replace the [R,V] logits
-    fuse_greedy = k == 1 and dw.use_tc and dtype == torch.bfloat16 and not dw.exact
+    fuse_greedy = k == 1 and method == 0 and dw.use_tc and dtype == torch.bfloat16 and not dw.exact
     f, s, i32 = torch.float32, dtype, torch.int32
     _n = [0]
 
@@ -58,13 +65,17 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * H), f),
              h=mk((R, H), s), c=mk((R, H), f), hn=mk((R, H), s), cn=mk((R, H), f), hp=mk((R, A + D + 4 * H), f),
              z=mk((R, D), s), gz=mk((R, D), s), xo=mk((R, E), s), alpha_all=mk((S + 1, R, L), f),
-             cand_val=mk((R, k), f), cand_idx=mk((R, k), i32), tok_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev),
+             cand_val=mk((R, kcap), f), cand_idx=mk((R, kcap), i32), tok_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev),
              asrc_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev), top_scores=mk((R,), f), cur_tok=mk((R,), i32),
              src_row=torch.zeros((R,), dtype=i32, device=dev), alive=mk((R,), i32), kcur=mk((n_img,), i32),
              fin_tokens=torch.zeros((n_img, k, S + 1), dtype=i32, device=dev),
              fin_asrc=torch.zeros((n_img, k, S + 1), dtype=i32, device=dev), fin_len=mk((n_img, k), i32),
              fin_score=torch.full((n_img, k), float("-inf"), dtype=f, device=dev), fin_ppl=mk((n_img, k), f),
              fin_count=mk((n_img,), i32))
+    if method == 1:
+        t["cand_key"] = mk((R, kcap), f)
+    if noise != 0.0:
+        t["h_noisy"] = mk((R, H), s)
     if fuse_greedy:
         t["topk_stats"] = mk((R, (V + 127) // 128, 4), f)
     else:
@@ -79,6 +90,7 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     b.temps = C.cast(temps_arr, C.c_void_p)
     b.k, b.max_gen_length, b.rescore, b.reward = k, S, RESCORE[rescore_method], float(rescore_reward)
     b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK = vocab["PAD"], vocab["START"], vocab["END"], vocab["UNK"]
+    b.sample_method, b.sample_topk, b.kcap, b.decoder_noise, b.sample_seed = method, int(sample_topk), kcap, noise, int(seed or 0)
     _lib.check(L_.sat_decode(C.byref(d), dw.pw.ref(), C.byref(b), _lib.stream_ptr()), "sat_decode")
     t["ann"] = ann_bld
     t["_dims"] = (n_img, k, S, L)
@@ -164,10 +176,12 @@ def inference_weights(model):
     return model._packed_infer[1]
 
 
-def caption_from_annotations(model, ann, beamk, max_gen_length, temperature, rescore_method, rescore_reward, return_all):
+def caption_from_annotations(model, ann, beamk, max_gen_length, temperature, rescore_method, rescore_reward, return_all,
+                             sample_method="beam", sample_topk=3, decoder_noise=None):
     dw = inference_weights(model)
     hw = tuple(ann.shape[2:])
     bld = decoder.annotations_as_bld(ann, dw.pw.dtype)
     vocab = dict(PAD=model.stoi("<PAD>"), START=model.stoi("<START>"), END=model.stoi("<END>"), UNK=model.stoi("<UNK>"))
-    t = decode_annotations(dw, bld, int(beamk), max_gen_length, temperature, rescore_method, rescore_reward, vocab)
+    t = decode_annotations(dw, bld, int(beamk), max_gen_length, temperature, rescore_method, rescore_reward, vocab,
+                           sample_method=sample_method, sample_topk=sample_topk, decoder_noise=decoder_noise)
     return assemble(t, hw, return_all=return_all)

@@ -670,12 +670,13 @@ class SAT(_Base):
     def forward(self, img, beamk=3, max_gen_length=32, temperature=1.0, sample_method="beam", sample_topk=3,
                 decoder_noise=None, rescore_method=None, rescore_reward=0.5, return_all=False):
         assert sample_method in ["beam", "multinomial", "topk"]
-        if sample_method != "beam" or (decoder_noise is not None and decoder_noise != 0.0):
-            raise NotImplementedError("only sample_method='beam' without decoder noise is on the accelerated path")
         from . import decode
         ann = self.encode(img)
+        # "multinomial" / "topk" sampling and decoder noise run on the device as Gumbel-top-k / stateless Gaussian draws seeded
+        # from torch's CPU generator (same distributions as the reference's torch.multinomial / torch.randn, not its RNG stream)
         return decode.caption_from_annotations(self, ann, beamk, max_gen_length, temperature, rescore_method,
-                                               rescore_reward, return_all)
+                                               rescore_reward, return_all, sample_method=sample_method, sample_topk=sample_topk,
+                                               decoder_noise=decoder_noise)
 
     @torch.no_grad()
     def caption_stream(self, batches, beamk=3, max_gen_length=32, temperature=1.0, rescore_method=None, rescore_reward=0.5,
