@@ -283,6 +283,11 @@ int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, con
  * 2 (embedded words, idx = (t*B+b)*E+e) or 3 (deep-output activations, idx = (t*B+b)*E+e).  Host-side mirror for tests. */
 float sat_dropout_multiplier(float p, uint64_t seed, uint32_t stream, uint64_t idx);
 
+/* int64 word ids / lengths (what the dataset's collate hands to SAT.train_batch, util.py:43-44) -> the int32 arrays
+ * SatTrainBuffers.caps / .lens point to; one launch. */
+int sat_cast_captions(const int64_t* caps64, const int64_t* lens64, int32_t* caps32, int32_t* lens32, int64_t n_caps, int64_t n_lens,
+                      void* stream);
+
 int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
 
 /* Hand-written BPTT of sat_train_forward (what autograd derives from model.py:510-548): fills

@@ -289,6 +289,14 @@ static __global__ void tok_init_kernel(const int32_t* __restrict__ caps, int32_t
   tok[m] = w;
 }
 
+// the dataset hands out int64 word ids / lengths (torch.LongTensor, util.py:43-44); the kernels index with int32
+static __global__ void cast_captions_kernel(const int64_t* __restrict__ caps64, const int64_t* __restrict__ lens64, int32_t* __restrict__ caps32,
+                                            int32_t* __restrict__ lens32, int64_t n_caps, int64_t n_lens) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_caps) caps32[i] = (int32_t)caps64[i];
+  else if (i < n_caps + n_lens) lens32[i - n_caps] = (int32_t)lens64[i - n_caps];
+}
+
 // =============================================================================================
 // embedding gather over `rows` time-major rows:  Xe[m,:] = Emb[tok[m],:]                 model.py:526
 // =============================================================================================

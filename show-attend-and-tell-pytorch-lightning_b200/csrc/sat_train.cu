@@ -66,7 +66,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   SAT_TRY((prepare_images_impl<TS>(d, w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st, b.dropout_p, b.dropout_seed)));
 
   // ---- hoisted: embeddings of the (teacher-forced) previous words and their gate projection ---
-  SAT_CUDA(cudaMemsetAsync(b.out + 6, 0, sizeof(float), st));
+  SAT_CUDA(cudaMemsetAsync(b.out, 0, 8 * sizeof(float), st));
   tok_init_kernel<<<(T * B + 255) / 256, 256, 0, st>>>(b.caps, b.tok, B, T, caplen, V0, b.out + 6);
   SAT_COUNT_LAUNCH();
   embed_gather_kernel<TS><<<T * B, 64, 0, st>>>((const TS*)w.Emb, b.tok, (TS*)b.Xe, E, 0, b.emb_dropout_p, b.dropout_seed);
@@ -257,6 +257,17 @@ int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, con
     if (d->exact) SAT_LAUNCH_ATT(bf16, true); else SAT_LAUNCH_ATT(bf16, false);
   }
 #undef SAT_LAUNCH_ATT
+  return 0;
+}
+
+int sat_cast_captions(const int64_t* caps64, const int64_t* lens64, int32_t* caps32, int32_t* lens32, int64_t n_caps, int64_t n_lens,
+                      void* stream) {
+  SAT_REQUIRE(caps64 && lens64 && caps32 && lens32 && n_caps >= 0 && n_lens >= 0, "sat_cast_captions: bad argument");
+  const int64_t n = n_caps + n_lens;
+  if (n == 0) return 0;
+  cast_captions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(caps64, lens64, caps32, lens32, n_caps, n_lens);
+  SAT_COUNT_LAUNCH();
+  SAT_LAUNCH_OK();
   return 0;
 }
 

@@ -22,6 +22,17 @@ _GRAD_FIELD = {
 }
 
 
+_ONES = {}
+
+
+def _one(device):
+    """a persistent device scalar 1.0 (default upstream gradient of the loss)"""
+    key = str(device)
+    if key not in _ONES:
+        _ONES[key] = torch.ones(1, dtype=torch.float32, device=device)
+    return _ONES[key]
+
+
 def make_dims(B, Bi, L, pw_or_dims, T, dtype, exact, use_tc, plain_output=False, dims0=None):
     """SatDims for a PackedWeights object (storage dims + the module's true dims) or an explicit dict of storage dims."""
     d = _lib.SatDims()
@@ -80,9 +91,9 @@ class TrainBuffers:
         t["row_loss"] = mk((T, B), f)
         t["row_argmax"] = mk((T, B), torch.int32)
         t["S"] = mk((B, L), f)
-        t["out"] = torch.zeros(8, dtype=f, device=device)
+        t["out"] = mk((8,), f)                     # zeroed by sat_train_forward
         if backward:
-            t["gscale"] = torch.ones(1, dtype=f, device=device)
+            t["gscale"] = _one(device)
             t["dpre"] = mk((T, B, E), s)
             t["dHZ"] = mk((T, B, H + D), f)
             t["DY"] = mk((T, B, NH3), s)
@@ -147,8 +158,18 @@ def train_forward(pw, ann_bld, caps, lens, label_smoothing=0.0, att_gamma=1.0, e
     L_ = _lib.lib()
     dev = ann_bld.device
     Bi, L, D = ann_bld.shape
-    caps2 = caps.reshape(-1, caps.shape[-1]).to(device=dev, dtype=torch.int32).contiguous()
-    lens2 = lens.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    caps2 = caps.reshape(-1, caps.shape[-1])
+    lens2 = lens.reshape(-1)
+    if caps2.dtype == torch.int64 and lens2.dtype == torch.int64 and caps2.device == dev and lens2.device == dev:
+        # int64 ids from the dataset: narrowed by the library (one launch) instead of two framework casts
+        c64, l64 = caps2.contiguous(), lens2.contiguous()
+        caps2 = torch.empty(c64.shape, dtype=torch.int32, device=dev)
+        lens2 = torch.empty(l64.shape, dtype=torch.int32, device=dev)
+        _lib.check(L_.sat_cast_captions(c64.data_ptr(), l64.data_ptr(), caps2.data_ptr(), lens2.data_ptr(), c64.numel(), l64.numel(),
+                                        _lib.stream_ptr()), "sat_cast_captions")
+    else:
+        caps2 = caps2.to(device=dev, dtype=torch.int32).contiguous()
+        lens2 = lens2.to(device=dev, dtype=torch.int32).contiguous()
     B, caplen = caps2.shape
     dm, dm0 = pw.dims, pw.dims0
     if D == dm0["D"] and D != dm["D"]:
@@ -177,9 +198,13 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
     dm0 = pw.dims0
     dev = t["dlogits"].device
     if grad_loss is None:
-        t["gscale"].fill_(1.0)
+        buf.c.gscale = _lib.ptr(t["gscale"])          # the ones written at allocation
     else:
-        t["gscale"].copy_(grad_loss.detach().reshape(1).to(torch.float32))
+        gl = grad_loss.detach().reshape(1)
+        if gl.dtype != torch.float32 or gl.device != dev:
+            gl = gl.to(device=dev, dtype=torch.float32)
+        t["gscale_in"] = gl                            # upstream gradient read in place (kept alive with the buffers)
+        buf.c.gscale = _lib.ptr(gl)
     if dalpha_ext is not None:
         t["dalpha_ext"] = dalpha_ext.to(torch.float32).contiguous()
         buf.c.dalpha_ext = _lib.ptr(t["dalpha_ext"])

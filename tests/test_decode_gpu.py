@@ -126,3 +126,35 @@ def test_beam_candidates_with_tied_logits(n_tied):
         for c in caps[i]:
             assert len(c) == 6 and set(c) <= {10, 11, 12}, c           # never <END>: flushed at the maximum length
         assert all(abs(s - scores[i][0]) < 1e-5 for s in scores[i])     # every hypothesis has the same score
+
+
+def test_rows_that_die_mid_decode_produce_zero_attention():
+    """A beam slot that stops being live (its hypothesis ended) is skipped by every kernel of the following steps: the
+    attention kernel reads the liveness array only after its predecessors in the launch chain have completed (it is
+    rewritten every step by beam_update_kernel), and writes exact zeros for dead slots."""
+    from sat_b200 import decode, decoder
+    z, W, _ = load_golden("decode_small")
+    V, max_len = int(z["dims"][4]), int(z["dims"][5])
+    ann = torch.from_numpy(z["ann"])
+    k = 5
+    dw = decode.DecodeWeights(W, torch.float32, torch.device("cuda"), True, False)
+    t = decode.decode_annotations(dw, decoder.annotations_as_bld(ann.cuda(), torch.float32), k, max_len, 1.0, "LN", 0.5, VOC(V))
+    torch.cuda.synchronize()
+    alpha_all = t["alpha_all"].cpu()                       # [S+1, R, L]
+    fin_len = t["fin_len"].cpu()
+    fin_cnt = t["fin_count"].cpu()
+    n_img = ann.shape[0]
+    checked_dead = 0
+    for n in range(n_img):
+        lens_n = sorted(int(fin_len[n, i]) for i in range(int(fin_cnt[n])))
+        for step in range(1, max_len + 1):
+            # a hypothesis of length l (fin_len = step at which it ended) leaves the beam after step l; flushed ones end at max_len
+            live = k - sum(1 for l in lens_n if l < step)
+            for j in range(k):
+                row = alpha_all[step, n * k + j]
+                if j < live:
+                    assert abs(float(row.sum()) - 1.0) < 1e-5, (n, step, j)
+                else:
+                    assert float(row.abs().max()) == 0.0, (n, step, j)
+                    checked_dead += 1
+    assert checked_dead > 0                                # the golden's beams do shrink
