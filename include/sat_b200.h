@@ -38,7 +38,8 @@ extern "C" {
 #define SAT_BF16 1
 #define SAT_ERR_INVALID (-1)
 
-#define SAT_ABI_VERSION 2
+#define SAT_ABI_VERSION 3
+#define SAT_MAX_LAYERS 4      /* decoder_layers (nn.LSTM num_layers, model.py:175-180) supported by the kernels */
 
 typedef struct SatDims {
   int32_t B, Bi, ncap;
@@ -48,7 +49,9 @@ typedef struct SatDims {
   int32_t use_tc;     /* 1: tcgen05 tensor-core GEMMs where the shape allows (bf16 only); 0: SIMT FFMA GEMMs */
   int32_t plain_output; /* 1: DeepOutput with deep=False (model.py:128-129: x = W_ho h', no tanh / embedding / context); 0: deep */
   int32_t D0, A0, E0, H0, V0; /* true sizes of the reference module (<= the storage dims above; 0 = same as storage) */
-  int32_t reserved0;
+  int32_t layers;     /* decoder_layers: stacked LSTM layers (0 or 1 = one layer).  Layer 0 takes [embedding ; beta*z], layer l > 0 the new
+                         hidden state of layer l-1 (no dropout between layers); attention, beta gate and the output layer read the TOP
+                         layer's state (model.py:300-327,538-547) */
 } SatDims;
 
 /* Packed decoder weights (device).  "s" = storage dtype of SatDims.dtype. */
@@ -78,6 +81,10 @@ typedef struct SatWeights {
   const void* WaT;     /* [D,A] s */
   const void* WinitT;  /* [E,2H] s */
   const void* WfactT;  /* [D,E] s */
+  /* stacked layers l = 1 .. layers-1 (index l-1): the layer's input is the new hidden state of the layer below */
+  const void* Wl[SAT_MAX_LAYERS - 1];    /* [4H,2H] s   lstm.weight_ih_l{l} | lstm.weight_hh_l{l}, gate-interleaved rows   */
+  const float* bgl[SAT_MAX_LAYERS - 1];  /* [4H]        bias_ih_l{l} + bias_hh_l{l}, gate-interleaved                       */
+  const void* WlT[SAT_MAX_LAYERS - 1];   /* [2H,4H] s   transposed (backward)                                              */
 } SatWeights;
 
 /* fp32 master parameters under the reference's names (device pointers, contiguous). */
@@ -100,6 +107,10 @@ typedef struct SatMasterWeights {
   const float* out_context;  /* output.context.weight [E,D] or NULL (deep_output=False: destination stays zero) */
   const float* out_w;        /* output.output.weight [V,E]                   */
   const float* out_b;        /* output.output.bias [V] or NULL (weight tying) */
+  const float* w_ih_l[SAT_MAX_LAYERS - 1];   /* lstm.weight_ih_l{l} [4H,H], l = 1 ..   (NULL beyond decoder_layers) */
+  const float* w_hh_l[SAT_MAX_LAYERS - 1];   /* lstm.weight_hh_l{l} [4H,H]  */
+  const float* b_ih_l[SAT_MAX_LAYERS - 1];   /* lstm.bias_ih_l{l} [4H]      */
+  const float* b_hh_l[SAT_MAX_LAYERS - 1];   /* lstm.bias_hh_l{l} [4H]      */
 } SatMasterWeights;
 
 /* Buffers of one teacher-forced training step.  fwd = written by sat_train_forward and read by
@@ -116,13 +127,13 @@ typedef struct SatTrainBuffers {
   void* P;               /* [Bi,L,A] s   W_a * a, once per image (reference recomputes per step, model.py:100) */
   void* meanv;           /* [Bi,D] s     mean over locations (model.py:78)                        */
   void* f1;              /* [Bi,E] s     init_lstm.factorize output                               */
-  float* init_out;       /* [Bi,2H]      init_lstm.init output before the [2,B,H] reinterpretation */
+  float* init_out;       /* [Bi,2*layers*H]  init_lstm.init output before the [2*layers,B,H] reinterpretation */
   /* per-step buffers are TIME-MAJOR (row m = t*B + b): each step's slice is a contiguous GEMM
    * operand, and the whole-sequence projections are single GEMMs with M = T*B. */
   void* Xe;              /* [T,B,E] s    embedded previous words                                  */
   float* Gx;             /* [T,B,4H]     Xe * Wihe^T + bg                                          */
-  void* Hs;              /* [T+1,B,H] s  hidden state before step t at [t] (Hs[0] = h0)           */
-  float* Cs;             /* [T+1,B,H]    cell state                                               */
+  void* Hs;              /* [layers,T+1,B,H] s  hidden state of every layer before step t at [l][t] ([l][0] = h0 of layer l) */
+  float* Cs;             /* [layers,T+1,B,H]    cell state                                        */
   float* hp;             /* [B,A+D+4H]   per-step scratch: q | beta_pre | W_hh h                   */
   float* Q;              /* [T,B,A]      q_t = W_h h_t (saved for backward)                        */
   float* alphas;         /* [B,T,L]      attention weights (batch-major, the reference's return layout);
@@ -130,7 +141,7 @@ typedef struct SatTrainBuffers {
   void* Z;               /* [T,B,D] s    context z_t                                               */
   void* GZ;              /* [T,B,D] s    beta_t * z_t  (LSTM input)                                */
   void* Beta;            /* [T,B,D] s    beta_t                                                    */
-  void* Gates;           /* [T,B,4H] s   post-activation i,f,g,o (gate-interleaved)                */
+  void* Gates;           /* [layers,T,B,4H] s   post-activation i,f,g,o (gate-interleaved)         */
   void* Xo;              /* [T,B,E] s    tanh(Xe + W_ho h' + W_zo z)                               */
   void* logits;          /* [T,B,V]      s, or fp32 when logits_f32 != 0; zeros where inactive.  May be NULL when ce_stats is
                                          given (fused path)                                        */
@@ -155,7 +166,12 @@ typedef struct SatTrainBuffers {
   void* DY;              /* [T,B,A+D+4H] s: dq | dbeta_pre | dG (gate-interleaved)                 */
   float* dgz;            /* [16,B,D]     per-step scratch: split-K partials of dG * Wihz                   */
   float* dh;             /* [16,B,H]     running grad wrt h: split-K partials of the h-chain GEMM          */
-  float* dc;             /* [B,H]        running grad wrt c                                        */
+  float* dc;             /* [layers,B,H] running grad wrt c of every layer                         */
+  void* dGl;             /* [layers-1,T,B,4H] s  pre-activation gate grads of the stacked layers l >= 1 (NULL for one layer) */
+  float* dxl;            /* [layers-1,16,B,2H]   split-K partials of dG_l * [W_ih_l | W_hh_l]: columns 0..H = grad wrt the
+                                         layer's input (new state of layer l-1, same step), H..2H = grad wrt its own previous state */
+  float* dhq;            /* [16,B,H]     layers > 1: split-K partials of [dq | dbeta_pre] * [W_h ; W_beta] (grad wrt the top state);
+                                         `dh` then holds dG_0 * W_hh_l0 only                       */
   void* dZ;              /* [T,B,D] s    total grad wrt z_t (for d_ann)                            */
   float* dP;             /* [B,L,A]      accumulated grad wrt P                                    */
   void* dP16;            /* [B,L,A] s    copy of dP in the operand dtype, written at the last backward step (t = 0);
@@ -190,10 +206,10 @@ typedef struct SatDecodeBuffers {
   void* f1;              /* [n_img,E] s                                                          */
   float* init_out;       /* [n_img,2H]                                                           */
   const float* GxV;      /* [V,4H]  Emb * Wihe^T + bg per vocabulary entry (sat_decode_prepare_weights) */
-  void* h;               /* [R,H] s   state entering the step                                     */
-  float* c;              /* [R,H]                                                                 */
-  void* hn;              /* [R,H] s   state after the LSTM update, before the beam reorder         */
-  float* cn;             /* [R,H]                                                                 */
+  void* h;               /* [layers,R,H] s   state entering the step                              */
+  float* c;              /* [layers,R,H]                                                          */
+  void* hn;              /* [layers,R,H] s   state after the LSTM update, before the beam reorder  */
+  float* cn;             /* [layers,R,H]                                                          */
   float* hp;             /* [R,A+D+4H]                                                            */
   void* z;               /* [R,D] s                                                               */
   void* gz;              /* [R,D] s                                                               */
@@ -205,7 +221,7 @@ typedef struct SatDecodeBuffers {
   float* cand_val;       /* [R,kcap]   per-row candidates: score (log-prob + parent score)        */
   int32_t* cand_idx;     /* [R,kcap]   word                                                       */
   float* cand_key;       /* [R,kcap]   sampling key (multinomial sampler), NULL for beam search   */
-  void* h_noisy;         /* [R,H] s    h + noise, operand of the recurrent projection (decoder_noise != 0), else NULL */
+  void* h_noisy;         /* [layers,R,H] s  h + noise, operand of the recurrent projections (decoder_noise != 0), else NULL */
   int32_t* tok_hist;     /* [2,R,S+1]  generated words per live beam (ping-pong)                   */
   int32_t* asrc_hist;    /* [2,R,S+1]  row of alpha_all[step] that belongs to the beam's ancestry  */
   float* top_scores;     /* [R]                                                                   */
@@ -316,6 +332,10 @@ typedef struct SatParamGrads {
   float* out_context;  /* output.context.weight [E0,D0] (deep output only) */
   float* out_w;        /* output.output.weight [V0,E0]; NULL when weight-tied */
   float* out_b;        /* output.output.bias [V0] or NULL      */
+  float* w_ih_l[SAT_MAX_LAYERS - 1];   /* lstm.weight_ih_l{l} [4H0,H0], l = 1 .. decoder_layers-1 */
+  float* w_hh_l[SAT_MAX_LAYERS - 1];   /* lstm.weight_hh_l{l} [4H0,H0] */
+  float* b_ih_l[SAT_MAX_LAYERS - 1];   /* lstm.bias_ih_l{l} [4H0]      */
+  float* b_hh_l[SAT_MAX_LAYERS - 1];   /* lstm.bias_hh_l{l} [4H0]      */
   int32_t pad_idx;     /* embedding row whose own gradient is zero, -1 = none */
   int32_t weight_tying;/* 1: output.output.weight IS embedding.weight (model.py:198-199): its gradient is added into `embedding` */
 } SatParamGrads;

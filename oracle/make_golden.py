@@ -22,10 +22,10 @@ warnings.filterwarnings("ignore")
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def build(model, seed, D, A, E, H, V, label_smoothing=0.0, att_gamma=1.0, sharpen=None):
+def build(model, seed, D, A, E, H, V, label_smoothing=0.0, att_gamma=1.0, sharpen=None, layers=1):
     torch.manual_seed(seed)
     hp = rh.default_hparams(encoder_dim=D, attention_dim=A, embed_dim=E, decoder_dim=H, vocab_size=V,
-                            label_smoothing=label_smoothing, att_gamma=att_gamma, input_size=64)
+                            label_smoothing=label_smoothing, att_gamma=att_gamma, input_size=64, decoder_layers=layers)
     m = model.SAT(**hp)
     m.encoder = nn.Identity()
     if sharpen:
@@ -42,8 +42,8 @@ def weights_of(m):
     return {"W/" + k: v.detach().numpy().copy() for k, v in m.state_dict().items() if not k.startswith("encoder")}
 
 
-def train_case(model, name, seed, B_img, ncap, hw, D, A, E, H, V, T, ragged, label_smoothing, sharpen=None):
-    m = build(model, seed, D, A, E, H, V, label_smoothing, 1.0, sharpen)
+def train_case(model, name, seed, B_img, ncap, hw, D, A, E, H, V, T, ragged, label_smoothing, sharpen=None, layers=1):
+    m = build(model, seed, D, A, E, H, V, label_smoothing, 1.0, sharpen, layers)
     g = torch.Generator().manual_seed(seed + 1)
     ann = torch.randn(B_img, D, hw[0], hw[1], generator=g)
     ann.requires_grad_(True)
@@ -83,8 +83,8 @@ def train_case(model, name, seed, B_img, ncap, hw, D, A, E, H, V, T, ragged, lab
     print(name, "loss", loss.item(), "acc", acc.item(), "tokens", lp.data.shape[0])
 
 
-def decode_case(model, name, seed, n_img, hw, D, A, E, H, V, max_len, sharpen):
-    m = build(model, seed, D, A, E, H, V, 0.0, 1.0, sharpen)
+def decode_case(model, name, seed, n_img, hw, D, A, E, H, V, max_len, sharpen, layers=1):
+    m = build(model, seed, D, A, E, H, V, 0.0, 1.0, sharpen, layers)
     g = torch.Generator().manual_seed(seed + 1)
     ann = torch.randn(n_img, D, hw[0], hw[1], generator=g)
     out = weights_of(m)
@@ -223,11 +223,25 @@ def c1_case(model):
     print("c1_resnet18 loss", loss.item(), "training_step loss", float(ts["loss"]), "acc", acc.item())
 
 
+def layers_cases(model):
+    """decoder_layers > 1 (nn.LSTM num_layers, model.py:175-180): stacked states, attention / beta / output on h[-1]."""
+    # two layers, ragged, two captions per image, sizes that are NOT multiples of 8 (zero-padded storage on the device)
+    train_case(model, "train_layers2", 5, B_img=3, ncap=2, hw=(3, 4), D=16, A=8, E=10, H=14, V=50, T=6,
+               ragged=True, label_smoothing=0.1, sharpen=dict(fatt=20.0), layers=2)
+    # three layers, tile-sized dims, ragged
+    train_case(model, "train_layers3", 6, B_img=4, ncap=1, hw=(4, 4), D=64, A=32, E=32, H=64, V=128, T=10,
+               ragged=True, label_smoothing=0.05, sharpen=dict(fatt=10.0), layers=3)
+    decode_case(model, "decode_layers2", 7, n_img=5, hw=(4, 4), D=64, A=32, E=32, H=64, V=128, max_len=16,
+                sharpen=dict(wo=8.0, emb=2.0, fatt=30.0, end_bias=3.0), layers=2)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     model, _ = rh.load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "c1":
         return c1_case(model)
+    if len(sys.argv) > 1 and sys.argv[1] == "layers":
+        return layers_cases(model)
     # tiny, ragged, 2 captions per image, non-square map, label smoothing, peaky attention
     train_case(model, "train_tiny", 0, B_img=3, ncap=2, hw=(3, 4), D=16, A=8, E=10, H=14, V=50, T=6,
                ragged=True, label_smoothing=0.1, sharpen=dict(fatt=20.0))
@@ -242,6 +256,7 @@ def main():
                 sharpen=dict(wo=8.0, emb=2.0, fatt=30.0, end_bias=2.0))
     decode_case(model, "decode_small", 4, n_img=5, hw=(4, 4), D=64, A=32, E=32, H=64, V=128, max_len=16,
                 sharpen=dict(wo=8.0, emb=2.0, fatt=30.0, end_bias=3.0))
+    layers_cases(model)
     c1_case(model)
 
 

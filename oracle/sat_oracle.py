@@ -19,7 +19,9 @@ Weights are passed as a dict keyed by the reference's state_dict names (SURVEY.m
   attention.encoder_att.weight [A,D]; attention.decoder_att.weight [A,H]; attention.f_att.weight [1,A];
   beta.0.{weight [D,H],bias [D]}; output.hidden.weight [E,H]; output.context.weight [E,D];
   output.output.{weight [V,E], bias [V]}.
-Only decoder_layers == 1 is restated (the configurations of BASELINE.json).
+decoder_layers > 1 (nn.LSTM num_layers, model.py:175-180) adds lstm.{weight_ih,weight_hh,bias_ih,bias_hh}_l{l} ([4H,H] / [4H]) per
+layer l >= 1 and widens init_lstm.init to [2*layers*H, E]; the states are then [layers,B,H] and attention, the beta gate and
+the output layer read the top layer's state h[-1] (model.py:299-300,327,538-547).  With one layer the states stay [B,H].
 """
 import math
 
@@ -39,10 +41,26 @@ def init_lstm(W, ann):
     mean = ann.mean((2, 3))
     f1 = mean @ W["init_lstm.factorize.weight"].t() + W["init_lstm.factorize.bias"]
     out = f1 @ W["init_lstm.init.weight"].t() + W["init_lstm.init.bias"]
-    B = mean.shape[0]
-    H = out.shape[1] // 2
-    st = out.reshape(2, B, H)
-    return st[0], st[1]
+    return _split_init(W, out)
+
+
+def num_layers(W):
+    """decoder_layers of a weight dict (presence of lstm.weight_ih_l{l})."""
+    n = 1
+    while ("lstm.weight_ih_l%d" % n) in W:
+        n += 1
+    return n
+
+
+def _split_init(W, out):
+    """model.py:79-80: the [B, 2*layers*H] init output reinterpreted row-major as [2*layers, B, H]; first `layers` states are h."""
+    nl = num_layers(W)
+    B = out.shape[0]
+    H = out.shape[1] // (2 * nl)
+    st = out.reshape(2 * nl, B, H)
+    if nl == 1:
+        return st[0], st[1]
+    return st[:nl], st[nl:]
 
 
 def attention(W, ann, h):
@@ -64,12 +82,23 @@ def beta_gate(W, h):
 
 
 def lstm_cell(W, x, h, c):
-    """torch.nn.LSTM single layer, seq_len 1 (model.py:175-180,326,544): gate order i,f,g,o."""
-    G = x @ W["lstm.weight_ih_l0"].t() + W["lstm.bias_ih_l0"] + h @ W["lstm.weight_hh_l0"].t() + W["lstm.bias_hh_l0"]
-    i, f, g, o = G.chunk(4, dim=1)
-    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-    h2 = torch.sigmoid(o) * torch.tanh(c2)
-    return h2, c2
+    """torch.nn.LSTM, seq_len 1 (model.py:175-180,326,544): gate order i,f,g,o.  h, c [B,H] (one layer) or [layers,B,H]:
+    layer l > 0 takes the new hidden state of layer l-1 as its input (no dropout between layers: nn.LSTM(dropout=0))."""
+    def cell(l, x, h, c):
+        G = x @ W["lstm.weight_ih_l%d" % l].t() + W["lstm.bias_ih_l%d" % l] + h @ W["lstm.weight_hh_l%d" % l].t() + W["lstm.bias_hh_l%d" % l]
+        i, f, g, o = G.chunk(4, dim=1)
+        c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h2 = torch.sigmoid(o) * torch.tanh(c2)
+        return h2, c2
+
+    if h.dim() == 2:
+        return cell(0, x, h, c)
+    hs, cs = [], []
+    for l in range(h.shape[0]):
+        x, c2 = cell(l, x, h[l], c[l])
+        hs.append(x)
+        cs.append(c2)
+    return torch.stack(hs), torch.stack(cs)
 
 
 def deep_output(W, x_e, h, z, deep=True, drop=None):
@@ -91,10 +120,11 @@ def decoder_step(W, ann, words, h, c, deep=True, emb_drop=None, out_drop=None):
     x_e = W["embedding.weight"][words]
     if emb_drop is not None:
         x_e = x_e * emb_drop                      # embedding_dropout (model.py:526)
-    z, alpha = attention(W, ann, h)
-    beta = beta_gate(W, h)
+    htop = h if h.dim() == 2 else h[-1]
+    z, alpha = attention(W, ann, htop)
+    beta = beta_gate(W, htop)
     h2, c2 = lstm_cell(W, torch.cat([x_e, beta * z], dim=1), h, c)
-    logit = deep_output(W, x_e, h2, z, deep, out_drop)      # ungated z, new h
+    logit = deep_output(W, x_e, h2 if h2.dim() == 2 else h2[-1], z, deep, out_drop)      # ungated z, new (top) h
     return logit, alpha, h2, c2
 
 
@@ -123,8 +153,7 @@ def train_batch(W, ann_img, encoded_captions, lengths, epsilon=1.0, deep=True, r
         mean = ann.mean((2, 3)) * masks["mean"]
         f1 = mean @ W["init_lstm.factorize.weight"].t() + W["init_lstm.factorize.bias"]
         out0 = f1 @ W["init_lstm.init.weight"].t() + W["init_lstm.init.bias"]
-        st0 = out0.reshape(2, mean.shape[0], out0.shape[1] // 2)
-        h, c = st0[0], st0[1]
+        h, c = _split_init(W, out0)
     else:
         h, c = init_lstm(W, ann)
     h, c = h.clone(), c.clone()
@@ -146,11 +175,17 @@ def train_batch(W, ann_img, encoded_captions, lengths, epsilon=1.0, deep=True, r
             words = torch.argmax(logits[idx, step - 1, :], dim=1)   # model.py:523 (no grad path)
         ed = masks["emb"][idx, step] if masks is not None and masks.get("emb") is not None else None
         od = masks["out"][idx, step] if masks is not None and masks.get("out") is not None else None
-        logit, alpha, h2, c2 = decoder_step(W, ann[idx], words, h[idx], c[idx], deep, ed, od)
+        stacked = h.dim() == 3
+        logit, alpha, h2, c2 = decoder_step(W, ann[idx], words, h[:, idx] if stacked else h[idx], c[:, idx] if stacked else c[idx],
+                                            deep, ed, od)
         alphas = alphas.index_put((idx, torch.tensor(step)), alpha)
         logits = logits.index_put((idx, torch.tensor(step)), logit)
-        h = h.index_put((idx,), h2)
-        c = c.index_put((idx,), c2)
+        if stacked:
+            h = h.index_copy(1, idx, h2)
+            c = c.index_copy(1, idx, c2)
+        else:
+            h = h.index_put((idx,), h2)
+            c = c.index_put((idx,), c2)
     return logits, alphas, caps, lens
 
 
@@ -226,7 +261,7 @@ def caption(W, ann_img, vocab, beamk=3, max_gen_length=32, temperature=1.0,
                 wrd = torch.remainder(flat, V).unsqueeze(0)
                 preds = torch.cat([preds[:, src], wrd], 0)
                 alph = torch.cat([alph[:, src], alpha.unsqueeze(0)[:, src]], 0)
-                h, c, ann = h[src], c[src], ann[src]
+                h, c, ann = (h[:, src], c[:, src], ann[src]) if h.dim() == 3 else (h[src], c[src], ann[src])
             done = preds[step + 1] == END
 
             def rescore(s):
@@ -247,7 +282,7 @@ def caption(W, ann_img, vocab, beamk=3, max_gen_length=32, temperature=1.0,
                     f_ppl.append(float(torch.exp(-ds[i] / step)))
                 keep = ~done
                 preds, alph, top = preds[:, keep], alph[:, keep], top[keep]
-                h, c, ann = h[keep], c[keep], ann[keep]
+                h, c, ann = (h[:, keep], c[:, keep], ann[keep]) if h.dim() == 3 else (h[keep], c[keep], ann[keep])
                 k = int(keep.sum())
                 if k == 0:
                     break
@@ -301,7 +336,7 @@ def build_encoder(arch="resnet18", encoder_dim=512, encoder_size=None, input_siz
     return nn.Sequential(_Norm(), *layers)
 
 
-def random_weights(D, A, E, H, V, seed=0, dtype=torch.float32, sharpen=False):
+def random_weights(D, A, E, H, V, seed=0, dtype=torch.float32, sharpen=False, layers=1):
     """Synthetic decoder weights with torch-default-like scales (for sizes where no reference run is stored)."""
     g = torch.Generator().manual_seed(seed)
 
@@ -321,6 +356,11 @@ def random_weights(D, A, E, H, V, seed=0, dtype=torch.float32, sharpen=False):
         "output.hidden.weight": U((E, H), H), "output.context.weight": U((E, D), D),
         "output.output.weight": U((V, E), E), "output.output.bias": U((V,), E),
     }
+    if layers > 1:                             # drawn after the one-layer parameters: the layers=1 streams stay what they were
+        W["init_lstm.init.weight"], W["init_lstm.init.bias"] = U((2 * layers * H, E), E), U((2 * layers * H,), E)
+        for l in range(1, layers):
+            W["lstm.weight_ih_l%d" % l], W["lstm.weight_hh_l%d" % l] = U((4 * H, H), H), U((4 * H, H), H)
+            W["lstm.bias_ih_l%d" % l], W["lstm.bias_hh_l%d" % l] = U((4 * H,), H), U((4 * H,), H)
     W["embedding.weight"][0].zero_()          # padding_idx row
     if sharpen:                                # makes <END>/beam-shrink paths reachable
         W["output.output.weight"] *= 8

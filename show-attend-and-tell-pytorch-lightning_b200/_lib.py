@@ -11,24 +11,28 @@ LIB_PATH = os.path.join(_HERE, "libsat_b200.so")
 SAT_F32, SAT_BF16 = 0, 1
 
 vp, fp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # all device pointers travel as void*
+SAT_MAX_LAYERS = 4
+_vpl = vp * (SAT_MAX_LAYERS - 1)                   # per-layer pointers of the stacked LSTM layers l = 1 ..
 
 
 class SatDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("B", "Bi", "ncap", "L", "D", "A", "E", "H", "V", "T", "dtype", "exact", "use_tc", "plain_output",
-                 "D0", "A0", "E0", "H0", "V0", "reserved0")]
+                 "D0", "A0", "E0", "H0", "V0", "layers")]
 
 
 class SatWeights(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("Wa", "Whcat", "bhcat", "Wihz", "Wihe", "bg", "Whozo", "Wo", "bo", "wf", "Emb", "Wfact", "bfact",
-                 "Winit", "binit", "WoT", "WhozoT", "WihzT", "WiheT", "WhcatT", "WaT", "WinitT", "WfactT")]
+                 "Winit", "binit", "WoT", "WhozoT", "WihzT", "WiheT", "WhcatT", "WaT", "WinitT", "WfactT")] + \
+               [("Wl", _vpl), ("bgl", _vpl), ("WlT", _vpl)]
 
 
 class SatMasterWeights(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("embedding", "fact_w", "fact_b", "init_w", "init_b", "w_ih", "w_hh", "b_ih", "b_hh", "enc_att", "dec_att",
-                 "f_att", "beta_w", "beta_b", "out_hidden", "out_context", "out_w", "out_b")]
+                 "f_att", "beta_w", "beta_b", "out_hidden", "out_context", "out_w", "out_b")] + \
+               [("w_ih_l", _vpl), ("w_hh_l", _vpl), ("b_ih_l", _vpl), ("b_hh_l", _vpl)]
 
 
 class SatTrainBuffers(C.Structure):
@@ -36,7 +40,7 @@ class SatTrainBuffers(C.Structure):
                 ("ann", "caps", "lens", "sampled", "tok", "P", "meanv", "f1", "init_out", "Xe", "Gx", "Hs", "Cs", "hp", "Q", "alphas",
                  "Z", "GZ", "Beta", "Gates", "Xo", "logits", "dlogits", "row_loss", "row_argmax", "S", "out",
                  "ce_stats", "row_lse", "row_xt",
-                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dZ", "dP", "dP16", "dwf_part", "de", "dXe", "d_init_out",
+                 "gscale", "dalpha_ext", "dpre", "dHZ", "DY", "dgz", "dh", "dc", "dGl", "dxl", "dhq", "dZ", "dP", "dP16", "dwf_part", "de", "dXe", "d_init_out",
                  "df1", "d_init_out16", "df116", "dmean", "d_ann")] + \
                [("label_smoothing", C.c_float), ("att_gamma", C.c_float), ("dropout_p", C.c_float),
                 ("emb_dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("logits_f32", C.c_int32),
@@ -58,6 +62,7 @@ class SatParamGrads(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("embedding", "fact_w", "fact_b", "init_w", "init_b", "w_ih", "w_hh", "b_ih", "b_hh", "enc_att", "dec_att",
                  "f_att", "beta_w", "beta_b", "out_hidden", "out_context", "out_w", "out_b")] + \
+               [("w_ih_l", _vpl), ("w_hh_l", _vpl), ("b_ih_l", _vpl), ("b_hh_l", _vpl)] + \
                [("pad_idx", C.c_int32), ("weight_tying", C.c_int32)]
 
 

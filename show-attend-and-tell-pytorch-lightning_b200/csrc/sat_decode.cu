@@ -32,10 +32,12 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   SAT_COUNT_LAUNCH();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.meanv, D, D), (const TS*)w.Wfact, D, n_img, E,
                            EpiStore<TS>{(TS*)b.f1, E, w.bfact, nullptr, 0}, st)));
-  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.f1, E, E), (const TS*)w.Winit, E, n_img, 2 * H,
-                           EpiStore<float>{b.init_out, 2 * H, w.binit, nullptr, 0}, st)));
-  init_state_decode_kernel<TS><<<(unsigned)(((int64_t)R * H + 255) / 256), 256, 0, st>>>(b.init_out, 2 * H, (TS*)b.h, b.c, n_img, k,
-                                                                                         d.H0 ? d.H0 : H, H);
+  const int nl = d.layers > 1 ? d.layers : 1;
+  const int64_t RH = (int64_t)R * H;             // one layer of the state arrays
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.f1, E, E), (const TS*)w.Winit, E, n_img, 2 * nl * H,
+                           EpiStore<float>{b.init_out, 2 * nl * H, w.binit, nullptr, 0}, st)));
+  init_state_decode_kernel<TS><<<(unsigned)((nl * RH + 255) / 256), 256, 0, st>>>(b.init_out, 2 * nl * H, (TS*)b.h, b.c, n_img, k,
+                                                                                  d.H0 ? d.H0 : H, H, nl);
   SAT_COUNT_LAUNCH();
   decode_init_kernel<<<(R + 255) / 256, 256, 0, st>>>(b.cur_tok, b.alive, b.top_scores, b.kcur, b.fin_count, b.fin_len, R, n_img, k,
                                                       b.tokSTART);
@@ -73,19 +75,22 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   // instead of being gathered by source row
   void* h_cur = b.h; float* c_cur = b.c; void* h_nxt = b.hn; float* c_nxt = b.cn;
   for (int step = 0; step <= S; ++step) {
-    if (!noisy) {
+    const TS* h_top = (const TS*)h_cur + (nl - 1) * RH;      // attention, beta gate and the output layer read the top layer (model.py:299-300,327)
+    if (!noisy && nl == 1) {
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
                                st)));
     } else {
-      // decoder noise: attention and the beta gate read the clean state, the recurrent projection W_hh (h + noise) the noisy one
-      const int64_t nh = (int64_t)R * H;
-      SAT_CUDA(sat_launch_pdl(noisy_state_kernel<TS>, dim3((unsigned)((nh + 255) / 256)), dim3(256), 0, st, (const TS*)h_cur, (TS*)b.h_noisy, nh,
-                              b.decoder_noise / (float)(step + 1), b.sample_seed, step));
-      SAT_COUNT_LAUNCH();
-      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, A + D, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
+      // decoder noise: attention and the beta gate read the clean state, the recurrent projections W_hh (h + noise) the noisy
+      // one (every layer's state gets noise, model.py:324)
+      if (noisy) {
+        SAT_CUDA(sat_launch_pdl(noisy_state_kernel<TS>, dim3((unsigned)((nl * RH + 255) / 256)), dim3(256), 0, st, (const TS*)h_cur,
+                                (TS*)b.h_noisy, nl * RH, b.decoder_noise / (float)(step + 1), b.sample_seed, step));
+        SAT_COUNT_LAUNCH();
+      }
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_top, H, H), (const TS*)w.Whcat, H, R, A + D, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
                                st)));
-      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.h_noisy, H, H), (const TS*)w.Whcat + (int64_t)(A + D) * H, H, R, 4 * H,
-                               EpiStore<float>{b.hp + A + D, NH3, nullptr, nullptr, 0}, st)));
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(noisy ? (const TS*)b.h_noisy : (const TS*)h_cur, H, H), (const TS*)w.Whcat + (int64_t)(A + D) * H, H,
+                               R, 4 * H, EpiStore<float>{b.hp + A + D, NH3, nullptr, nullptr, 0}, st)));
     }
     SAT_PROF(1, st);
     SAT_TRY((launch_attention_fwd<TS, kExact>(ann, (const TS*)b.P, w.wf, b.hp, NH3, b.alive, 0, R, k, L, D, A, scale,
@@ -95,7 +100,13 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
     EpiLstm<TS, kExact> epi{b.GxV, 4 * H, b.hp + A + D, NH3, (const TS*)h_cur, c_cur, (TS*)h_nxt, c_nxt, H, H,
                             (TS*)nullptr, 0, b.alive, 0, b.cur_tok};
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.gz, D, D), (const TS*)w.Wihz, D, R, 4 * H, epi, st)));
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(h_nxt, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
+    for (int l = 1; l < nl; ++l) {      // stacked layers: input = the new state of the layer below
+      const TS* hl = (noisy ? (const TS*)b.h_noisy : (const TS*)h_cur) + l * RH;
+      EpiLstm<TS, kExact> epl{w.bgl[l - 1], 0, nullptr, 0, (const TS*)h_cur + l * RH, c_cur + l * RH, (TS*)h_nxt + l * RH, c_nxt + l * RH, H, H,
+                              (TS*)nullptr, 0, b.alive, 0, nullptr};
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)h_nxt + (l - 1) * RH, H, H, hl, H, H), (const TS*)w.Wl[l - 1], 2 * H, R, 4 * H, epl, st)));
+    }
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)h_nxt + (nl - 1) * RH, H, H, b.z, D, D), (const TS*)w.Whozo, H + D, R, E,
                              EpiTanhAdd<TS, kExact>{(const TS*)w.Emb, (TS*)b.xo, E, b.cur_tok, d.plain_output, 0.0f, 0ull, 0}, st)));
     SAT_PROF(3, st);
     if (fuse_greedy) {
@@ -133,9 +144,9 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
       void* th = h_cur; h_cur = h_nxt; h_nxt = th;
       float* tcp = c_cur; c_cur = c_nxt; c_nxt = tcp;
     } else {
-      SAT_CUDA(sat_launch_pdl(gather_state_kernel<TS>, dim3((unsigned)(((int64_t)R * H + 255) / 256)), dim3(256), 0, st,
+      SAT_CUDA(sat_launch_pdl(gather_state_kernel<TS>, dim3((unsigned)((nl * RH + 255) / 256)), dim3(256), 0, st,
                               (const TS*)b.hn, (const float*)b.cn, (const int32_t*)b.src_row, (const int32_t*)b.alive, (TS*)b.h, b.c, R,
-                              H));
+                              H, nl));
       SAT_COUNT_LAUNCH();
     }
   }

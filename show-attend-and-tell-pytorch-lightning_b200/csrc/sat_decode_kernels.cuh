@@ -14,18 +14,25 @@ enum { SAT_RESCORE_NONE = 0, SAT_RESCORE_LN = 1, SAT_RESCORE_WR = 2, SAT_RESCORE
 //   h0[j] = o[(j % 2) * H : ...],  c0[j] = o[((k + j) % 2) * H : ...]   where o = init_out[img] ([2H]).
 template <typename T>
 __global__ void init_state_decode_kernel(const float* __restrict__ init_out, int64_t ld_io, T* __restrict__ h0, float* __restrict__ c0,
-                                         int n_img, int k, int H, int ld) {
-  // H = the module's true decoder_dim (the rule indexes the [2H] init vector); ld = storage pitch of the state rows
-  // (columns H..ld are padding and get zeros)
+                                         int n_img, int k, int H, int ld, int nl) {
+  // The k rows of an image are identical, so the [k, 2*nl*H] init output read row-major as [2*nl, k, H] (model.py:79-80,
+  // 265-269) gives state st, beam j, unit jj the element o[(st*k*H + j*H + jj) mod (2*nl*H)] of the image's init vector o.
+  // H = the module's true decoder_dim; ld = storage pitch of the state rows (columns H..ld are padding and get zeros);
+  // layer l of h / c lives at h0 + l * n_img*k*ld.
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)n_img * k * ld) return;
-  const int jj = (int)(idx % ld);
-  const int64_t row = idx / ld;
+  const int64_t per = (int64_t)n_img * k * ld;
+  if (idx >= nl * per) return;
+  const int l = (int)(idx / per);
+  const int64_t rem = idx - l * per;
+  const int jj = (int)(rem % ld);
+  const int64_t row = rem / ld;
   const int j = (int)(row % k);
   const int64_t n = row / k;
   const float* o = init_out + n * ld_io;
-  h0[idx] = from_f<T>(jj < H ? o[(j % 2) * H + jj] : 0.0f);
-  c0[idx] = jj < H ? o[((k + j) % 2) * H + jj] : 0.0f;
+  const int64_t W2 = 2 * (int64_t)nl * H;
+  const int64_t fh = ((int64_t)l * k + j) * H + jj, fc = ((int64_t)(nl + l) * k + j) * H + jj;
+  h0[idx] = from_f<T>(jj < H ? o[fh % W2] : 0.0f);
+  c0[idx] = jj < H ? o[fc % W2] : 0.0f;
 }
 
 // scores = log_softmax(logit / temp) (model.py:330); <START>,<PAD> -> -inf (model.py:333); step 0 also
@@ -522,17 +529,19 @@ beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, c
 // h, c <- hn, cn gathered by source row (model.py:397); dead rows are left alone.
 template <typename T>
 __global__ void gather_state_kernel(const T* __restrict__ hn, const float* __restrict__ cn, const int32_t* __restrict__ src_row,
-                                    const int32_t* __restrict__ alive, T* __restrict__ h, float* __restrict__ c, int R, int H) {
+                                    const int32_t* __restrict__ alive, T* __restrict__ h, float* __restrict__ c, int R, int H, int nl) {
   SAT_PDL_TRIGGER();
   SAT_PDL_WAIT();
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)R * H) return;
-  const int64_t r = idx / H;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over [layers, R, H]: R = rows of ONE layer
+  const int64_t RH = (int64_t)R * H;
+  const int64_t l = idx / RH, rem = idx - l * RH;
+  if (l >= nl) return;
+  const int64_t r = rem / H;
   if (alive[r] == 0) return;
-  const int j = (int)(idx - r * H);
+  const int j = (int)(rem - r * H);
   const int64_t s = src_row[r];
-  h[idx] = hn[s * H + j];
-  c[idx] = cn[s * H + j];
+  h[idx] = hn[l * RH + s * H + j];
+  c[idx] = cn[l * RH + s * H + j];
 }
 
 static __global__ void decode_init_kernel(int32_t* cur_tok, int32_t* alive, float* top_scores, int32_t* kcur, int32_t* fin_count,

@@ -307,8 +307,8 @@ struct EpiLstm {
     c.active = t < lens[m];
     c.cp = c_prev[(int64_t)m * ldst_c + (n >> 2)];
     if (c.active) {
-      c.gx = ld4(Gx + (int64_t)(gx_row ? gx_row[m] : m) * ldgx + n);
-      c.gh = ld4(Gh + (int64_t)m * ldgh + n);
+      c.gx = ld4(Gx + (int64_t)(gx_row ? gx_row[m] : m) * ldgx + n);      // ldgx = 0: one bias row for every m (stacked layers)
+      c.gh = Gh ? ld4(Gh + (int64_t)m * ldgh + n) : make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       c.gx = c.gh = make_float4(0.f, 0.f, 0.f, 0.f);
     }

@@ -223,32 +223,36 @@ __global__ void __launch_bounds__(256) mean_L_kernel(const T* __restrict__ ann, 
 // =============================================================================================
 template <typename T>
 __global__ void init_state_kernel(const float* __restrict__ init_out, int64_t ld_io, T* __restrict__ h0, float* __restrict__ c0,
-                                  int64_t ld_h, int64_t ld_c, int B, int H, int ncap) {
+                                  int64_t ld_h, int64_t ld_c, int64_t lstride_h, int64_t lstride_c, int B, int H, int ncap, int nl) {
   // H is the module's TRUE decoder_dim (the reinterpretation mixes rows and columns, so it must not see the padding);
-  // ld_io / ld_h / ld_c are the storage pitches.  Padded state columns are zeroed by the caller.
+  // ld_io / ld_h / ld_c are the storage pitches, lstride_* the distance between the layers' state arrays.  The [B, 2*nl*H]
+  // init output is read row-major as [2*nl, B, H]: states 0..nl-1 are h of the layers, nl..2nl-1 their c (model.py:79-80).
+  // Padded state columns are zeroed by the caller.
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t BH = (int64_t)B * H;
-  if (idx >= 2 * BH) return;
-  const int64_t r = idx / (2 * H);          // row of the (virtual) repeated [B,2H] matrix
-  const int col = (int)(idx - r * 2 * H);
+  if (idx >= 2 * nl * BH) return;
+  const int64_t r = idx / (2 * nl * H);     // row of the (virtual) repeated [B, 2*nl*H] matrix
+  const int col = (int)(idx - r * 2 * nl * H);
   const float v = init_out[(r / ncap) * ld_io + col];
-  if (idx < BH) {
-    const int64_t b = idx / H;
-    const int j = (int)(idx - b * H);
-    h0[b * ld_h + j] = from_f<T>(v);
-  } else {
-    const int64_t k = idx - BH;
-    const int64_t b = k / H;
-    const int j = (int)(k - b * H);
-    c0[b * ld_c + j] = v;
-  }
+  const int st = (int)(idx / BH);
+  const int64_t g = idx - (int64_t)st * BH;
+  const int64_t b = g / H;
+  const int j = (int)(g - b * H);
+  if (st < nl) h0[st * lstride_h + b * ld_h + j] = from_f<T>(v);
+  else c0[(st - nl) * lstride_c + b * ld_c + j] = v;
 }
 
-// inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i
-// (H = true decoder_dim; ld_st = storage pitch of dh0 / dc0 rows; ld_io = pitch of d_init_out, whose padding gets zeros)
-static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int ns_dh, int64_t dh_stride,
-                                             const float* __restrict__ dc0, int64_t ld_st, float* __restrict__ d_init_out,
-                                             bf16* __restrict__ d_init_out16, int64_t ld_io, int B, int H, int ncap) {
+// inverse of the above for the backward pass: d_init_out[i, col] = sum over the ncap caption rows of image i of the state
+// gradient that element fed.  dh0 of layer l: ns_dh[l] split-K partials at dh0[l] (see the backward driver); dc0: [nl,B,ld_st].
+struct InitBwdSrc {
+  const float* p[SAT_MAX_LAYERS][2];   // up to two partial sets per layer (recurrent GEMM, q/beta GEMM)
+  int ns[SAT_MAX_LAYERS][2];
+  int64_t stride[SAT_MAX_LAYERS][2];   // distance between partials
+  int64_t ld[SAT_MAX_LAYERS][2];       // row pitch
+};
+static __global__ void init_state_bwd_kernel(const __grid_constant__ InitBwdSrc src, const float* __restrict__ dc0, int64_t ld_st,
+                                             int64_t lstride_c, float* __restrict__ d_init_out, bf16* __restrict__ d_init_out16,
+                                             int64_t ld_io, int B, int H, int ncap, int nl) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [Bi, ld_io]
   const int Bi = B / ncap;
   if (idx >= (int64_t)Bi * ld_io) return;
@@ -256,16 +260,18 @@ static __global__ void init_state_bwd_kernel(const float* __restrict__ dh0, int 
   const int col = (int)(idx - i * ld_io);
   const int64_t BH = (int64_t)B * H;
   float s = 0.0f;
-  if (col < 2 * H) {
+  if (col < 2 * nl * H) {
     for (int c = 0; c < ncap; ++c) {
       const int64_t r = i * ncap + c;
-      const int64_t f = r * 2 * H + col;          // flat index into the [2,B,H] view
-      if (f < BH) {
-        const int64_t b = f / H, j = f - b * H;
-        for (int sp = 0; sp < ns_dh; ++sp) s += dh0[(int64_t)sp * dh_stride + b * ld_st + j];
+      const int64_t f = r * 2 * nl * H + col;     // flat index into the [2*nl,B,H] view
+      const int st = (int)(f / BH);
+      const int64_t g = f - (int64_t)st * BH;
+      const int64_t b = g / H, j = g - b * H;
+      if (st < nl) {
+        for (int q = 0; q < 2; ++q)
+          for (int sp = 0; sp < src.ns[st][q]; ++sp) s += src.p[st][q][(int64_t)sp * src.stride[st][q] + b * src.ld[st][q] + j];
       } else {
-        const int64_t k = f - BH, b = k / H, j = k - b * H;
-        s += dc0[b * ld_st + j];
+        s += dc0[(st - nl) * lstride_c + b * ld_st + j];
       }
     }
   }
@@ -511,10 +517,15 @@ loss_finalize_kernel(const float* __restrict__ row_loss, const int32_t* __restri
 //   Writes dG (gate-interleaved, pre-activation grads) into DY[t,:,A+D:], updates dc in place and
 //   leaves dh untouched (the h-chain GEMM that follows overwrites it for active rows).
 // =============================================================================================
+struct DhSrc {                 // gradient contributions to this layer's new hidden state, summed in fixed order
+  const float* p[3];           // partial sets: [ns][B rows at pitch ld][H]
+  int ns[3];
+  int64_t stride[3], ld[3];
+};
 template <typename TS, bool kExact>
 __global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* __restrict__ c_prev,
-                                     const float* __restrict__ c_next, const float* __restrict__ dh, int ns_dh,
-                                     int64_t dh_stride, const float* __restrict__ dHo, int64_t ld_dho, float* __restrict__ dc,
+                                     const float* __restrict__ c_next, const __grid_constant__ DhSrc dh,
+                                     const float* __restrict__ dHo, int64_t ld_dho, float* __restrict__ dc,
                                      TS* __restrict__ dG, int64_t ld_dg, const int32_t* __restrict__ lens, int t, int B,
                                      int H) {
   SAT_PDL_TRIGGER();
@@ -528,14 +539,18 @@ __global__ void lstm_bwd_step_kernel(const TS* __restrict__ gates, const float* 
   const int len_b = lens[b];
   const float4 g4 = ld4(gates + (int64_t)b * 4 * H + 4 * j);
   const float cp = c_prev[idx], cn = c_next[idx];
-  const float dho = dHo[(int64_t)b * ld_dho + j], dc_in = dc[idx];
+  const float dho = dHo ? dHo[(int64_t)b * ld_dho + j] : 0.0f, dc_in = dc[idx];
   float dhs = 0.0f;
-  for (int sp0 = 0; sp0 < ns_dh; sp0 += 8) {      // split-K partials of the h-chain GEMM, 8 loads in flight
-    float p[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) p[u] = (sp0 + u) < ns_dh ? dh[(int64_t)(sp0 + u) * dh_stride + idx] : 0.0f;
+  for (int q = 0; q < 3; ++q) {
+    const float* base = dh.p[q] + (int64_t)b * dh.ld[q] + j;
+    for (int sp0 = 0; sp0 < dh.ns[q]; sp0 += 8) {      // split-K partials, 8 loads in flight
+      float p[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) dhs += p[u];
+      for (int u = 0; u < 8; ++u) p[u] = (sp0 + u) < dh.ns[q] ? base[(int64_t)(sp0 + u) * dh.stride[q]] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dhs += p[u];
+    }
   }
   if (t >= len_b) {
     st4(dg, make_float4(0.f, 0.f, 0.f, 0.f));

@@ -18,7 +18,7 @@ struct PackJob {
   int tile0;            // first 32x32 tile of this job in the grid
 };
 
-constexpr int MAXJOBS = 40;
+constexpr int MAXJOBS = 48;
 struct PackTable {
   PackJob job[MAXJOBS];
   int njobs;
@@ -94,6 +94,8 @@ extern "C" int sat_pack_weights(const SatDims* d, const SatMasterWeights* m, con
   const int D0 = d->D0 ? d->D0 : D, A0 = d->A0 ? d->A0 : A, E0 = d->E0 ? d->E0 : E, H0 = d->H0 ? d->H0 : H, V0 = d->V0 ? d->V0 : V;
   SAT_REQUIRE(D0 <= D && A0 <= A && E0 <= E && H0 <= H && V0 <= V, "sat_pack_weights: true dims exceed the storage dims");
   const int NH3 = A + D + 4 * H, NH4 = NH3 + E;
+  const int nl = d->layers > 1 ? d->layers : 1;
+  SAT_REQUIRE(nl <= SAT_MAX_LAYERS, "decoder_layers %d > %d", nl, SAT_MAX_LAYERS);
   SAT_REQUIRE(m->embedding && m->w_ih && m->w_hh && m->b_ih && m->b_hh && m->enc_att && m->dec_att && m->f_att && m->beta_w &&
                   m->beta_b && m->out_hidden && m->out_w && m->fact_w && m->fact_b && m->init_w && m->init_b,
               "sat_pack_weights: missing master parameter");
@@ -116,8 +118,16 @@ extern "C" int sat_pack_weights(const SatDims* d, const SatMasterWeights* m, con
   if (w->Emb != w->Wo) b.add(m->embedding, nullptr, w->Emb, V0, E0, E0, E, 0, 0, 0, 0, 0);
   b.add(m->fact_w, nullptr, w->Wfact,    E0,     D0,   D0,      D,      0,       0, 0,  0, 0);
   b.add(m->fact_b, nullptr, w->bfact,    1,      E0,   E0,      E,      0,       0, 0,  0, 1);
-  b.add(m->init_w, nullptr, w->Winit,    2 * H0, E0,   E0,      E,      0,       0, 0,  0, 0);
-  b.add(m->init_b, nullptr, w->binit,    1,      2 * H0, 2 * H0, 2 * H, 0,       0, 0,  0, 1);
+  b.add(m->init_w, nullptr, w->Winit,    2 * nl * H0, E0, E0,   E,      0,       0, 0,  0, 0);
+  b.add(m->init_b, nullptr, w->binit,    1,      2 * nl * H0, 2 * nl * H0, 2 * nl * H, 0, 0, 0, 0, 1);
+  for (int l = 1; l < nl; ++l) {      // stacked layers: [W_ih_l | W_hh_l] gate-interleaved, summed biases, transposed copy
+    SAT_REQUIRE(m->w_ih_l[l - 1] && m->w_hh_l[l - 1] && m->b_ih_l[l - 1] && m->b_hh_l[l - 1], "sat_pack_weights: parameters of LSTM layer %d missing", l);
+    b.add(m->w_ih_l[l - 1], nullptr, w->Wl[l - 1], 4 * H0, H0, H0, 2 * H, 0, 0, H0, 0, 0);
+    b.add(m->w_hh_l[l - 1], nullptr, w->Wl[l - 1], 4 * H0, H0, H0, 2 * H, 0, H, H0, 0, 0);
+    b.add(m->b_ih_l[l - 1], m->b_hh_l[l - 1], w->bgl[l - 1], 4 * H0, 1, 1, 1, 0, 0, H0, 0, 1);
+    b.add(m->w_ih_l[l - 1], nullptr, w->WlT[l - 1], 4 * H0, H0, H0, 4 * H, 0, 0, H0, 1, 0);
+    b.add(m->w_hh_l[l - 1], nullptr, w->WlT[l - 1], 4 * H0, H0, H0, 4 * H, H, 0, H0, 1, 0);
+  }
   // transposed copies for the backward GEMMs (skipped when the destination pointers are NULL)
   b.add(m->out_w, nullptr, w->WoT,       V0,     E0,   E0,      V,      0,       0, 0,  1, 0);
   b.add(m->out_hidden, nullptr, w->WhozoT, E0,   H0,   H0,      E,      0,       0, 0,  1, 0);
@@ -128,7 +138,7 @@ extern "C" int sat_pack_weights(const SatDims* d, const SatMasterWeights* m, con
   b.add(m->beta_w, nullptr, w->WhcatT,   D0,     H0,   H0,      NH3,    0,       A, 0,  1, 0);
   b.add(m->w_hh, nullptr, w->WhcatT,     4 * H0, H0,   H0,      NH3,    0,       A + D, H0, 1, 0);
   b.add(m->enc_att, nullptr, w->WaT,     A0,     D0,   D0,      A,      0,       0, 0,  1, 0);
-  b.add(m->init_w, nullptr, w->WinitT,   2 * H0, E0,   E0,      2 * H,  0,       0, 0,  1, 0);
+  b.add(m->init_w, nullptr, w->WinitT,   2 * nl * H0, E0, E0,   2 * nl * H, 0,   0, 0,  1, 0);
   b.add(m->fact_w, nullptr, w->WfactT,   E0,     D0,   D0,      E,      0,       0, 0,  1, 0);
   SAT_REQUIRE(b.ok, "sat_pack_weights: job table overflow");
   cudaStream_t st = (cudaStream_t)stream;

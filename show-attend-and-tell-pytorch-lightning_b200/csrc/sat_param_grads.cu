@@ -154,7 +154,7 @@ struct FinJob {
   int accumulate;          // dst += (weight tying: dW_o is added to the embedding gradient)
   int blk0;                // first 256-element block of this job in the grid
 };
-constexpr int FIN_MAXJOBS = 24;
+constexpr int FIN_MAXJOBS = 40;
 struct FinTable {
   FinJob job[FIN_MAXJOBS];
   int njobs;
@@ -217,8 +217,11 @@ struct FinBuilder {
 };
 
 // ---- plan: the weight-gradient GEMMs, their split factors and the workspace layout (a pure function of the dims) ------
-enum { G_WO = 0, G_WHO, G_WZO, G_WH3, G_WIHE, G_WIHZ, G_WA, G_WINIT, G_WFACT, G_COUNT };
-enum { C_BO = 0, C_DY, C_WF, C_INIT, C_FACT, C_COUNT };
+// stacked LSTM layers l >= 1 add G_WHH0 (layer 0's recurrent weight, split from G_WH3 because q / beta read the top layer) and,
+// per layer, G_WLI + l-1 (weight_ih_l{l}), G_WLH + l-1 (weight_hh_l{l}) and the bias column sum C_GL + l-1
+enum { G_WO = 0, G_WHO, G_WZO, G_WH3, G_WIHE, G_WIHZ, G_WA, G_WINIT, G_WFACT, G_WHH0, G_WLI, G_WLH = G_WLI + SAT_MAX_LAYERS - 1,
+       G_COUNT = G_WLH + SAT_MAX_LAYERS - 1 };
+enum { C_BO = 0, C_DY, C_WF, C_INIT, C_FACT, C_GL, C_COUNT = C_GL + SAT_MAX_LAYERS - 1 };
 struct Plan {
   int n1[G_COUNT], n2[G_COUNT], kr[G_COUNT], sk[G_COUNT];
   int64_t off[G_COUNT];                 // float offsets into the workspace
@@ -237,11 +240,17 @@ static Plan make_plan(const SatDims& d) {
   set(G_WO, V, E, M);
   set(G_WHO, E, H, M);
   set(G_WZO, E, D, M);
-  set(G_WH3, NH3, H, M);
+  const int nl = d.layers > 1 ? d.layers : 1;
+  set(G_WH3, nl == 1 ? NH3 : A + D, H, M);
+  set(G_WHH0, nl == 1 ? 0 : 4 * H, H, M);
+  for (int l = 1; l < SAT_MAX_LAYERS; ++l) {
+    set(G_WLI + l - 1, l < nl ? 4 * H : 0, H, M);
+    set(G_WLH + l - 1, l < nl ? 4 * H : 0, H, M);
+  }
   set(G_WIHE, 4 * H, E, M);
   set(G_WIHZ, 4 * H, D, M);
   set(G_WA, A, D, Bi * L);
-  set(G_WINIT, 2 * H, E, Bi);
+  set(G_WINIT, 2 * nl * H, E, Bi);
   set(G_WFACT, E, D, Bi);
   int64_t o = 0;
   for (int g = 0; g < G_COUNT; ++g) {
@@ -260,8 +269,9 @@ static Plan make_plan(const SatDims& d) {
   cs(C_BO, M, V);
   cs(C_DY, M, NH3);
   cs(C_WF, M, A);
-  cs(C_INIT, Bi, 2 * H);
+  cs(C_INIT, Bi, 2 * nl * H);
   cs(C_FACT, Bi, E);
+  for (int l = 1; l < SAT_MAX_LAYERS; ++l) cs(C_GL + l - 1, l < nl ? M : 0, 4 * H);
   p.dpimg_off = o;
   if (d.ncap > 1) o += (int64_t)Bi * L * A;
   p.total_floats = o;
@@ -294,10 +304,23 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   const TS* dlog = (const TS*)b.dlogits;
   const TS* DY = (const TS*)b.DY;
   const TS* Hs = (const TS*)b.Hs;
+  const int nl = d.layers > 1 ? d.layers : 1;
+  const int64_t LS = (int64_t)(T + 1) * B * H, GS = (int64_t)T * B * 4 * H;
+  const TS* Hs_top = Hs + (nl - 1) * LS;
   SAT_TRY(nt(G_WO, dlog, V, true, b.Xo, E));
-  SAT_TRY(nt(G_WHO, b.dpre, E, true, Hs + (int64_t)B * H, H));
+  SAT_TRY(nt(G_WHO, b.dpre, E, true, Hs_top + (int64_t)B * H, H));
   if (!d.plain_output) SAT_TRY(nt(G_WZO, b.dpre, E, true, b.Z, D));
-  SAT_TRY(nt(G_WH3, DY, NH3, true, Hs, H));
+  SAT_TRY(nt(G_WH3, DY, NH3, true, Hs_top, H));          // one layer: [dq | dbeta_pre | dG]^T h;  stacked: [dq | dbeta_pre]^T h_top
+  if (nl > 1) {
+    SAT_REQUIRE(b.dGl, "sat_train_param_grads: decoder_layers > 1 needs dGl");
+    SAT_TRY(nt(G_WHH0, DY + A + D, NH3, true, Hs, H));
+    for (int l = 1; l < nl; ++l) {
+      const TS* dG_l = (const TS*)b.dGl + (l - 1) * GS;
+      SAT_TRY(nt(G_WLI + l - 1, dG_l, 4 * H, true, Hs + (l - 1) * LS + (int64_t)B * H, H));   // input: the new state of the layer below
+      SAT_TRY(nt(G_WLH + l - 1, dG_l, 4 * H, true, Hs + l * LS, H));
+      SAT_TRY(launch_colsum<TS>(dG_l, 4 * H, M, 4 * H, ws + p.cs_off[C_GL + l - 1], st));
+    }
+  }
   SAT_TRY(nt(G_WIHE, DY + A + D, NH3, true, b.Xe, E));
   SAT_TRY(nt(G_WIHZ, DY + A + D, NH3, true, b.GZ, D));
   // dW_a = dP^T ann over the Bi*L image locations (dP summed over the captions of an image first when ncap > 1)
@@ -326,10 +349,10 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   {
     const bool have16 = tc && b.d_init_out16 != nullptr && b.df116 != nullptr;
     if (have16) {
-      SAT_TRY(nt(G_WINIT, b.d_init_out16, 2 * H, true, b.f1, E));
+      SAT_TRY(nt(G_WINIT, b.d_init_out16, 2 * nl * H, true, b.f1, E));
       SAT_TRY(nt(G_WFACT, b.df116, E, true, b.meanv, D));
     } else {
-      SAT_TRY(nt(G_WINIT, b.d_init_out, 2 * H, std::is_same<TS, float>::value, b.f1, E));
+      SAT_TRY(nt(G_WINIT, b.d_init_out, 2 * nl * H, std::is_same<TS, float>::value, b.f1, E));
       SAT_TRY(nt(G_WFACT, b.df1, E, std::is_same<TS, float>::value, b.meanv, D));
     }
   }
@@ -337,7 +360,7 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   if (g.out_b) SAT_TRY(launch_colsum<TS>(dlog, V, M, V, ws + p.cs_off[C_BO], st));
   SAT_TRY(launch_colsum<TS>(DY, NH3, M, NH3, ws + p.cs_off[C_DY], st));
   SAT_TRY(launch_colsum<float>(b.dwf_part, A, M, A, ws + p.cs_off[C_WF], st));
-  SAT_TRY(launch_colsum<float>(b.d_init_out, 2 * H, Bi, 2 * H, ws + p.cs_off[C_INIT], st));
+  SAT_TRY(launch_colsum<float>(b.d_init_out, 2 * nl * H, Bi, 2 * nl * H, ws + p.cs_off[C_INIT], st));
   SAT_TRY(launch_colsum<float>(b.df1, E, Bi, E, ws + p.cs_off[C_FACT], st));
   // embedding: segment sum of dXe by the word that was fed
   if (g.embedding) {
@@ -364,11 +387,18 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   if (!d.plain_output) gj(G_WZO, 0, 0, g.out_context, D0, 0, E0, D0, 0, 0, 0);
   gj(G_WH3, 0, 0, g.dec_att, H0, 0, A0, H0, 0, 0, 0);
   gj(G_WH3, A, 0, g.beta_w, H0, 0, D0, H0, 0, 0, 0);
-  gj(G_WH3, A + D, 0, g.w_hh, H0, 0, 4 * H0, H0, H0, 0, 0);
+  if (nl == 1) gj(G_WH3, A + D, 0, g.w_hh, H0, 0, 4 * H0, H0, H0, 0, 0);
+  else gj(G_WHH0, 0, 0, g.w_hh, H0, 0, 4 * H0, H0, H0, 0, 0);
+  for (int l = 1; l < nl; ++l) {
+    gj(G_WLI + l - 1, 0, 0, g.w_ih_l[l - 1], H0, 0, 4 * H0, H0, H0, 0, 0);
+    gj(G_WLH + l - 1, 0, 0, g.w_hh_l[l - 1], H0, 0, 4 * H0, H0, H0, 0, 0);
+    cj(C_GL + l - 1, 0, g.b_ih_l[l - 1], 4 * H0, H0);
+    cj(C_GL + l - 1, 0, g.b_hh_l[l - 1], 4 * H0, H0);
+  }
   gj(G_WIHE, 0, 0, g.w_ih, E0 + D0, 0, 4 * H0, E0, H0, 0, 0);
   gj(G_WIHZ, 0, 0, g.w_ih, E0 + D0, E0, 4 * H0, D0, H0, 0, 0);
   gj(G_WA, 0, 0, g.enc_att, D0, 0, A0, D0, 0, 0, 0);
-  gj(G_WINIT, 0, 0, g.init_w, E0, 0, 2 * H0, E0, 0, 0, 0);
+  gj(G_WINIT, 0, 0, g.init_w, E0, 0, 2 * nl * H0, E0, 0, 0, 0);
   gj(G_WFACT, 0, 0, g.fact_w, D0, 0, E0, D0, 0, 0, 0);
   if (g.out_b) {
     const int nch = (M + CS_ROWS - 1) / CS_ROWS;
@@ -378,7 +408,7 @@ int param_grads_impl(const SatDims& d, const SatTrainBuffers& b, const SatParamG
   cj(C_DY, A + D, g.b_ih, 4 * H0, H0);
   cj(C_DY, A + D, g.b_hh, 4 * H0, H0);
   cj(C_WF, 0, g.f_att, A0, 0);
-  cj(C_INIT, 0, g.init_b, 2 * H0, 0);
+  cj(C_INIT, 0, g.init_b, 2 * nl * H0, 0);
   cj(C_FACT, 0, g.fact_b, E0, 0);
   SAT_REQUIRE(f.ok, "sat_train_param_grads: finalize job table overflow");
   if (f.blocks > 0) {

@@ -19,8 +19,11 @@ namespace {
 
 template <typename TS>
 static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void* ann, void* P, void* meanv, void* f1,
-                               float* init_out, void* h0, float* c0, cudaStream_t st, float drop_p = 0.0f, uint64_t seed = 0) {
+                               float* init_out, void* h0, float* c0, int64_t lstride, cudaStream_t st, float drop_p = 0.0f,
+                               uint64_t seed = 0) {
+  // h0 / c0: state arrays of layer 0; layer l lives lstride elements further (training: (T+1)*B*H, single call: B*H)
   const int B = d.B, Bi = d.Bi, L = d.L, D = d.D, A = d.A, E = d.E, H = d.H;
+  const int nl = d.layers > 1 ? d.layers : 1;
   const bool tc = d.use_tc != 0;
   // P = ann * Wa^T  ([Bi*L, D] x [A, D]^T)
   // first launch of a driver: no PDL attribute, so that operands written by the caller's preceding launch (the weight
@@ -35,15 +38,18 @@ static int prepare_images_impl(const SatDims& d, const SatWeights& w, const void
   SAT_LAUNCH_OK();
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(meanv, D, D), (const TS*)w.Wfact, D, Bi, E,
                            EpiStore<TS>{(TS*)f1, E, w.bfact, nullptr, 0}, st)));
-  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(f1, E, E), (const TS*)w.Winit, E, Bi, 2 * H,
-                           EpiStore<float>{init_out, 2 * H, w.binit, nullptr, 0}, st)));
-  const int H0 = d.H0 ? d.H0 : H;      // the [B,2H] -> [2,B,H] reinterpretation works on the module's true decoder_dim
+  const int IO = 2 * nl * H;           // init_lstm.init output width (storage)
+  SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(f1, E, E), (const TS*)w.Winit, E, Bi, IO,
+                           EpiStore<float>{init_out, IO, w.binit, nullptr, 0}, st)));
+  const int H0 = d.H0 ? d.H0 : H;      // the [B,2nH] -> [2n,B,H] reinterpretation works on the module's true decoder_dim
   if (H0 != H) {                        // padded state columns start (and stay) at zero
-    SAT_CUDA(cudaMemsetAsync(h0, 0, sizeof(TS) * (size_t)B * H, st));
-    SAT_CUDA(cudaMemsetAsync(c0, 0, sizeof(float) * (size_t)B * H, st));
+    for (int l = 0; l < nl; ++l) {
+      SAT_CUDA(cudaMemsetAsync((TS*)h0 + l * lstride, 0, sizeof(TS) * (size_t)B * H, st));
+      SAT_CUDA(cudaMemsetAsync(c0 + l * lstride, 0, sizeof(float) * (size_t)B * H, st));
+    }
   }
-  const int64_t n = 2 * (int64_t)B * H0;
-  init_state_kernel<TS><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(init_out, 2 * H, (TS*)h0, c0, H, H, B, H0, d.ncap);
+  const int64_t n = 2 * (int64_t)nl * B * H0;
+  init_state_kernel<TS><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(init_out, IO, (TS*)h0, c0, H, H, lstride, lstride, B, H0, d.ncap, nl);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   return 0;
@@ -63,7 +69,11 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
   SAT_REQUIRE(fuse_ce || b.logits != nullptr, "sat_train_forward: logits buffer missing (only the fused tensor-core path can do without)");
 
   // ---- once per image ------------------------------------------------------------------------
-  SAT_TRY((prepare_images_impl<TS>(d, w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, st, b.dropout_p, b.dropout_seed)));
+  const int nl = d.layers > 1 ? d.layers : 1;
+  const int64_t LS = (int64_t)(T + 1) * B * H;           // distance between the layers' state arrays in Hs / Cs
+  const int64_t GS = (int64_t)T * B * 4 * H;             // ... in Gates
+  TS* const Hs_top = (TS*)b.Hs + (nl - 1) * LS;          // attention, beta gate and the output layer read the top layer
+  SAT_TRY((prepare_images_impl<TS>(d, w, b.ann, b.P, b.meanv, b.f1, b.init_out, b.Hs, b.Cs, LS, st, b.dropout_p, b.dropout_seed)));
 
   // ---- hoisted: embeddings of the (teacher-forced) previous words and their gate projection ---
   SAT_CUDA(cudaMemsetAsync(b.out, 0, 8 * sizeof(float), st));
@@ -91,7 +101,7 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
       // scheduled sampling (model.py:518-523): this step's input word is argmax_v logits[t-1]; compute the output of
       // step t-1 now (the hoisted whole-sequence GEMMs below recompute the same values), then re-embed and re-project.
       const int64_t o1 = (int64_t)(t - 1) * B;
-      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)b.Hs + (int64_t)t * B * H, H, H, (const TS*)b.Z + o1 * D, D, D), (const TS*)w.Whozo,
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2((const TS*)Hs_top + (int64_t)t * B * H, H, H, (const TS*)b.Z + o1 * D, D, D), (const TS*)w.Whozo,
                                H + D, B, E, EpiTanhAdd<TS, kExact>{(const TS*)b.Xe + o1 * E, (TS*)b.Xo + o1 * E, E, nullptr, d.plain_output, b.dropout_p, b.dropout_seed, o1}, st)));
       if (b.logits_f32) {
         SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xo + o1 * E, E, E), (const TS*)w.Wo, E, B, V,
@@ -110,11 +120,20 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1((const TS*)b.Xe + (int64_t)t * B * E, E, E), (const TS*)w.Wihe, E, B, 4 * H,
                                EpiStore<float>{b.Gx + (int64_t)t * B * 4 * H, 4 * H, w.bg, nullptr, 0}, st)));
     }
-    const TS* h_t = (const TS*)b.Hs + (int64_t)t * B * H;
+    const TS* h_t = (const TS*)b.Hs + (int64_t)t * B * H;            // layer 0
     const float* c_t = b.Cs + (int64_t)t * B * H;
-    // hp = h_t * [W_h | W_beta | W_hh]^T + [0 | b_beta | 0]
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_t, H, H), (const TS*)w.Whcat, H, B, NH3,
-                             EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0}, st)));
+    const TS* htop_t = Hs_top + (int64_t)t * B * H;
+    if (nl == 1) {
+      // hp = h_t * [W_h | W_beta | W_hh]^T + [0 | b_beta | 0]
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_t, H, H), (const TS*)w.Whcat, H, B, NH3,
+                               EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0}, st)));
+    } else {
+      // stacked layers: q | beta_pre from the top layer's state, the recurrent projection of layer 0 from its own
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(htop_t, H, H), (const TS*)w.Whcat, H, B, A + D,
+                               EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0}, st)));
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_t, H, H), (const TS*)w.Whcat + (int64_t)(A + D) * H, H, B, 4 * H,
+                               EpiStore<float>{b.hp + A + D, NH3, nullptr, nullptr, 0}, st)));
+    }
     TS* z_t = (TS*)b.Z + (int64_t)t * B * D;
     TS* gz_t = (TS*)b.GZ + (int64_t)t * B * D;
     TS* beta_t = (TS*)b.Beta + (int64_t)t * B * D;
@@ -130,10 +149,20 @@ int train_forward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& b
     SAT_PROF(4, st);
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(gz_t, D, D), (const TS*)w.Wihz, D, B, 4 * H, epi, st)));
     SAT_PROF(4, st);
+    for (int l = 1; l < nl; ++l) {
+      // layer l: gates = [h'_{l-1} ; h_l] * [W_ih_l | W_hh_l]^T + b_l  (no dropout between layers, model.py:175-180)
+      const TS* hin = (const TS*)b.Hs + (l - 1) * LS + (int64_t)(t + 1) * B * H;
+      const TS* hl = (const TS*)b.Hs + l * LS + (int64_t)t * B * H;
+      const float* cl = b.Cs + l * LS + (int64_t)t * B * H;
+      EpiLstm<TS, kExact> epl{w.bgl[l - 1], 0, nullptr, 0, hl, cl, (TS*)b.Hs + l * LS + (int64_t)(t + 1) * B * H,
+                              b.Cs + l * LS + (int64_t)(t + 1) * B * H, H, H, (TS*)b.Gates + l * GS + (int64_t)t * B * 4 * H, 4 * H, b.lens,
+                              t, nullptr};
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(hin, H, H, hl, H, H), (const TS*)w.Wl[l - 1], 2 * H, B, 4 * H, epl, st)));
+    }
   }
 
   // ---- hoisted: deep output (model.py:127) and vocabulary projection (model.py:130) over all T*B rows
-  const TS* Hnext = (const TS*)b.Hs + (int64_t)B * H;   // h' of step t lives at Hs[t+1]
+  const TS* Hnext = (const TS*)Hs_top + (int64_t)B * H;   // h' of step t lives at Hs[top][t+1]
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a2(Hnext, H, H, b.Z, D, D), (const TS*)w.Whozo, H + D, T * B, E,
                            EpiTanhAdd<TS, kExact>{(const TS*)b.Xe, (TS*)b.Xo, E, nullptr, d.plain_output, b.dropout_p, b.dropout_seed, 0}, st)));
   ntok_kernel<<<1, 256, 0, st>>>(b.lens, B, b.out);
@@ -197,6 +226,7 @@ int check_dims(const SatDims* d) {
   SAT_REQUIRE(d->B > 0 && d->Bi > 0 && d->ncap > 0 && d->B == d->Bi * d->ncap, "B=%d must equal Bi*ncap=%d*%d", d->B, d->Bi,
               d->ncap);
   SAT_REQUIRE(d->L > 0 && d->T >= 0, "bad L=%d T=%d", d->L, d->T);
+  SAT_REQUIRE(d->layers >= 0 && d->layers <= SAT_MAX_LAYERS, "decoder_layers %d not in 1..%d", d->layers, SAT_MAX_LAYERS);
   SAT_REQUIRE(d->D % 8 == 0 && d->A % 8 == 0 && d->E % 8 == 0 && d->H % 8 == 0 && d->V % 8 == 0 && d->D > 0 && d->A > 0 &&
                   d->E > 0 && d->H > 0 && d->V > 0,
               "storage dims D=%d A=%d E=%d H=%d V=%d must be positive multiples of 8 (pad the module's dims: SatDims.D0 ..)", d->D, d->A,
@@ -236,8 +266,8 @@ int sat_prepare_images(const SatDims* d, const SatWeights* w, const void* ann, v
   SAT_TRY(check_dims(d));
   SAT_REQUIRE(w && ann && P && meanv && f1 && init_out && h0 && c0, "sat_prepare_images: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->dtype == SAT_F32) return prepare_images_impl<float>(*d, *w, ann, P, meanv, f1, init_out, h0, c0, st);
-  return prepare_images_impl<bf16>(*d, *w, ann, P, meanv, f1, init_out, h0, c0, st);
+  if (d->dtype == SAT_F32) return prepare_images_impl<float>(*d, *w, ann, P, meanv, f1, init_out, h0, c0, (int64_t)d->B * d->H, st);
+  return prepare_images_impl<bf16>(*d, *w, ann, P, meanv, f1, init_out, h0, c0, (int64_t)d->B * d->H, st);
 }
 
 int sat_attention_step_fwd(const SatDims* d, const void* ann, const void* P, const float* wf, const float* hp, int64_t ldhp,

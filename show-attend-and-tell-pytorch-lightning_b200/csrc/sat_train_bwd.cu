@@ -30,14 +30,31 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(b.dpre, E, E), (const TS*)w.WhozoT, E, M, H + D,
                            EpiStore<float>{b.dHZ, H + D, nullptr, nullptr, 0}, st)));
 
-  // split-K factors of the two skinny per-step GEMMs (tensor-core core only; partials are summed by their consumers)
+  // split-K factors of the skinny per-step GEMMs (tensor-core core only; partials are summed by their consumers)
   const int NH3_ = A + D + 4 * H;
+  const int nl = d.layers > 1 ? d.layers : 1;
+  const int64_t LS = (int64_t)(T + 1) * B * H, GS = (int64_t)T * B * 4 * H;     // layer strides of Hs/Cs and Gates/dGl
+  const int64_t BH = (int64_t)B * H;
   const bool tc_dgz = gemm_tn_uses_tc<TS, TS>(tc, gemm_a1((const TS*)b.DY + A + D, NH3_, 4 * H), (const TS*)w.WihzT, 4 * H, B, D);
-  const bool tc_dh = gemm_tn_uses_tc<TS, TS>(tc, gemm_a1(b.DY, NH3_, NH3_), (const TS*)w.WhcatT, NH3_, B, H);
   const int sk_dgz = tc_dgz ? tc::pick_splitk(B, D, 4 * H) : 1;
-  const int sk_dh = tc_dh ? tc::pick_splitk(B, H, NH3_) : 1;
-  SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)sk_dh * B * H, st));
-  SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)B * H, st));
+  // one layer: dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh] in one GEMM.  Stacked layers: q / beta read the TOP layer's
+  // state and the recurrent projection layer 0's, so the GEMM splits in two (dhq: K = A+D, dh: K = 4H).
+  const int k_dh = nl == 1 ? NH3_ : 4 * H;
+  const TS* w_dh = (const TS*)w.WhcatT + (nl == 1 ? 0 : A + D);
+  const bool tc_dh = gemm_tn_uses_tc<TS, TS>(tc, gemm_a1((const TS*)b.DY + (nl == 1 ? 0 : A + D), NH3_, k_dh), w_dh, NH3_, B, H);
+  const int sk_dh = tc_dh ? tc::pick_splitk(B, H, k_dh) : 1;
+  int sk_hq = 1, sk_x = 1;
+  if (nl > 1) {
+    SAT_REQUIRE(b.dGl && b.dxl && b.dhq, "sat_train_backward: decoder_layers > 1 needs the dGl / dxl / dhq buffers");
+    for (int l = 1; l < nl; ++l) SAT_REQUIRE(w.WlT[l - 1], "sat_train_backward: transposed weights of LSTM layer %d missing", l);
+    if (gemm_tn_uses_tc<TS, TS>(tc, gemm_a1(b.DY, NH3_, A + D), (const TS*)w.WhcatT, NH3_, B, H)) sk_hq = tc::pick_splitk(B, H, A + D);
+    if (gemm_tn_uses_tc<TS, TS>(tc, gemm_a1(b.dGl, 4 * H, 4 * H), (const TS*)w.WlT[0], 4 * H, B, 2 * H)) sk_x = tc::pick_splitk(B, 2 * H, 4 * H);
+    SAT_CUDA(cudaMemsetAsync(b.dhq, 0, sizeof(float) * (size_t)sk_hq * BH, st));
+    SAT_CUDA(cudaMemsetAsync(b.dxl, 0, sizeof(float) * (size_t)(nl - 1) * 16 * BH * 2, st));
+  }
+  SAT_CUDA(cudaMemsetAsync(b.dh, 0, sizeof(float) * (size_t)sk_dh * BH, st));
+  SAT_CUDA(cudaMemsetAsync(b.dc, 0, sizeof(float) * (size_t)nl * BH, st));
+  auto dxl_of = [&](int l) { return b.dxl + (int64_t)(l - 1) * 16 * BH * 2; };   // [16][B][2H] partials of layer l >= 1
   const bool dann_tc = tc && b.dP16 != nullptr && !std::is_same<TS, float>::value;
   const float scale = (float)(1.0 / sqrt((double)L));
   // pipelined attention backward: saves de_t per step and dP is rebuilt once after the loop (dP_deferred_kernel);
@@ -62,9 +79,27 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   for (int t = T - 1; t >= 0; --t) {
     TS* DY_t = (TS*)b.DY + (int64_t)t * B * NH3;
     const float* dHZ_t = b.dHZ + (int64_t)t * B * (H + D);
-    SAT_CUDA(sat_launch_pdl(lstm_bwd_step_kernel<TS, kExact>, dim3((B * H + 255) / 256), dim3(256), 0, st,
-        (const TS*)b.Gates + (int64_t)t * B * 4 * H, b.Cs + (int64_t)t * B * H, b.Cs + (int64_t)(t + 1) * B * H, b.dh, sk_dh,
-        (int64_t)B * H, dHZ_t, H + D, b.dc, DY_t + A + D, NH3, b.lens, t, B, H));
+    for (int l = nl - 1; l >= 1; --l) {
+      // layer l: grad wrt its new state = its own recurrent use at t+1 (dxl[l][:, H:], written at step t+1) + the layer
+      // above's input use at this step (dxl[l+1][:, :H]) or, for the top layer, q / beta at t+1 (dhq) and the output layer
+      DhSrc src{{dxl_of(l) + H, l < nl - 1 ? dxl_of(l + 1) : b.dhq, b.dc}, {sk_x, l < nl - 1 ? sk_x : sk_hq, 0},
+                {2 * BH, l < nl - 1 ? 2 * BH : BH, 0}, {2 * H, l < nl - 1 ? 2 * H : H, 0}};
+      TS* dG_l = (TS*)b.dGl + (l - 1) * GS + (int64_t)t * B * 4 * H;
+      SAT_CUDA(sat_launch_pdl(lstm_bwd_step_kernel<TS, kExact>, dim3((B * H + 255) / 256), dim3(256), 0, st,
+          (const TS*)b.Gates + l * GS + (int64_t)t * B * 4 * H, (const float*)(b.Cs + l * LS + (int64_t)t * BH),
+          (const float*)(b.Cs + l * LS + (int64_t)(t + 1) * BH), src, l == nl - 1 ? dHZ_t : (const float*)nullptr, (int64_t)(H + D),
+          b.dc + l * BH, dG_l, (int64_t)(4 * H), (const int32_t*)b.lens, t, B, H));
+      SAT_COUNT_LAUNCH();
+      // [d input | d own previous state] = dG_l * [W_ih_l | W_hh_l]
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(dG_l, 4 * H, 4 * H), (const TS*)w.WlT[l - 1], 4 * H, B, 2 * H,
+                               EpiStore<float>{dxl_of(l), 2 * H, nullptr, nullptr, 0, 2 * BH}, st, sk_x)));
+    }
+    {
+      DhSrc src{{b.dh, nl > 1 ? dxl_of(1) : b.dc, b.dc}, {sk_dh, nl > 1 ? sk_x : 0, 0}, {BH, 2 * BH, 0}, {H, 2 * H, 0}};
+      SAT_CUDA(sat_launch_pdl(lstm_bwd_step_kernel<TS, kExact>, dim3((B * H + 255) / 256), dim3(256), 0, st,
+          (const TS*)b.Gates + (int64_t)t * B * 4 * H, (const float*)(b.Cs + (int64_t)t * BH), (const float*)(b.Cs + (int64_t)(t + 1) * BH), src,
+          nl == 1 ? dHZ_t : (const float*)nullptr, (int64_t)(H + D), b.dc, DY_t + A + D, (int64_t)NH3, (const int32_t*)b.lens, t, B, H));
+    }
     SAT_COUNT_LAUNCH();
     // dgz = dG * Wihz     (A operand: DY_t[:, A+D:], K = 4H)
     SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + A + D, NH3, 4 * H), (const TS*)w.WihzT, 4 * H, B, D,
@@ -82,8 +117,11 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
     SAT_COUNT_LAUNCH();
     // dh = [dq | dbeta_pre | dG] * [W_h ; W_beta ; W_hh]   (rows inactive at t keep their dh)
     // (rows not active at t have an all-zero DY row, and their dh is still zero in backward order, so a plain store is exact)
-    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t, NH3, NH3), (const TS*)w.WhcatT, NH3, B, H,
-                             EpiStore<float>{b.dh, H, nullptr, nullptr, 0, (int64_t)B * H}, st, sk_dh)));
+    SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t + (nl == 1 ? 0 : A + D), NH3, k_dh), w_dh, NH3, B, H,
+                             EpiStore<float>{b.dh, H, nullptr, nullptr, 0, BH}, st, sk_dh)));
+    if (nl > 1)
+      SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(DY_t, NH3, A + D), (const TS*)w.WhcatT, NH3, B, H,
+                               EpiStore<float>{b.dhq, H, nullptr, nullptr, 0, BH}, st, sk_hq)));
   }
 
   if (att_pipe) {
@@ -105,18 +143,25 @@ int train_backward_impl(const SatDims& d, const SatWeights& w, SatTrainBuffers& 
   }
   // initial state: inverse of the [B,2H] -> [2,B,H] reinterpretation, then the two Linear layers
   const bool init_tc = tc && !std::is_same<TS, float>::value && b.d_init_out16 != nullptr && b.df116 != nullptr;
-  init_state_bwd_kernel<<<(Bi * 2 * H + 255) / 256, 256, 0, st>>>(b.dh, sk_dh, (int64_t)B * H, b.dc, H, b.d_init_out,
-                                                                  init_tc ? (bf16*)b.d_init_out16 : (bf16*)nullptr, 2 * H, B,
-                                                                  d.H0 ? d.H0 : H, d.ncap);
+  const int IO = 2 * nl * H;
+  InitBwdSrc isrc{};
+  for (int l = 0; l < nl; ++l)
+    for (int q = 0; q < 2; ++q) { isrc.p[l][q] = b.dc; isrc.ns[l][q] = 0; isrc.stride[l][q] = 0; isrc.ld[l][q] = 0; }
+  // grad wrt h0 of layer l: what its step-0 consumers left behind (recurrent projection; for the top layer also q / beta)
+  isrc.p[0][0] = b.dh; isrc.ns[0][0] = sk_dh; isrc.stride[0][0] = BH; isrc.ld[0][0] = H;
+  for (int l = 1; l < nl; ++l) { isrc.p[l][0] = dxl_of(l) + H; isrc.ns[l][0] = sk_x; isrc.stride[l][0] = 2 * BH; isrc.ld[l][0] = 2 * H; }
+  if (nl > 1) { isrc.p[nl - 1][1] = b.dhq; isrc.ns[nl - 1][1] = sk_hq; isrc.stride[nl - 1][1] = BH; isrc.ld[nl - 1][1] = H; }
+  init_state_bwd_kernel<<<(Bi * IO + 255) / 256, 256, 0, st>>>(isrc, b.dc, H, BH, b.d_init_out, init_tc ? (bf16*)b.d_init_out16 : (bf16*)nullptr,
+                                                               IO, B, d.H0 ? d.H0 : H, d.ncap, nl);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
   if (init_tc) {
-    SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.d_init_out16, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,
+    SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.d_init_out16, IO, IO), (const TS*)w.WinitT, IO, Bi, E,
                              EpiStoreDual<TS>{b.df1, (TS*)b.df116, E}, st)));
     SAT_TRY((gemm_tn<TS, TS>(true, gemm_a1(b.df116, E, E), (const TS*)w.WfactT, E, Bi, D,
                              EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));
   } else {
-    SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.d_init_out, 2 * H, 2 * H), (const TS*)w.WinitT, 2 * H, Bi, E,
+    SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.d_init_out, IO, IO), (const TS*)w.WinitT, IO, Bi, E,
                                 EpiStore<float>{b.df1, E, nullptr, nullptr, 0}, st)));
     SAT_TRY((gemm_tn<float, TS>(false, gemm_a1(b.df1, E, E), (const TS*)w.WfactT, E, Bi, D,
                                 EpiStore<float>{b.dmean, D, nullptr, nullptr, 0}, st)));

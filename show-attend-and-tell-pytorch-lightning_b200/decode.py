@@ -48,6 +48,7 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     R = n_img * k
     dtype = dw.pw.dtype
     d = decoder.make_dims(R, n_img, L, dw.pw, S + 1, dtype, dw.exact, dw.use_tc)
+    nl = dw.pw.layers
     method = SAMPLE[sample_method]
     noise = float(decoder_noise) if decoder_noise else 0.0
     kcap = max(k, int(sample_topk)) if method == 2 else k
@@ -62,8 +63,8 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
         _n[0] += 1
         return _redzone.empty(shape, dt, dev, "decode buffer #%d" % _n[0])
 
-    t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * H), f),
-             h=mk((R, H), s), c=mk((R, H), f), hn=mk((R, H), s), cn=mk((R, H), f), hp=mk((R, A + D + 4 * H), f),
+    t = dict(P=mk((n_img, L, A), s), meanv=mk((n_img, D), s), f1=mk((n_img, E), s), init_out=mk((n_img, 2 * nl * H), f),
+             h=mk((nl, R, H), s), c=mk((nl, R, H), f), hn=mk((nl, R, H), s), cn=mk((nl, R, H), f), hp=mk((R, A + D + 4 * H), f),
              z=mk((R, D), s), gz=mk((R, D), s), xo=mk((R, E), s), alpha_all=mk((S + 1, R, L), f),
              cand_val=mk((R, kcap), f), cand_idx=mk((R, kcap), i32), tok_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev),
              asrc_hist=torch.zeros((2, R, S + 1), dtype=i32, device=dev), top_scores=mk((R,), f), cur_tok=mk((R,), i32),
@@ -75,7 +76,7 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     if method == 1:
         t["cand_key"] = mk((R, kcap), f)
     if noise != 0.0:
-        t["h_noisy"] = mk((R, H), s)
+        t["h_noisy"] = mk((nl, R, H), s)
     if fuse_greedy:
         t["topk_stats"] = mk((R, (V + 127) // 128, 4), f)
     else:
@@ -156,8 +157,9 @@ def assemble(t, hw, return_all=False, want_alphas=True):
 
 def inference_weights(model):
     """cached DecodeWeights for a SAT module, rebuilt when any decoder parameter changed."""
-    from .packing import PARAM_NAMES
+    from .packing import param_names
     params = model.decoder_weights()
+    PARAM_NAMES = param_names(model.hparams.decoder_layers)
     cfg = model._cfg()
     key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params) + (cfg["dtype"],)
     cache = getattr(model, "_packed_infer", None)

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib, _redzone
-from .packing import PARAM_NAMES, PackedWeights
+from .packing import _LAYER_FIELDS, _LAYER_PARAMS, PARAM_NAMES, PackedWeights
 
 # reference parameter name -> field of SatParamGrads (include/sat_b200.h)
 _GRAD_FIELD = {
@@ -33,11 +33,11 @@ def _one(device):
     return _ONES[key]
 
 
-def make_dims(B, Bi, L, pw_or_dims, T, dtype, exact, use_tc, plain_output=False, dims0=None):
+def make_dims(B, Bi, L, pw_or_dims, T, dtype, exact, use_tc, plain_output=False, dims0=None, layers=1):
     """SatDims for a PackedWeights object (storage dims + the module's true dims) or an explicit dict of storage dims."""
     d = _lib.SatDims()
     if isinstance(pw_or_dims, PackedWeights):
-        dm, dm0, plain_output = pw_or_dims.dims, pw_or_dims.dims0, pw_or_dims.plain_output
+        dm, dm0, plain_output, layers = pw_or_dims.dims, pw_or_dims.dims0, pw_or_dims.plain_output, pw_or_dims.layers
     else:
         dm, dm0 = pw_or_dims, dims0 or pw_or_dims
     d.plain_output = 1 if plain_output else 0
@@ -47,6 +47,7 @@ def make_dims(B, Bi, L, pw_or_dims, T, dtype, exact, use_tc, plain_output=False,
     d.dtype = _lib.dtype_code(dtype)
     d.exact = 1 if exact else 0
     d.use_tc = 1 if use_tc else 0
+    d.layers = int(layers)
     return d
 
 
@@ -56,6 +57,7 @@ class TrainBuffers:
     def __init__(self, d, dtype, device, logits_f32=False, backward=True, keep_logits=False, fuse_ce=False):
         B, Bi, L, D, A, E, H, V, T = d.B, d.Bi, d.L, d.D, d.A, d.E, d.H, d.V, d.T
         NH3 = A + D + 4 * H
+        nl = max(1, d.layers)
         s, f = dtype, torch.float32
         t = self.t = {}
         mk = lambda shape, dt: _redzone.empty(shape, dt, device, "train buffer #%d" % len(t))   # torch.empty unless SAT_REDZONE=1
@@ -63,18 +65,18 @@ class TrainBuffers:
         t["P"] = mk((Bi, L, A), s)
         t["meanv"] = mk((Bi, D), s)
         t["f1"] = mk((Bi, E), s)
-        t["init_out"] = mk((Bi, 2 * H), f)
+        t["init_out"] = mk((Bi, 2 * nl * H), f)
         t["Xe"] = mk((T, B, E), s)
         t["Gx"] = mk((T, B, 4 * H), f)
-        t["Hs"] = mk((T + 1, B, H), s)
-        t["Cs"] = mk((T + 1, B, H), f)
+        t["Hs"] = mk((nl, T + 1, B, H), s)
+        t["Cs"] = mk((nl, T + 1, B, H), f)
         t["hp"] = mk((B, NH3), f)
         t["Q"] = mk((T, B, A), f)
         t["alphas"] = mk((B, T, L), f)
         t["Z"] = mk((T, B, D), s)
         t["GZ"] = mk((T, B, D), s)
         t["Beta"] = mk((T, B, D), s)
-        t["Gates"] = mk((T, B, 4 * H), s)
+        t["Gates"] = mk((nl, T, B, 4 * H), s)
         t["Xo"] = mk((T, B, E), s)
         # fused vocabulary projection + cross entropy (tensor-core mode): no logits buffer at all, only the per-tile statistics
         self.fuse_ce = bool(fuse_ce and d.use_tc and dtype == torch.bfloat16 and not logits_f32 and not keep_logits)
@@ -99,7 +101,11 @@ class TrainBuffers:
             t["DY"] = mk((T, B, NH3), s)
             t["dgz"] = mk((16, B, D), f)        # split-K partials (SAT_MAX_SPLITK)
             t["dh"] = mk((16, B, H), f)
-            t["dc"] = mk((B, H), f)
+            t["dc"] = mk((nl, B, H), f)
+            if nl > 1:
+                t["dGl"] = mk((nl - 1, T, B, 4 * H), s)
+                t["dxl"] = mk((nl - 1, 16, B, 2 * H), f)
+                t["dhq"] = mk((16, B, H), f)
             t["dZ"] = mk((T, B, D), s)
             t["dP"] = mk((B, L, A), f)
             if dtype != torch.float32:
@@ -107,10 +113,10 @@ class TrainBuffers:
             t["dwf_part"] = mk((T, B, A), f)
             t["de"] = mk((T, B, L), f)
             t["dXe"] = mk((T, B, E), f)
-            t["d_init_out"] = mk((Bi, 2 * H), f)
+            t["d_init_out"] = mk((Bi, 2 * nl * H), f)
             t["df1"] = mk((Bi, E), f)
             if dtype != torch.float32:
-                t["d_init_out16"] = mk((Bi, 2 * H), s)
+                t["d_init_out16"] = mk((Bi, 2 * nl * H), s)
                 t["df116"] = mk((Bi, E), s)
             t["dmean"] = mk((Bi, D), f)
             t["d_ann"] = mk((B, L, D), s)          # per caption row; the host sums the ncap rows of an image
@@ -213,9 +219,10 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
     _lib.check(L_.sat_train_backward(C.byref(d), pw.ref(), C.byref(buf.c), _lib.stream_ptr()), "sat_train_backward")
     # parameter gradients: destinations with the reference's shapes
     V0, E0, H0, D0, A0 = dm0["V"], dm0["E"], dm0["H"], dm0["D"], dm0["A"]
+    nl = pw.layers
     shapes = {
         "embedding.weight": (V0, E0), "init_lstm.factorize.weight": (E0, D0), "init_lstm.factorize.bias": (E0,),
-        "init_lstm.init.weight": (2 * H0, E0), "init_lstm.init.bias": (2 * H0,), "lstm.weight_ih_l0": (4 * H0, E0 + D0),
+        "init_lstm.init.weight": (2 * nl * H0, E0), "init_lstm.init.bias": (2 * nl * H0,), "lstm.weight_ih_l0": (4 * H0, E0 + D0),
         "lstm.weight_hh_l0": (4 * H0, H0), "lstm.bias_ih_l0": (4 * H0,), "lstm.bias_hh_l0": (4 * H0,),
         "attention.encoder_att.weight": (A0, D0), "attention.decoder_att.weight": (A0, H0), "attention.f_att.weight": (1, A0),
         "beta.0.weight": (D0, H0), "beta.0.bias": (D0,), "output.hidden.weight": (E0, H0), "output.context.weight": (E0, D0),
@@ -235,6 +242,10 @@ def train_backward(pw, buf, grad_loss=None, pad_idx=0, weight_tying=False, dalph
             continue
         G[name] = torch.empty(shapes[name], dtype=torch.float32, device=dev)
         setattr(g, _GRAD_FIELD[name], G[name].data_ptr())
+    for l in range(1, nl):
+        for field, name, shp in zip(_LAYER_FIELDS, _LAYER_PARAMS, ((4 * H0, H0), (4 * H0, H0), (4 * H0,), (4 * H0,))):
+            G[name % l] = torch.empty(shp, dtype=torch.float32, device=dev)
+            getattr(g, field)[l - 1] = G[name % l].data_ptr()
     g.pad_idx = -1 if pad_idx is None else int(pad_idx)
     g.weight_tying = 1 if weight_tying else 0
     nbytes = int(L_.sat_param_grads_workspace_bytes(C.byref(d)))

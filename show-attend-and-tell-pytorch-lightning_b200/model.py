@@ -17,7 +17,7 @@ from torch import nn
 from torch.nn.utils.rnn import pack_padded_sequence
 
 from . import _lib, decoder
-from .packing import PARAM_NAMES, PackedWeights
+from .packing import PackedWeights, layers_of, param_names
 
 try:  # PyTorch-Lightning is optional (not installed in the build image)
     import pytorch_lightning as pl
@@ -306,7 +306,7 @@ class _FusedTrainLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ann, caps, lens, cfg, *params):
-        W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
+        W = {n: p for n, p in zip(param_names(layers_of(len(params))), params) if p is not None}
         pw = _packed_for(cfg, W, ann.device)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, cfg["label_smoothing"], cfg["att_gamma"], exact=cfg["exact"],
@@ -326,7 +326,7 @@ class _FusedTrainLoss(torch.autograd.Function):
         G, d_ann = decoder.train_backward(ctx.pw, ctx.buf, gloss, pad_idx=cfg["pad_idx"], weight_tying=cfg["weight_tying"])
         Bi, D, h, w = ctx.ann_shape
         d_ann = d_ann.reshape(Bi, h, w, D).permute(0, 3, 1, 2).to(ctx.ann_dtype)
-        grads = [G.get(n) if have else None for n, have in zip(PARAM_NAMES, ctx.have)]
+        grads = [G.get(n) if have else None for n, have in zip(param_names(layers_of(len(ctx.have))), ctx.have)]
         ctx.buf = None
         return (d_ann, None, None, None, *grads)
 
@@ -337,7 +337,7 @@ class _TrainLogits(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ann, caps, lens, cfg, *params):
-        W = {n: p for n, p in zip(PARAM_NAMES, params) if p is not None}
+        W = {n: p for n, p in zip(param_names(layers_of(len(params))), params) if p is not None}
         pw = _packed_for(cfg, W, ann.device)
         bld = decoder.annotations_as_bld(ann, cfg["dtype"])
         buf = decoder.train_forward(pw, bld, caps, lens, 0.0, 0.0, exact=cfg["exact"], use_tc=cfg["use_tc"],
@@ -364,7 +364,7 @@ class _TrainLogits(torch.autograd.Function):
         buf.c.att_gamma = saved_gamma
         Bi, D, h, w = ctx.ann_shape
         d_ann = d_ann.reshape(Bi, h, w, D).permute(0, 3, 1, 2).to(ctx.ann_dtype)
-        grads = [G.get(n) if have else None for n, have in zip(PARAM_NAMES, ctx.have)]
+        grads = [G.get(n) if have else None for n, have in zip(param_names(layers_of(len(ctx.have))), ctx.have)]
         ctx.buf = None
         return (d_ann, None, None, None, *grads)
 
@@ -393,8 +393,8 @@ class SAT(_Base):
             if k not in hp:
                 hp[k] = v
         assert 0 <= hp.label_smoothing < (hp.vocab_size - 1) / hp.vocab_size
-        if hp.decoder_layers != 1:
-            raise NotImplementedError("decoder_layers > 1 is not on the accelerated path (BASELINE configs use 1 layer)")
+        if not 1 <= hp.decoder_layers <= _lib.SAT_MAX_LAYERS:
+            raise NotImplementedError("decoder_layers=%d: the kernels support 1..%d stacked LSTM layers" % (hp.decoder_layers, _lib.SAT_MAX_LAYERS))
         self.criterion = LabelSmoothing(hp.label_smoothing)
         self.special_idxs = [self.stoi("<PAD>"), self.stoi("<START>"), self.stoi("<END>")]
         # module construction order follows model.py:154-195 so that a seeded default init is identical
@@ -465,11 +465,11 @@ class SAT(_Base):
             torch.embedding_renorm_(w, ids, float(mn), 2.0)
 
     def decoder_weights(self):
-        """reference-named decoder parameters in PARAM_NAMES order (None where absent)."""
+        """reference-named decoder parameters in packing.param_names(decoder_layers) order (None where absent)."""
         sd = dict(self.named_parameters())
         if "output.output.weight" not in sd:           # tied: shares embedding.weight
             sd["output.output.weight"] = self.embedding.weight
-        return [sd.get(n) for n in PARAM_NAMES]
+        return [sd.get(n) for n in param_names(self.hparams.decoder_layers)]
 
     def encode(self, img):
         """images -> annotations [B,D,h,w]; bf16 mode runs the trunk channels_last under autocast so the

@@ -15,6 +15,25 @@ PARAM_NAMES = [
     "output.hidden.weight", "output.context.weight", "output.output.weight", "output.output.bias",
 ]
 
+_LAYER_PARAMS = ("lstm.weight_ih_l%d", "lstm.weight_hh_l%d", "lstm.bias_ih_l%d", "lstm.bias_hh_l%d")
+_LAYER_FIELDS = ("w_ih_l", "w_hh_l", "b_ih_l", "b_hh_l")       # SatMasterWeights / SatParamGrads arrays, index l - 1
+
+
+def param_names(layers=1):
+    """reference parameter names of a decoder with `layers` stacked LSTM layers (decoder_layers, model.py:175-180):
+    PARAM_NAMES followed by the four nn.LSTM parameters of every layer l >= 1."""
+    return PARAM_NAMES + [n % l for l in range(1, int(layers)) for n in _LAYER_PARAMS]
+
+
+def layers_of(names_or_count):
+    """number of LSTM layers of a parameter list in param_names() order (or of a dict keyed by the reference names)"""
+    if isinstance(names_or_count, dict):
+        n = 1
+        while ("lstm.weight_ih_l%d" % n) in names_or_count and names_or_count["lstm.weight_ih_l%d" % n] is not None:
+            n += 1
+        return n
+    return 1 + (int(names_or_count) - len(PARAM_NAMES)) // 4
+
 
 def interleave_gates(w):
     """[4H, ...] in torch order (i|f|g|o blocks) -> row 4*j+g = row g*H+j."""
@@ -47,6 +66,9 @@ class PackedWeights:
         V0, E0 = W["embedding.weight"].shape
         H0 = W["lstm.weight_hh_l0"].shape[1]
         A0, D0 = W["attention.encoder_att.weight"].shape
+        nl = self.layers = layers_of(W)
+        if nl > _lib.SAT_MAX_LAYERS:
+            raise _lib.SatError("decoder_layers=%d: the kernels support up to %d stacked LSTM layers" % (nl, _lib.SAT_MAX_LAYERS))
         # The kernels work on storage dims that are multiples of 8 (16-byte vectors, TMA rows).  A module with other sizes
         # (V = words above min_count + 4, 100/300-d GloVe embeddings ...) is zero-padded here: zero weights keep the padded
         # lanes exactly zero through forward and backward, the padded vocabulary entries get a bias of -inf.
@@ -77,8 +99,11 @@ class PackedWeights:
         t["Emb"] = z((V, E), dtype)
         t["Wfact"] = z((E, D), dtype)
         t["bfact"] = z((E,), f)
-        t["Winit"] = z((2 * H, E), dtype)
-        t["binit"] = z((2 * H,), f)
+        t["Winit"] = z((2 * nl * H, E), dtype)
+        t["binit"] = z((2 * nl * H,), f)
+        for l in range(1, nl):
+            t["Wl%d" % l] = z((4 * H, 2 * H), dtype)
+            t["bgl%d" % l] = z((4 * H,), f)
         if backward:
             t["WoT"] = z((E, V), dtype)
             t["WhozoT"] = z((H + D, E), dtype)
@@ -86,32 +111,44 @@ class PackedWeights:
             t["WiheT"] = z((E, 4 * H), dtype)
             t["WhcatT"] = z((H, NH3), dtype)
             t["WaT"] = z((D, A), dtype)
-            t["WinitT"] = z((E, 2 * H), dtype)
+            t["WinitT"] = z((E, 2 * nl * H), dtype)
             t["WfactT"] = z((D, E), dtype)
+            for l in range(1, nl):
+                t["WlT%d" % l] = z((2 * H, 4 * H), dtype)
         self.c = _lib.SatWeights()
-        for name, _ in _lib.SatWeights._fields_:
-            setattr(self.c, name, _lib.ptr(t.get(name)))
+        for name, typ in _lib.SatWeights._fields_:
+            if typ is C.c_void_p:
+                setattr(self.c, name, _lib.ptr(t.get(name)))
+            else:                                       # per-layer arrays (index l - 1)
+                arr = getattr(self.c, name)
+                for l in range(1, _lib.SAT_MAX_LAYERS):
+                    arr[l - 1] = _lib.ptr(t.get("%s%d" % (name, l)))
         self._d = _lib.SatDims()
         self._d.B = self._d.Bi = self._d.ncap = 1
         self._d.L, self._d.D, self._d.A, self._d.E, self._d.H, self._d.V, self._d.T = 1, D, A, E, H, V, 1
         self._d.D0, self._d.A0, self._d.E0, self._d.H0, self._d.V0 = int(D0), int(A0), int(E0), int(H0), int(V0)
         self._d.dtype = _lib.dtype_code(dtype)
+        self._d.layers = nl
         self.repack(W)
 
     def repack(self, W):
         """(re)fill every packed buffer from the current master parameters: one kernel launch."""
         m = _lib.SatMasterWeights()
         keep = []
-        for field, name in self._SRC:
-            p = W.get(name, None)
-            if p is None:
-                setattr(m, field, None)
-                continue
+
+        def src(p):
             x = p.detach()
             if x.device != self.device or x.dtype != torch.float32 or not x.is_contiguous():
                 x = x.to(device=self.device, dtype=torch.float32).contiguous()
             keep.append(x)
-            setattr(m, field, x.data_ptr())
+            return x.data_ptr()
+
+        for field, name in self._SRC:
+            p = W.get(name, None)
+            setattr(m, field, None if p is None else src(p))
+        for l in range(1, self.layers):
+            for field, name in zip(_LAYER_FIELDS, _LAYER_PARAMS):
+                getattr(m, field)[l - 1] = src(W[name % l])
         self._keep = keep            # sources must outlive the (asynchronous) kernel
         _lib.check(_lib.lib().sat_pack_weights(C.byref(self._d), C.byref(m), C.byref(self.c), _lib.stream_ptr()), "sat_pack_weights")
         return self

@@ -17,7 +17,7 @@ def relerr(a, b):
 VOC = lambda V: dict(PAD=0, UNK=V - 3, START=V - 2, END=V - 1)
 
 
-@pytest.mark.parametrize("name", ["train_tiny", "train_small", "train_ragged"])
+@pytest.mark.parametrize("name", ["train_tiny", "train_small", "train_ragged", "train_layers2", "train_layers3"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_train_forward_loss_and_grads(name, dtype):
     z, W, G = load_golden(name)
@@ -45,7 +45,7 @@ def test_label_smoothing_zero_is_cross_entropy():
     assert torch.allclose(O.label_smoothing_loss(x, y, 0.0), torch.nn.functional.cross_entropy(x, y), atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["decode_tiny", "decode_small"])
+@pytest.mark.parametrize("name", ["decode_tiny", "decode_small", "decode_layers2"])
 @pytest.mark.parametrize("k", [1, 3, 5])
 @pytest.mark.parametrize("rescore", [None, "LN", "WR", "BAR"])
 @pytest.mark.parametrize("return_all", [False, True])

@@ -42,8 +42,8 @@ def test_forward_fp32_vs_reference_golden(name):
     assert abs(r["acc"] - float(z["acc"])) < 1e-6
 
 
-def synth(Bi, ncap, hw, D, A, E, H, V, T, ragged, seed=0, sharpen=False):
-    W = O.random_weights(D, A, E, H, V, seed=seed, sharpen=sharpen)
+def synth(Bi, ncap, hw, D, A, E, H, V, T, ragged, seed=0, sharpen=False, layers=1):
+    W = O.random_weights(D, A, E, H, V, seed=seed, sharpen=sharpen, layers=layers)
     g = torch.Generator().manual_seed(seed + 100)
     ann = torch.randn(Bi, D, hw[0], hw[1], generator=g)
     caps = torch.randint(1, V - 3, (Bi, ncap, T + 1), generator=g)
