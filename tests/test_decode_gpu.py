@@ -80,7 +80,10 @@ def test_greedy_bf16_runs_and_mostly_agrees(use_tc):
     ref = O.caption(W, ann, VOC(V), beamk=1, max_gen_length=30)
     got = cuda_caption(W, ann, 1, 30, dtype=torch.bfloat16, use_tc=use_tc)
     agree = sum(1 for a, b in zip(got[0], ref[0]) if a[:3] == b[:3])
-    assert agree >= 3          # bf16 token ids are not expected to be bit-exact
+    assert agree >= 3          # bf16 token ids are not expected to be bit-exact ...
+    from test_full_size_gpu import oracle_gaps
+    gaps = oracle_gaps(W, ann, got[0], VOC(V))
+    assert max(max(gp) for gp in gaps) < 0.1      # ... but every chosen word is a near-tie (nats) under the teacher-forced fp32 oracle
 
 
 def test_decode_single_image_and_wide_beam():

@@ -60,13 +60,20 @@ if args.decode:
     print("decode k=%d B=%d: median %.3f ms (min %.3f) over %d iters" % (args.decode, B, times[len(times) // 2], times[0], len(times)))
 else:
     pw = PackedWeights(W, dtype=dtype, device="cuda", backward=True)
+    import time
+    cpu = []
     for it in range(args.iters):
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
         ev0.record()
         buf = decoder.train_forward(pw, ann, caps, lens, 0.0, 1.0, exact=args.fp32, use_tc=use_tc, backward=True, fuse_ce=not args.no_fuse_ce)
         G, d_ann = decoder.train_backward(pw, buf)
         ev1.record()
+        cpu.append(1e3 * (time.perf_counter() - c0))      # host time to ISSUE the step (no synchronize inside)
         torch.cuda.synchronize()
         times.append(ev0.elapsed_time(ev1))
+    cpu = sorted(cpu[2:] or cpu)
+    print("host issue time per step: median %.3f ms (min %.3f)" % (cpu[len(cpu) // 2], cpu[0]))
     if args.profile:
         from sat_b200 import _lib
         _lib.profile_begin(args.profile)
