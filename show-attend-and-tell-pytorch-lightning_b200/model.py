@@ -106,10 +106,14 @@ class _Normalize(nn.Module):
     def __init__(self, mean, std):
         super().__init__()
         self.mean, self.std = list(mean), list(std)
+        self._cache = {}            # (device, dtype) -> (mean, std) device tensors: one upload, not a host->device copy per call
 
     def forward(self, x):
-        mean = torch.as_tensor(self.mean, dtype=x.dtype, device=x.device).view(1, -1, 1, 1)
-        std = torch.as_tensor(self.std, dtype=x.dtype, device=x.device).view(1, -1, 1, 1)
+        key = (x.device, x.dtype)
+        if key not in self._cache:
+            self._cache[key] = (torch.as_tensor(self.mean, dtype=x.dtype, device=x.device).view(1, -1, 1, 1),
+                                torch.as_tensor(self.std, dtype=x.dtype, device=x.device).view(1, -1, 1, 1))
+        mean, std = self._cache[key]
         return x.sub_(mean).div_(std)
 
 
@@ -402,8 +406,12 @@ class SAT(_Base):
         if self._dtype() == torch.bfloat16 and hp.get("cudnn_batchnorm", True):
             # encoder boundary: PyTorch does not route bf16 batch-norm to cuDNN (ATen's channels_last kernels are 3-4x slower
             # on B200); same parameters / buffers / state_dict keys, training-mode NHWC half-precision inputs go to cuDNN
-            from .cudnn_bn import convert_batchnorm
+            from .cudnn_bn import convert_batchnorm, fuse_residual_blocks
             convert_batchnorm(self.encoder)
+            if hp.get("cudnn_fuse_blocks", True):
+                # ... and the ReLU / residual add that follow a batch-norm in torchvision's ResNet blocks ride in the same cuDNN
+                # call (bnOps BN_ACTIVATION / BN_ADD_ACTIVATION); the stem's max-pool goes to cudnnPooling*
+                fuse_residual_blocks(self.encoder)
         self.embedding = nn.Embedding(num_embeddings=hp.vocab_size, embedding_dim=hp.embed_dim, max_norm=hp.embed_norm,
                                       padding_idx=self.stoi("<PAD>"))
         self.embedding_dropout = nn.Dropout(p=hp.embedding_dropout)
