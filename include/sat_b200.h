@@ -304,6 +304,15 @@ float sat_dropout_multiplier(float p, uint64_t seed, uint32_t stream, uint64_t i
 int sat_cast_captions(const int64_t* caps64, const int64_t* lens64, int32_t* caps32, int32_t* lens32, int64_t n_caps, int64_t n_lens,
                       void* stream);
 
+/* Encoder tail (readme.md:118-121: nn.Upsample((s,s), mode="bilinear", align_corners=False) appended to the encoder
+ * of model.py:16-63): bilinear resize of an NHWC map [n,h,w,D] to [n,H2,W2,D], i.e. straight into the [B,L,D] annotation array the
+ * decoder kernels read -- fp32 interpolation of the stored values, one rounding to `dtype` (SAT_F32 / SAT_BF16).  _bwd is its
+ * transpose in gather form (no atomics: deterministic), d_dst [n,H2,W2,D] -> d_src [n,h,w,D].  D % (16 / sizeof(dtype)) == 0. */
+int sat_resize_nhwc_fwd(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t H2, int32_t W2, int32_t D, int32_t dtype,
+                        void* stream);
+int sat_resize_nhwc_bwd(const void* d_dst, void* d_src, int32_t n, int32_t h, int32_t w, int32_t H2, int32_t W2, int32_t D, int32_t dtype,
+                        void* stream);
+
 int sat_train_forward(const SatDims* d, const SatWeights* w, SatTrainBuffers* b, void* stream);
 
 /* Hand-written BPTT of sat_train_forward (what autograd derives from model.py:510-548): fills

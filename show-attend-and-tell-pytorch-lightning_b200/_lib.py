@@ -67,7 +67,7 @@ class SatParamGrads(C.Structure):
 
 
 EXPORTS = ["sat_version", "sat_last_error", "sat_abi_sizeof", "sat_launch_count", "sat_profile_begin", "sat_profile_end", "sat_dropout_multiplier", "sat_pack_weights",
-           "sat_linear", "sat_linear_nt", "sat_prepare_images",
+           "sat_linear", "sat_linear_nt", "sat_prepare_images", "sat_resize_nhwc_fwd", "sat_resize_nhwc_bwd",
            "sat_attention_step_fwd", "sat_cast_captions", "sat_train_forward", "sat_train_backward", "sat_param_grads_workspace_bytes", "sat_train_param_grads",
            "sat_decode_prepare_weights", "sat_decode"]
 
@@ -115,6 +115,8 @@ def lib():
     L.sat_prepare_images.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), vp, vp, vp, vp, vp, vp, vp, vp]
     L.sat_attention_step_fwd.argtypes = [C.POINTER(SatDims), vp, vp, vp, vp, C.c_int64, vp, C.c_int32, vp, C.c_int64,
                                          vp, vp, vp, C.c_int64, vp]
+    L.sat_resize_nhwc_fwd.argtypes = [vp, vp] + [C.c_int32] * 7 + [vp]
+    L.sat_resize_nhwc_bwd.argtypes = [vp, vp] + [C.c_int32] * 7 + [vp]
     L.sat_cast_captions.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int64, vp]
     L.sat_train_forward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]
     L.sat_train_backward.argtypes = [C.POINTER(SatDims), C.POINTER(SatWeights), C.POINTER(SatTrainBuffers), vp]

@@ -158,7 +158,8 @@ def get_encoder(args):
         if size < final_size:
             layers.append(nn.AdaptiveAvgPool2d((size, size)))
         elif size > final_size:
-            layers.append(nn.Upsample((size, size), mode="bilinear", align_corners=False))
+            from .encoder_tail import ResizeBilinearNHWC          # nn.Upsample subclass: one library pass for CUDA channels_last maps
+            layers.append(ResizeBilinearNHWC((size, size), mode="bilinear", align_corners=False))
     return nn.Sequential(_Normalize(args.mean, args.std), *layers)
 
 
@@ -743,19 +744,23 @@ class SAT(_Base):
         lr = _hp(hp, "decoder_lr", 1e-3)
         params = groups([self.init_lstm, self.lstm, self.attention, self.beta, self.output], wd, lr)
         if _hp(hp, "embedding_lr", lr) > 0 and not hp.weight_tying:
-            params += [{"params": self.embedding.parameters(), "lr": _hp(hp, "embedding_lr", lr), "weight_decay": 0.0}]
+            params += [{"params": list(self.embedding.parameters()), "lr": _hp(hp, "embedding_lr", lr), "weight_decay": 0.0}]
         # the reference adds the encoder group when encoder_finetune_after > 0 and encoder_lr > 0 (model.py:744); a trunk that
         # trains from scratch (pretrained=False: every parameter requires grad, model.py:23-25) is included as well, otherwise
         # its gradients would be computed and never applied
         if _hp(hp, "encoder_lr", 0.0) > 0 and (_hp(hp, "encoder_finetune_after", -1) > 0 or not hp.pretrained):
             params += groups([self.encoder], wd, hp.encoder_lr)
         opt = _hp(hp, "opt", "adam")
+        # same update rule as the reference's torch.optim calls; on CUDA the single-kernel ("fused") implementation of the
+        # stock optimizer replaces the default multi-pass one (same arithmetic in fp32, one read / write of p, g, m, v)
+        every = [p for g in params for p in g["params"]]
+        fused = {"fused": True} if (every and all(p.is_cuda and p.is_floating_point() for p in every)) else {}
         if opt == "sgd":
             optimizer = torch.optim.SGD(params, lr=lr, momentum=_hp(hp, "momentum", 0.9), nesterov=_hp(hp, "nesterov", False))
         elif opt == "adamw":
-            optimizer = torch.optim.AdamW(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)))
+            optimizer = torch.optim.AdamW(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)), **fused)
         else:
-            optimizer = torch.optim.Adam(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)))
+            optimizer = torch.optim.Adam(params, lr=lr, betas=(_hp(hp, "adam_b1", 0.9), _hp(hp, "adam_b2", 0.999)), **fused)
         self.opt_init_lr = [pg["lr"] for pg in optimizer.param_groups]
         self._optimizer = optimizer
         self.scheduler = self._build_scheduler(optimizer)

@@ -151,3 +151,40 @@ def test_sat_module_uses_the_fused_trunk_and_keeps_the_reference_state_dict():
     m.eval(); m2.eval()
     with torch.no_grad():
         assert torch.equal(m.encode(img.clone()), m2.encode(img.clone()))        # eval: stock batch-norm kernels in both
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 7, 7, 14, 14), (3, 72, 8, 8, 14, 14), (2, 32, 5, 10, 16, 12), (2, 16, 9, 9, 6, 7)])
+def test_resize_layer_matches_upsample(shape):
+    """encoder tail (readme.md:118-121): the library's one-pass NHWC bilinear resize against nn.Upsample(mode="bilinear",
+    align_corners=False) -- fp32 to 1e-6 (forward and backward), bf16 = the fp32 interpolation of the stored bf16 values rounded
+    once; the gather-form backward is bit-reproducible"""
+    from sat_b200.encoder_tail import ResizeBilinearNHWC
+    n, D, h, w, H2, W2 = shape
+    layer, ref = ResizeBilinearNHWC((H2, W2), mode="bilinear", align_corners=False), nn.Upsample((H2, W2), mode="bilinear", align_corners=False)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, D, h, w, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(n, D, H2, W2, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = layer(xa), ref(xb)
+    assert ya.is_contiguous(memory_format=torch.channels_last) and ya.shape == yb.shape
+    assert relerr(ya, yb) < 1e-6
+    ya.backward(dy)
+    yb.backward(dy)
+    assert relerr(xa.grad, xb.grad) < 1e-6
+    # bf16
+    xh = x.bfloat16()
+    xc = xh.clone().requires_grad_(True)
+    yh = layer(xc)
+    assert yh.dtype == torch.bfloat16
+    want = ref(xh.float())
+    assert relerr(yh.float(), want) < 8e-3                      # one bf16 rounding of the fp32 interpolation
+    yh.backward(dy.bfloat16())
+    g1 = xc.grad.clone()
+    xr = xh.float().requires_grad_(True)
+    ref(xr).backward(dy.bfloat16().float())
+    assert relerr(g1.float(), xr.grad) < 8e-3
+    xc.grad = None
+    layer(xc).backward(dy.bfloat16())
+    assert torch.equal(xc.grad, g1)                              # deterministic
+    # NCHW input: stock path
+    assert torch.equal(layer(x.contiguous()), ref(x.contiguous()))
