@@ -20,7 +20,11 @@ BN_ADD_ACTIVATION): y = relu(bn(x)) and y = relu(bn(x) + z) cost what the plain 
 forward / backward and residual-add kernels of the eager trunk (5.9 ms of the 36.8 ms BASELINE configs[1] step, profiles/
 r02_full_train_step_launches.txt).  fuse_residual_blocks(trunk) switches torchvision's Bottleneck / BasicBlock (and the
 conv-bn-relu-maxpool stem) to these calls; the stem's max-pool goes to cudnnPooling{Forward,Backward} (249 / 1484 us against
-ATen's 748 / 2005 us at [256,64,112,112]).  Parameters, buffers, state_dict keys and eval / fp32 behaviour are unchanged.
+ATen's 748 / 2005 us at [256,64,112,112]).  In inference (eval mode under no_grad) the same blocks fold the batch-norm into the
+convolution weights and call cuDNN's fused convolution + bias (+ residual) + ReLU (torch.cudnn_convolution_relu /
+cudnn_convolution_add_relu; tools/conv_fuse_probe.py: 61-160 us against 285-820 us for conv + bn + add + relu at the 56x56 layers),
+so the captioning trunk runs without a single element-wise pass.  Parameters, buffers, state_dict keys and fp32 behaviour are
+unchanged.
 """
 import ctypes as C
 import glob
@@ -274,8 +278,66 @@ class CudnnMaxPool2d(nn.MaxPool2d):
         return super().forward(x)
 
 
+# ---- inference: batch-norm folded into the convolution, bias / residual add / ReLU in cuDNN's fused convolution ------------
+def _foldable(conv, bn):
+    return (isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and bn.track_running_stats and bn.running_mean is not None
+            and bn.affine and conv.groups == 1 and tuple(conv.dilation) == (1, 1) and conv.padding_mode == "zeros"
+            and not isinstance(conv.padding, str))
+
+
+def _fold(conv, bn, dtype):
+    """(weight, bias) of the convolution with the eval-mode batch-norm folded in: w * g/sqrt(var+eps), beta + (b - mean) * g/sqrt(var+eps);
+    computed in fp32, stored once in `dtype` (channels_last) and rebuilt when any source tensor changes (version counters)."""
+    src = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version) if t is not None else None for t in src) + (dtype,)
+    cached = bn.__dict__.get("_folded")
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    with torch.no_grad():
+        sc = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        w = (conv.weight.float() * sc.view(-1, 1, 1, 1)).to(dtype).contiguous(memory_format=torch.channels_last)
+        b0 = conv.bias.float() if conv.bias is not None else 0.0
+        b = (bn.bias.float() + (b0 - bn.running_mean.float()) * sc).to(dtype)
+    bn.__dict__["_folded"] = (key, w, b)
+    return w, b
+
+
+def _conv_relu(x, conv, bn, z=None, extra_bias=None):
+    w, b = _fold(conv, bn, x.dtype)
+    if extra_bias is not None:
+        b = b + extra_bias
+    if z is None:
+        return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return torch.cudnn_convolution_add_relu(x, w, z, 1.0, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def _identity_eval(self, x):
+    """residual branch in inference: x, or the downsample convolution with its folded batch-norm's bias deferred to the block's
+    last fused call (both biases are added before the ReLU)"""
+    ds = self.downsample
+    if ds is None:
+        return x, None
+    w, b = _fold(ds[0], ds[1], x.dtype)
+    return torch.nn.functional.conv2d(x, w, None, ds[0].stride, ds[0].padding, ds[0].dilation, ds[0].groups), b
+
+
+def _block_can_fold(self, x, pairs):
+    if self.training or not _half_nhwc(x) or torch.is_grad_enabled():
+        return False
+    ds = self.downsample
+    if ds is not None and not (isinstance(ds, nn.Sequential) and len(ds) == 2 and _foldable(ds[0], ds[1])):
+        return False
+    return all(_foldable(getattr(self, c), getattr(self, b)) for c, b in pairs)
+
+
 def _bottleneck_forward(self, x):
-    """torchvision Bottleneck.forward with the ReLUs and the residual add folded into the batch-norm calls"""
+    """torchvision Bottleneck.forward with the ReLUs and the residual add folded into the batch-norm calls (training) or, with
+    the batch-norms folded into the weights, into cuDNN's fused convolutions (inference under no_grad)"""
+    if _block_can_fold(self, x, (("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3"))):
+        out = _conv_relu(x, self.conv1, self.bn1)
+        out = _conv_relu(out, self.conv2, self.bn2)
+        identity, bias = _identity_eval(self, x)
+        return _conv_relu(out, self.conv3, self.bn3, z=identity, extra_bias=bias)
     out = self.bn1(self.conv1(x), relu=True)
     out = self.bn2(self.conv2(out), relu=True)
     identity = x if self.downsample is None else self.downsample(x)
@@ -283,6 +345,10 @@ def _bottleneck_forward(self, x):
 
 
 def _basicblock_forward(self, x):
+    if _block_can_fold(self, x, (("conv1", "bn1"), ("conv2", "bn2"))):
+        out = _conv_relu(x, self.conv1, self.bn1)
+        identity, bias = _identity_eval(self, x)
+        return _conv_relu(out, self.conv2, self.bn2, z=identity, extra_bias=bias)
     out = self.bn1(self.conv1(x), relu=True)
     identity = x if self.downsample is None else self.downsample(x)
     return self.bn2(self.conv2(out), z=identity, relu=True)

@@ -698,7 +698,12 @@ class SAT(_Base):
         self.eval()
         dev = self.device
         cur = torch.cuda.current_stream(dev)
-        copy_stream = torch.cuda.Stream(dev)
+        # the two helper streams live with the module: the caching allocator keeps one pool per stream, so fresh streams per
+        # call would cudaMalloc (and implicitly synchronise) the staging buffers again every time
+        cache = self.__dict__.get("_stream_cache")
+        if cache is None or cache[0] != dev:
+            cache = self.__dict__["_stream_cache"] = (dev, torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        copy_stream, side = cache[1], cache[2]
 
         def stage(x):
             with torch.cuda.stream(copy_stream):
@@ -709,6 +714,14 @@ class SAT(_Base):
 
         vocab = dict(PAD=self.stoi("<PAD>"), START=self.stoi("<START>"), END=self.stoi("<END>"), UNK=self.stoi("<UNK>"))
         dw = decode.inference_weights(self)
+        # results of batch i are read back on a side stream that waits only for batch i's decode: the device-side gather of
+        # the selected attention maps and the device->host copies run next to batch i+1's kernels, and the host's
+        # synchronous reads do not wait for work queued after them
+        def finish(t, hw, done):
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                return decode.assemble(t, hw, return_all=return_all)
+
         it = iter(batches)
         nxt = next(it, None)
         staged = stage(nxt) if nxt is not None else None
@@ -722,11 +735,13 @@ class SAT(_Base):
             ann = self.encode(img)
             bld = decoder.annotations_as_bld(ann, dw.pw.dtype)
             t = decode.decode_annotations(dw, bld, int(beamk), max_gen_length, temperature, rescore_method, rescore_reward, vocab)
+            done = torch.cuda.Event()
+            done.record(cur)
             if pending is not None:
-                yield decode.assemble(*pending, return_all=return_all)
-            pending = (t, tuple(ann.shape[2:]))
+                yield finish(*pending)
+            pending = (t, tuple(ann.shape[2:]), done)
         if pending is not None:
-            yield decode.assemble(*pending, return_all=return_all)
+            yield finish(*pending)
 
     # ---- optimisers (model.py:720-817; host-side, stock torch) ---------------------------------
     def configure_optimizers(self):

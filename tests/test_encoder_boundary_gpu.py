@@ -150,7 +150,12 @@ def test_sat_module_uses_the_fused_trunk_and_keeps_the_reference_state_dict():
     m2.load_state_dict(m.state_dict())                                           # same running statistics
     m.eval(); m2.eval()
     with torch.no_grad():
-        assert torch.equal(m.encode(img.clone()), m2.encode(img.clone()))        # eval: stock batch-norm kernels in both
+        a, b = m.encode(img.clone()), m2.encode(img.clone())                     # inference: folded batch-norm + fused cuDNN convolutions
+    assert relerr(a.float(), b.float()) < 5e-2
+    with torch.enable_grad():                                                    # eval mode WITH autograd: the stock (differentiable) path
+        x = img.clone().requires_grad_(True)
+        y = m.encoder(x.contiguous(memory_format=torch.channels_last))
+    assert y.requires_grad
 
 
 @pytest.mark.parametrize("shape", [(4, 64, 7, 7, 14, 14), (3, 72, 8, 8, 14, 14), (2, 32, 5, 10, 16, 12), (2, 16, 9, 9, 6, 7)])
@@ -188,3 +193,44 @@ def test_resize_layer_matches_upsample(shape):
     assert torch.equal(xc.grad, g1)                              # deterministic
     # NCHW input: stock path
     assert torch.equal(layer(x.contiguous()), ref(x.contiguous()))
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_inference_trunk_with_folded_batchnorm(arch):
+    """eval mode under no_grad: the residual blocks fold the batch-norm into the convolution and call cuDNN's fused
+    convolution + bias (+ residual) + ReLU.  Yardstick as above: the fp32 eval trunk; the folded bf16 trunk must be as close to it
+    as the stock bf16 eval trunk; the folded weights follow parameter updates (version counters)."""
+    stock, fp32, fused = _trunks(arch)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    with torch.no_grad():                                   # non-trivial running statistics and affine parameters, same in all three
+        for net in (stock,):
+            for mod in net.modules():
+                if isinstance(mod, nn.BatchNorm2d):
+                    mod.running_mean.normal_(0, 0.2, generator=g)
+                    mod.running_var.uniform_(0.6, 1.6, generator=g)
+                    mod.weight.uniform_(0.7, 1.3, generator=g)
+                    mod.bias.normal_(0, 0.2, generator=g)
+    fp32.load_state_dict(stock.state_dict())
+    fused.load_state_dict(stock.state_dict())
+    x = torch.rand(8, 3, 128, 128, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    cos = lambda a, b: float((a.flatten().double() @ b.flatten().double()) / (a.double().norm() * b.double().norm()).clamp_min(1e-30))
+    for net in (stock, fp32, fused):
+        net.eval()
+    with torch.no_grad():
+        y0 = fp32(x.clone())
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ys, yf = stock(x.clone()), fused(x.clone())
+        assert yf.dtype == torch.bfloat16 and yf.shape == y0.shape
+        cs, cf = cos(ys.float(), y0), cos(yf.float(), y0)
+        print("%s inference: output cosine vs fp32 stock %.5f folded %.5f" % (arch, cs, cf))
+        assert cf > cs - 5e-3 and cf > 0.99
+        # the fold follows the parameters
+        for mod in fused.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.weight.mul_(0.5)
+        for mod in fp32.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.weight.mul_(0.5)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yf2 = fused(x.clone())
+        assert cos(yf2.float(), fp32(x.clone())) > 0.99 and not torch.equal(yf2, yf)
