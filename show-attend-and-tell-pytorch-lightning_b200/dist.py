@@ -38,12 +38,14 @@ class FlatGradBuckets:
     def _view(flat, off, p):
         """bucket slice with the parameter's own strides (channels_last conv weights keep their layout, so autograd's
         gradient-layout contract holds and no per-step transposes are inserted)."""
-        try:
-            if p.is_contiguous() or not p.is_non_overlapping_and_dense():
+        # exactly the parameter's strides, also where they are ambiguous (a channels_last 1x1 conv weight is "contiguous"
+        # with strides [Ci,1,Ci,Ci]): the fused optimizers require params, grads and state to have identical strides
+        expect = 1
+        for st, sz in sorted((st, sz) for sz, st in zip(p.shape, p.stride()) if sz != 1):
+            if st != expect:                               # not a permutation of a dense block: plain contiguous view
                 return flat[off:off + p.numel()].view_as(p)
-            return flat[off:off + p.numel()].as_strided(p.size(), p.stride())
-        except Exception:
-            return flat[off:off + p.numel()].view_as(p)
+            expect *= sz
+        return flat[off:off + p.numel()].as_strided(p.size(), p.stride())
 
     def zero(self):
         for f in self.flat:
