@@ -236,6 +236,11 @@ typedef struct SatDecodeBuffers {
   float* fin_ppl;        /* [n_img,k]  exp(-score/step) (model.py:425)                             */
   int32_t* fin_count;    /* [n_img]                                                               */
   const float* temps;    /* HOST pointer, [S+1]: temperature per step (model.py:292)              */
+  int32_t* live_images;  /* [1] device counter of images that still have live beams (optional, NULL = off)                  */
+  volatile int32_t* done_host; /* early-out (model.py:419,436: the reference stops an image's loop when its beams are used up):
+                            a pinned, device-accessible HOST int32.  The kernel that retires the last live image stores `call_id`
+                            there; the launch loop of sat_decode polls it before queueing the next step and stops when it matches.
+                            Effective when the host, not the GPU, paces the loop (few images); NULL = always run S+1 steps */
   int32_t k, max_gen_length, rescore;   /* rescore: 0 none, 1 LN, 2 WR, 3 BAR                      */
   float reward;
   int32_t tokPAD, tokSTART, tokEND, tokUNK;
@@ -246,6 +251,8 @@ typedef struct SatDecodeBuffers {
   int32_t kcap;          /* row pitch of cand_*: >= max(k, sample_topk); 0 = k                     */
   float decoder_noise;   /* base std-dev of the Gaussian noise added to h before the LSTM cell, scaled by 1/(step+1) */
   uint64_t sample_seed;  /* the sampling / noise draws are a pure function of (seed, step, row, word) */
+  int32_t call_id;       /* non-zero tag of this call for done_host (distinguishes calls still in flight on the stream) */
+  int32_t reserved1;
 } SatDecodeBuffers;
 
 int sat_version(void);

@@ -51,11 +51,11 @@ class SatDecodeBuffers(C.Structure):
     _fields_ = [(n, vp) for n in
                 ("ann", "P", "meanv", "f1", "init_out", "GxV", "h", "c", "hn", "cn", "hp", "z", "gz", "xo", "logits",
                  "alpha_all", "topk_stats", "cand_val", "cand_idx", "cand_key", "h_noisy", "tok_hist", "asrc_hist", "top_scores", "cur_tok", "src_row", "alive",
-                 "kcur", "fin_tokens", "fin_asrc", "fin_len", "fin_score", "fin_ppl", "fin_count", "temps")] + \
+                 "kcur", "fin_tokens", "fin_asrc", "fin_len", "fin_score", "fin_ppl", "fin_count", "temps", "live_images", "done_host")] + \
                [("k", C.c_int32), ("max_gen_length", C.c_int32), ("rescore", C.c_int32), ("reward", C.c_float),
                 ("tokPAD", C.c_int32), ("tokSTART", C.c_int32), ("tokEND", C.c_int32), ("tokUNK", C.c_int32),
                 ("sample_method", C.c_int32), ("sample_topk", C.c_int32), ("kcap", C.c_int32), ("decoder_noise", C.c_float),
-                ("sample_seed", C.c_uint64)]
+                ("sample_seed", C.c_uint64), ("call_id", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class SatParamGrads(C.Structure):

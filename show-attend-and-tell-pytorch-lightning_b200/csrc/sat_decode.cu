@@ -40,7 +40,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
                                                                                   d.H0 ? d.H0 : H, H, nl);
   SAT_COUNT_LAUNCH();
   decode_init_kernel<<<(R + 255) / 256, 256, 0, st>>>(b.cur_tok, b.alive, b.top_scores, b.kcur, b.fin_count, b.fin_len, R, n_img, k,
-                                                      b.tokSTART);
+                                                      b.tokSTART, b.live_images);
   SAT_COUNT_LAUNCH();
   SAT_LAUNCH_OK();
 
@@ -75,6 +75,8 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
   // instead of being gathered by source row
   void* h_cur = b.h; float* c_cur = b.c; void* h_nxt = b.hn; float* c_nxt = b.cn;
   for (int step = 0; step <= S; ++step) {
+    // every image has used up its beams (model.py:419,436): the steps not yet queued would only run dead rows
+    if (step > 0 && b.done_host != nullptr && b.live_images != nullptr && *b.done_host == b.call_id) break;
     const TS* h_top = (const TS*)h_cur + (nl - 1) * RH;      // attention, beta gate and the output layer read the top layer (model.py:299-300,327)
     if (!noisy && nl == 1) {
       SAT_TRY((gemm_tn<TS, TS>(tc, gemm_a1(h_cur, H, H), (const TS*)w.Whcat, H, R, NH3, EpiStore<float>{b.hp, NH3, w.bhcat, nullptr, 0},
@@ -138,7 +140,7 @@ int decode_impl(const SatDims& d, const SatWeights& w, SatDecodeBuffers& b, cuda
                             (const int32_t*)b.cand_idx, b.kcur, b.top_scores, b.cur_tok, b.src_row, b.alive,
                             (const int32_t*)(b.tok_hist + in * hist_sz), (const int32_t*)(b.asrc_hist + in * hist_sz),
                             b.tok_hist + out * hist_sz, b.asrc_hist + out * hist_sz, b.fin_tokens, b.fin_asrc, b.fin_len, b.fin_score,
-                            b.fin_ppl, b.fin_count));
+                            b.fin_ppl, b.fin_count, b.live_images, b.done_host, (int)b.call_id));
     SAT_COUNT_LAUNCH();
     if (k == 1) {
       void* th = h_cur; h_cur = h_nxt; h_nxt = th;

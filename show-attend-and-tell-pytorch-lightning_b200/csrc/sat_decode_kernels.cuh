@@ -388,7 +388,8 @@ beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, c
                    int32_t* __restrict__ src_row, int32_t* __restrict__ alive, const int32_t* __restrict__ tok_in,
                    const int32_t* __restrict__ asrc_in, int32_t* __restrict__ tok_out, int32_t* __restrict__ asrc_out,
                    int32_t* __restrict__ fin_tokens, int32_t* __restrict__ fin_asrc, int32_t* __restrict__ fin_len,
-                   float* __restrict__ fin_score, float* __restrict__ fin_ppl, int32_t* __restrict__ fin_count) {
+                   float* __restrict__ fin_score, float* __restrict__ fin_ppl, int32_t* __restrict__ fin_count,
+                   int32_t* __restrict__ live_images, volatile int32_t* done_host, int call_id) {
   SAT_PDL_TRIGGER();
   SAT_PDL_WAIT();
   constexpr int KMAX = 32;
@@ -521,6 +522,11 @@ beam_update_kernel(BeamParams p, int step, const float* __restrict__ cand_val, c
   if (lane == 0) {
     fin_count[n] += flush ? nnew : (nnew - s_kc_new);
     kcur[n] = flush ? 0 : s_kc_new;
+    // this image just used up its beams (it had kc > 0 on entry): the last image to do so tells the host's launch loop
+    if ((flush || s_kc_new == 0) && live_images != nullptr && atomicSub(live_images, 1) == 1 && done_host != nullptr) {
+      *done_host = call_id;
+      __threadfence_system();
+    }
   }
   const int kc_after = flush ? 0 : s_kc_new;
   for (int j = lane; j < k; j += 32) alive[r0 + j] = j < kc_after ? SAT_ALIVE : 0;
@@ -545,8 +551,9 @@ __global__ void gather_state_kernel(const T* __restrict__ hn, const float* __res
 }
 
 static __global__ void decode_init_kernel(int32_t* cur_tok, int32_t* alive, float* top_scores, int32_t* kcur, int32_t* fin_count,
-                                          int32_t* fin_len, int R, int n_img, int k, int tokSTART) {
+                                          int32_t* fin_len, int R, int n_img, int k, int tokSTART, int32_t* live_images) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && live_images != nullptr) *live_images = n_img;
   if (i < R) {
     cur_tok[i] = tokSTART;
     alive[i] = SAT_ALIVE;

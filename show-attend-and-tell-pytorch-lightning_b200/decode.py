@@ -28,10 +28,14 @@ class DecodeWeights:
         self.GxV = torch.empty(dm["V"], 4 * dm["H"], dtype=torch.float32, device=device)
         _lib.check(_lib.lib().sat_decode_prepare_weights(C.byref(d), self.pw.ref(), _lib.ptr(self.GxV), _lib.stream_ptr()),
                    "sat_decode_prepare_weights")
+        # early-out flag (include/sat_b200.h: done_host): pinned host int the device writes when every image has used up its
+        # beams; calls are told apart by a running tag
+        self.done = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.calls = 0
 
 
 def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_method=None, rescore_reward=0.5,
-                       vocab=None, sample_method="beam", sample_topk=3, decoder_noise=None, seed=None):
+                       vocab=None, sample_method="beam", sample_topk=3, decoder_noise=None, seed=None, early_out=True):
     """ann_bld [n_img,L,D] (dw.pw.dtype, cuda).  Returns dict of device tensors (fin_* + alpha_all) after
     enqueueing the whole decode; nothing is synchronised here.  sample_method "multinomial" / "topk" and decoder_noise
     (model.py:322-324,360-379) draw their randomness from `seed` (default: one draw from torch's CPU generator)."""
@@ -92,6 +96,10 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
     b.k, b.max_gen_length, b.rescore, b.reward = k, S, RESCORE[rescore_method], float(rescore_reward)
     b.tokPAD, b.tokSTART, b.tokEND, b.tokUNK = vocab["PAD"], vocab["START"], vocab["END"], vocab["UNK"]
     b.sample_method, b.sample_topk, b.kcap, b.decoder_noise, b.sample_seed = method, int(sample_topk), kcap, noise, int(seed or 0)
+    if early_out:
+        dw.calls = dw.calls % 0x7ffffff0 + 1
+        t["live_images"] = mk((1,), i32)
+        b.live_images, b.done_host, b.call_id = _lib.ptr(t["live_images"]), dw.done.data_ptr(), dw.calls
     _lib.check(L_.sat_decode(C.byref(d), dw.pw.ref(), C.byref(b), _lib.stream_ptr()), "sat_decode")
     t["ann"] = ann_bld
     t["_dims"] = (n_img, k, S, L)

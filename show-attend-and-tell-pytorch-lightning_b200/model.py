@@ -443,7 +443,11 @@ class SAT(_Base):
 
     # ---- plumbing -----------------------------------------------------------------------------
     def _dtype(self):
-        return torch.bfloat16 if str(self.hparams.precision).lower() in ("bf16", "bfloat16") else torch.float32
+        # the reference trains in fp32 or under PL's 16-bit AMP (train.py --precision 16).  The 16-bit mode here is bf16: same
+        # operand width, fp32 accumulation and master weights, no loss scaling needed (fp32's exponent range), and it is what
+        # the tcgen05 kernels take.  PL's spellings of mixed precision all select it.
+        half = ("bf16", "bfloat16", "bf16-mixed", "16", "16-mixed", "fp16", "half")
+        return torch.bfloat16 if str(self.hparams.precision).lower() in half else torch.float32
 
     def _cfg(self):
         dt = self._dtype()
@@ -557,7 +561,9 @@ class SAT(_Base):
             for p in self.encoder.parameters():
                 p.requires_grad = True
         loss, aux = self.fused_loss(batch, epsilon)
-        metrics = {"loss": loss, "accuracy": aux[3], "epsilon_tf": float(epsilon)}   # device scalars: no sync here
+        # device scalars: no sync here.  bad_token_ids = 1.0 when a caption held a word id outside [0, vocab_size): nn.Embedding
+        # would have raised; the kernels feed <PAD> for it and flag the step (include/sat_b200.h: out[6])
+        metrics = {"loss": loss, "accuracy": aux[3], "epsilon_tf": float(epsilon), "bad_token_ids": aux[6]}
         logger = getattr(self, "logger", None)
         if logger is not None and getattr(logger, "experiment", None) is not None:
             for k, v in metrics.items():

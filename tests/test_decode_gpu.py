@@ -161,3 +161,29 @@ def test_rows_that_die_mid_decode_produce_zero_attention():
                     assert float(row.abs().max()) == 0.0, (n, step, j)
                     checked_dead += 1
     assert checked_dead > 0                                # the golden's beams do shrink
+
+
+def test_early_out_stops_the_launch_loop_and_keeps_results():
+    """model.py:419,436: the reference leaves an image's loop when its beams are used up.  Here the kernel that retires the last
+    live image raises a host-visible flag and the launch loop stops queueing steps (it is the host that paces the loop for a
+    few images).  Same captions / scores as the full-length run, fewer launches."""
+    from sat_b200 import _lib, decode, decoder
+    D, A, E, H, V = 64, 32, 32, 64, 64
+    W = O.random_weights(D, A, E, H, V, seed=31, sharpen=True)
+    W["output.output.bias"][V - 1] = 30.0                       # <END> wins as soon as it is admissible (step 1)
+    g = torch.Generator().manual_seed(32)
+    ann = torch.randn(2, D, 3, 3, generator=g)
+    dw = decode.DecodeWeights(W, torch.float32, torch.device("cuda"), True, False)
+    bld = decoder.annotations_as_bld(ann.cuda(), torch.float32)
+    out, launches = {}, {}
+    for early in (False, True):
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        t = decode.decode_annotations(dw, bld, 3, 60, 1.0, "LN", 0.5, VOC(V), early_out=early)
+        launches[early] = _lib.launch_count() - n0
+        out[early] = decode.assemble(t, (3, 3), return_all=True)
+    assert out[True][0] == out[False][0] and out[True][1] == out[False][1]
+    assert max(len(c) for img in out[True][0] for c in img) <= 3
+    ref = O.caption(W, ann, VOC(V), beamk=3, max_gen_length=60, rescore_method="LN", return_all=True)
+    assert out[True][0] == ref[0]
+    assert launches[True] < launches[False], launches

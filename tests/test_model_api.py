@@ -66,3 +66,20 @@ def test_gate_interleave_roundtrip():
     p = interleave_gates(w)
     assert torch.equal(p[4 * 2 + 1], w[1 * 6 + 2])
     assert torch.equal(deinterleave_gates(p), w)
+
+
+def test_precision_spellings_and_stacked_layers_surface():
+    """PL's 16-bit spellings select the bf16 kernels (the fp16-AMP equivalent on B200); decoder_layers > 1 builds the reference's
+    parameter set (lstm.*_l{l}, init_lstm.init of 2*layers*H rows)."""
+    from sat_b200.model import SAT
+    for prec, want in ((32, torch.float32), ("32-true", torch.float32), (16, torch.bfloat16), ("16-mixed", torch.bfloat16),
+                       ("bf16", torch.bfloat16), ("bf16-mixed", torch.bfloat16)):
+        m = SAT(**small_hp(precision=prec, encoder_arch="resnet18"))
+        assert m._dtype() == want, prec
+    m = SAT(**small_hp(decoder_layers=3, encoder_arch="resnet18"))
+    sd = m.state_dict()
+    assert sd["lstm.weight_ih_l2"].shape == (4 * 512, 512) and sd["init_lstm.init.weight"].shape == (2 * 3 * 512, 256)
+    names = [n for n, _ in zip(__import__("sat_b200.packing", fromlist=["x"]).param_names(3), m.decoder_weights())]
+    assert names[-4:] == ["lstm.weight_ih_l2", "lstm.weight_hh_l2", "lstm.bias_ih_l2", "lstm.bias_hh_l2"]
+    with pytest.raises(NotImplementedError):
+        SAT(**small_hp(decoder_layers=9, encoder_arch="resnet18"))
