@@ -157,13 +157,17 @@ def load_peaks():
         return {}
 
 
-def load_traffic():
-    """DRAM bytes per launch of the named kernels from the committed `ncu --set full` capture (profiles/r02_kernel_traffic.json,
-    written by tools/ncu_traffic.py from the .ncu-rep of the same bench command)."""
+def load_traffic(workload):
+    """DRAM bytes per launch of the named kernels from the committed `ncu --set full` captures of the same decoder workloads
+    (profiles/r02_kernel_traffic.json, one entry per workload, written by tools/ncu_traffic.py from tools/profile_round2.sh's
+    .ncu-rep files); {} when that workload has no capture (traffic: null)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")))
     except Exception:
         return {}
+    if workload in d:
+        return d[workload]
+    return d if (workload == "train" and "attention_step_fwd_pipe_kernel" in d) else {}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -362,13 +366,20 @@ def timed(D, fn, steps, warmup, drain=None):
     return D.max_ms(evs[0].elapsed_time(evs[steps])), per
 
 
-def roof_entry(kernel, bound, work, ms, n, peak, unit, traffic, **extra):
+def roof_entry(kernel, bound, work, ms, n, peak, unit, traffic, traffic_keys=None, **extra):
+    """`traffic`: the committed ncu capture of THIS workload ({} = none: traffic null); traffic_keys: entries of it to sum
+    (default: the kernel's own name)"""
     per_launch_s = ms / max(n, 1) * 1e-3
     scale = 1e9 if unit == "GB/s" else 1e12
     achieved = work / per_launch_s / scale if n else None
+    tr = None
+    if isinstance(traffic, dict) and traffic:
+        # every key is a substring of exactly one captured kernel name (template arguments included)
+        hits = [[v for k, v in traffic.items() if sub in k] for sub in (traffic_keys or [kernel])]
+        if all(len(h) == 1 for h in hits):
+            tr = sum(h[0]["dram_bytes_per_launch"] for h in hits)
     e = {"kernel": kernel, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": (achieved / peak) if achieved else None,
-         "traffic": traffic.get(kernel, {}).get("dram_bytes_per_launch") if isinstance(traffic, dict) else None, "launches_timed": n,
-         "avg_launch_us": 1e6 * per_launch_s}
+         "traffic": tr, "launches_timed": n, "avg_launch_us": 1e6 * per_launch_s}
     e["algorithmic_%s_per_launch" % ("bytes" if bound == "hbm" else "flops")] = work
     e.update(extra)
     return e
@@ -480,7 +491,7 @@ def run_train(args, D, name):
     dec_ms, dec_per = timed(D, dec_step, args.steps, args.warmup)
 
     # rooflines: in-situ device time of the named kernels' launches (CUDA events around every launch inside the decoder step)
-    peaks, traffic = load_peaks(), load_traffic()
+    peaks, traffic = load_peaks(), (load_traffic(name) if B == c["B"] else {})
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     tfl = float(peaks.get("bf16_tflops", 1590.0))
     src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops burst)" if peaks else "fallback 6650 GB/s / 1590 TFLOP/s"
@@ -504,9 +515,10 @@ def run_train(args, D, name):
         roof_entry("attention_step_bwd_pipe_kernel", "hbm", B * (L * (A + Dd) * s + 2 * Dd * s + 8 * L), attb_ms, attb_n, hbm, "GB/s", traffic),
         roof_entry("gemm_tn_tc_kernel<EpiVocab> x2 + ce_finalize_kernel (fused vocabulary projection + cross entropy)", "tensor",
                    2 * 2.0 * M * V * E, voc_ms, voc_n, tfl, "TFLOP/s", traffic,
+                   traffic_keys=["EpiVocab<0>", "EpiVocab<1>"],
                    note="one launch group = statistics pass + row finalize + dlogits pass (the logits are computed twice, never stored)"),
         roof_entry("gemm_tn_tc_kernel<EpiLstm> (gate GEMM + LSTM cell)", "tensor", 2.0 * B * Dd * 4 * H, gate_ms, gate_n, tfl, "TFLOP/s", traffic,
-                   note="M = batch rows only: launch / latency bound, see DESIGN.md"),
+                   traffic_keys=["EpiLstm"], note="M = batch rows only: launch / latency bound, see DESIGN.md"),
     ]
     rec = {
         "value": value, "unit": "captions/s", "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
@@ -575,7 +587,7 @@ def run_decode(args, D, name):
     voc_ms, voc_n = _lib.profile_end()
     s = 2 if dw.pw.dtype == torch.bfloat16 else 4
     R = B * c["k"]
-    peaks, traffic = load_peaks(), load_traffic()
+    peaks, traffic = load_peaks(), load_traffic(name)
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     tfl = float(peaks.get("bf16_tflops", 1590.0))
     att_bytes = B * c["L"] * (c["A"] + c["D"]) * s + R * ((c["H"] + 2 * c["D"]) * s + 4 * c["L"])   # per image-step + per row
@@ -583,7 +595,7 @@ def run_decode(args, D, name):
     roof = roof_entry(kname, "hbm", att_bytes, att_ms, att_n, hbm, "GB/s", traffic,
                       peak_source="MEASURED_PEAKS.json (hbm_gbs, bf16_tflops burst)" if peaks else "fallback 6650 GB/s / 1590 TFLOP/s")
     roof["other_kernels"] = [roof_entry("vocabulary GEMM (gemm_tn_tc_kernel, M = live rows)", "tensor", 2.0 * R * c["V"] * c["E"], voc_ms, voc_n,
-                                        tfl, "TFLOP/s", traffic)]
+                                        tfl, "TFLOP/s", traffic, traffic_keys=["EpiVocab<2>" if c["k"] == 1 else "gemm_tn_tc_kernel<128, EpiStore"])]
     rec = {
         "value": value, "unit": "captions/s", "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
         "step_p50_ms": statistics.median(per), "dtype": "bf16" if args.precision == "bf16" else "f32",
@@ -615,7 +627,7 @@ def run_b200(args):
     if D.rank == 0:
         if D.world == 1 and not args.no_cpu_baseline:
             for n in names:
-                r = cpu_workload(n, steps=2 if n in ("train", "c3") else 1, warmup=1)
+                r = cpu_workload(n, steps=5 if n == "train" else 3, warmup=1)       # ≈20 s of host time in total
                 cb = {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
                 if n == head:
                     line["cpu_baseline"] = cb

@@ -1,5 +1,6 @@
 """Per-kernel DRAM traffic and key counters from an `ncu --set full` report, for bench.py's roofline.traffic:
-    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv ;  python tools/ncu_traffic.py raw.csv profiles/r02_kernel_traffic.json [summary.txt]
+    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv ;  python tools/ncu_traffic.py raw.csv profiles/r02_kernel_traffic.json [summary.txt [workload]]
+With a workload name (train / c3 / greedy / beam) the result is merged into the JSON under that key and the summary is appended.
 Averages over the captured launches of each kernel: dram bytes read + written, duration, warps active, issue active,
 tensor-pipe activity, L2 hit rate, registers.  The JSON maps the kernel's base name to {"dram_bytes_per_launch": ...}."""
 import collections
@@ -40,14 +41,23 @@ for row in rd:
 res, txt = {}, []
 for name, d in agg.items():
     mean = {k: sum(v) / len(v) for k, v in d.items()}
-    base = re.sub(r"<.*", "", name)
     e = {"launches": len(d.get("duration", [])), "dram_bytes_per_launch": mean.get("dram_read", 0.0) + mean.get("dram_write", 0.0),
          "duration_us": mean.get("duration"), **{k: mean.get(k) for k in ("warps_active_pct", "issue_active_pct", "tensor_pipe_pct", "l2_hit_pct", "dram_pct", "sm_pct", "regs", "grid", "block")}}
-    res[base if base not in res else name] = e
+    res[name] = e                                   # full name incl. template arguments (bench.py matches by substring)
     txt.append("%-70s n=%d  %.1f us  dram %.2f MB/launch (%.0f%% of peak)  warps active %.0f%%  issue active %.0f%%  tensor pipe %.0f%%  L2 hit %.0f%%  regs %s  grid %s x %s"
                % (name[:70], e["launches"], e["duration_us"] or 0, e["dram_bytes_per_launch"] / 1e6, e["dram_pct"] or 0, e["warps_active_pct"] or 0,
                   e["issue_active_pct"] or 0, e["tensor_pipe_pct"] or 0, e["l2_hit_pct"] or 0, e["regs"], e["grid"], e["block"]))
+workload = sys.argv[4] if len(sys.argv) > 4 else None
+if workload:
+    try:
+        full = json.load(open(out_json))
+    except Exception:
+        full = {}
+    full = {k: v for k, v in full.items() if k in ("train", "c3", "greedy", "beam")}     # drop entries of the un-keyed format
+    full[workload] = res
+    res = full
 json.dump(res, open(out_json, "w"), indent=1)
 print("\n".join(txt))
 if len(sys.argv) > 3:
-    open(sys.argv[3], "w").write("\n".join(txt) + "\n")
+    with open(sys.argv[3], "a" if workload else "w") as f:
+        f.write(("[%s]\n" % workload if workload else "") + "\n".join(txt) + "\n")
