@@ -234,3 +234,28 @@ def test_inference_trunk_with_folded_batchnorm(arch):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             yf2 = fused(x.clone())
         assert cos(yf2.float(), fp32(x.clone())) > 0.99 and not torch.equal(yf2, yf)
+
+
+@pytest.mark.parametrize("arch", ["resnext50_32x4d", "densenet121", "shufflenet_v2_x0_5", "mobilenet_v3_small", "squeezenet1_0"])
+def test_other_reference_trunks_run_through_the_swapped_modules(arch):
+    """the reference accepts every torchvision family in model.py:27-43; the cuDNN-routed modules must cope with their shapes
+    (grouped convolutions, concatenated feature maps, ReLU6 / Hardswish activations that are NOT fused): train step and
+    inference produce finite annotations / gradients of the reference's shape"""
+    from oracle import ref_harness as rh
+    from sat_b200.model import SAT
+    hp = rh.default_hparams(encoder_arch=arch, encoder_dim=64, attention_dim=32, embed_dim=32, decoder_dim=64, vocab_size=128,
+                            input_size=96, precision="bf16")
+    torch.manual_seed(0)
+    m = SAT(**hp).cuda()
+    m.encoder.to(memory_format=torch.channels_last)
+    img = torch.rand(4, 3, 96, 96, device="cuda")
+    m.train()
+    a = m.encode(img.clone())
+    assert a.shape[:2] == (4, 64) and torch.isfinite(a.float()).all()
+    a.float().square().mean().backward()
+    grads = [p.grad for p in m.encoder.parameters() if p.requires_grad]
+    assert grads and all(g is not None and torch.isfinite(g).all() for g in grads)
+    m.eval()
+    with torch.no_grad():
+        b = m.encode(img.clone())
+    assert b.shape == a.shape and torch.isfinite(b.float()).all()

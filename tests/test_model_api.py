@@ -83,3 +83,24 @@ def test_precision_spellings_and_stacked_layers_surface():
     assert names[-4:] == ["lstm.weight_ih_l2", "lstm.weight_hh_l2", "lstm.bias_ih_l2", "lstm.bias_hh_l2"]
     with pytest.raises(NotImplementedError):
         SAT(**small_hp(decoder_layers=9, encoder_arch="resnet18"))
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "densenet121", "shufflenet_v2_x0_5"])
+def test_encoder_boundary_swaps_keep_keys_and_cpu_results(arch):
+    """bf16 mode swaps batch-norm / ReLU / max-pool modules of the third-party trunk for the cuDNN-routed ones (sat_b200/cudnn_bn.py);
+    the state_dict keys stay the reference's and every swapped module falls back to the stock computation where cuDNN does not
+    apply (here: CPU, fp32), bit for bit."""
+    from sat_b200.model import SAT
+    torch.manual_seed(0)
+    a = SAT(**small_hp(encoder_arch=arch, precision="bf16"))
+    torch.manual_seed(0)
+    b = SAT(**small_hp(encoder_arch=arch, precision="bf16", cudnn_batchnorm=False))
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    assert any(type(m).__name__ == "CudnnBatchNorm2d" for m in a.encoder.modules())
+    assert not any(type(m).__name__ == "CudnnBatchNorm2d" for m in b.encoder.modules())
+    x = torch.rand(2, 3, 224, 224)
+    for mode in ("eval", "train"):
+        getattr(a, mode)()
+        getattr(b, mode)()
+        with torch.no_grad():
+            assert torch.equal(a.encoder(x.clone()), b.encoder(x.clone())), mode
