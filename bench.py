@@ -403,7 +403,10 @@ def run_train(args, D, name):
     opt = model.configure_optimizers()
     enc_params = [p for p in model.encoder.parameters() if p.requires_grad]
     dec_params = [p for n, p in model.named_parameters() if not n.startswith("encoder.") and p.requires_grad]
-    reducer = OverlappedGradReducer(dec_params, enc_params) if world > 1 else None
+    # SAT_BENCH_NO_REDUCE=1: diagnosis only (replicas without the gradient exchange, to separate communication cost from
+    # two-process effects); the record is marked and is not a valid data-parallel number
+    no_reduce = world > 1 and os.environ.get("SAT_BENCH_NO_REDUCE", "0") == "1"
+    reducer = OverlappedGradReducer(dec_params, enc_params) if (world > 1 and not no_reduce) else None
     img_d, caps_d, lens_d = synth_batch(B, T, V, seed=100 + rank, device=dev)
     img_h, caps_h, lens_h = synth_batch(B, T, V, seed=100 + rank, pin=True)
 
@@ -522,8 +525,8 @@ def run_train(args, D, name):
     ]
     rec = {
         "value": value, "unit": "captions/s", "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
-        "step_p50_ms": statistics.median(per), "dtype": "bf16" if args.precision == "bf16" else "f32",
-        "config": config_dict(name, c, B, world), "clocks": clk,
+        "step_p50_ms": statistics.median(per), "steps_ms": [round(x, 3) for x in per], "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "config": dict(config_dict(name, c, B, world), **({"INVALID_no_gradient_exchange": True} if no_reduce else {})), "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
@@ -532,6 +535,25 @@ def run_train(args, D, name):
                          "what": "weight pack + decoder fwd + loss + BPTT + parameter gradients (all libsat_b200 kernels), annotations resident"},
         "roofline": roof,
     }
+    if reducer is not None:
+        # self-check of the data-parallel path (untimed): after one step's exchange every rank must hold the same gradients,
+        # and they must differ from the rank's own local gradients (the ranks see different data)
+        import torch.distributed as dist
+        probe = [p for p in dec_params[:3] + enc_params[:2] + enc_params[-2:]]
+        loss, _ = model.fused_loss((img_d.clone(), caps_d, lens_d))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        local = torch.stack([p.grad.double().sum() for p in probe])
+        loss, _ = model.fused_loss((img_d.clone(), caps_d, lens_d))
+        reducer.prepare()
+        loss.backward()
+        reducer.finish()
+        mine = torch.stack([p.grad.double().sum() for p in probe])
+        both = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert all(torch.equal(both[0], b) for b in both), "gradients differ across ranks after the all-reduce"
+        assert not torch.allclose(mine, local, rtol=1e-6, atol=0), "all-reduce left the local gradients unchanged"
+        opt.zero_grad(set_to_none=True)
     if reducer is not None:
         reducer.close()
     del model, opt, reducer

@@ -261,6 +261,7 @@ class CudnnBatchNorm2d(nn.BatchNorm2d):
                 self.num_batches_tracked.add_(1)
         rm = self.running_mean if self.track_running_stats else None
         rv = self.running_var if self.track_running_stats else None
+        self.__dict__["_stats_gen"] = self.__dict__.get("_stats_gen", 0) + 1      # invalidates the inference fold (see _fold)
         ops = _OPS_BN if not relu else (_OPS_BN_ACT if z is None else _OPS_BN_ADD_ACT)
         if z is not None and not z.is_contiguous(memory_format=torch.channels_last):
             z = z.contiguous(memory_format=torch.channels_last)
@@ -289,7 +290,8 @@ def _fold(conv, bn, dtype):
     """(weight, bias) of the convolution with the eval-mode batch-norm folded in: w * g/sqrt(var+eps), beta + (b - mean) * g/sqrt(var+eps);
     computed in fp32, stored once in `dtype` (channels_last) and rebuilt when any source tensor changes (version counters)."""
     src = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
-    key = tuple((t.data_ptr(), t._version) if t is not None else None for t in src) + (dtype,)
+    # (_stats_gen: cuDNN updates the running statistics through raw pointers, which torch's version counters do not see)
+    key = tuple((t.data_ptr(), t._version) if t is not None else None for t in src) + (dtype, bn.__dict__.get("_stats_gen", 0))
     cached = bn.__dict__.get("_folded")
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]

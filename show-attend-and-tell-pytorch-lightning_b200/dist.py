@@ -81,9 +81,15 @@ class OverlappedGradReducer:
     Bucket 0 holds the decoder parameters: their gradients are all final when the fused decoder backward returns, i.e.
     BEFORE the encoder backward starts, so its all-reduce travels over NVLink while cuDNN runs the trunk's backward.  The
     encoder parameters follow in REVERSE order (autograd produces the last layers' gradients first) in buckets of
-    ~`bucket_bytes`; a post-accumulate-grad hook per parameter counts a bucket down and issues its asynchronous
-    all-reduce (ReduceOp.AVG on NCCL: no separate scaling pass) the moment its last gradient has landed.  `.grad` of every
-    parameter is a view into its bucket, zeroed by prepare() so that autograd accumulates in place.
+    ~`bucket_bytes`, tapering to 16 / 4 / 1 MB at the stem end (only the last bucket's all-reduce cannot hide under backward).
+    A post-accumulate-grad hook per parameter counts its bucket down; when the last gradient has landed the bucket's gradient
+    tensors are gathered into its flat fp32 buffer by ONE multi-tensor copy, `.grad` of every parameter becomes a view (with
+    the parameter's strides) into that buffer, and ONE asynchronous all-reduce (ReduceOp.AVG on NCCL: no scaling pass) is issued.
+
+    Two designs were measured and dropped (BASELINE configs[1] / [2], N=2): (a) pre-assigned, pre-zeroed bucket views as `.grad`
+    -- autograd then launches one accumulation kernel per parameter instead of handing its result over (+1.1 ms per 32 ms
+    step for ~180 parameters); (b) no flat buffers, a coalesced NCCL group over the raw gradient tensors -- fastest in steady
+    state (+0.4 ms) but with ~330 operations per step at configs[2] the host sporadically stalls 100-400 ms inside NCCL.
 
         reducer.prepare(); loss.backward(); reducer.finish(); optimizer.step()
     """
@@ -93,16 +99,19 @@ class OverlappedGradReducer:
         dec = [p for p in dec_params if p.requires_grad]
         enc = [p for p in enc_params if p.requires_grad][::-1]
         self.buckets = [dec] if dec else []
-        cur, cur_n = [], 0
-        for p in enc:
+        caps = [min(c << 20, bucket_bytes) for c in (1, 4, 16)]
+        rev, cur, cur_n = [], [], 0
+        for p in enc[::-1]:                                   # forward (registration) order: stem first
             n = p.numel()
-            if cur and (cur_n + n) * 4 > bucket_bytes:
-                self.buckets.append(cur)
+            cap = caps[len(rev)] if len(rev) < len(caps) else bucket_bytes
+            if cur and (cur_n + n) * 4 > cap:
+                rev.append(cur[::-1])
                 cur, cur_n = [], 0
             cur.append(p)
             cur_n += n
         if cur:
-            self.buckets.append(cur)
+            rev.append(cur[::-1])
+        self.buckets += rev[::-1]                             # backward order again: last layers first, stem last
         self.flat, self.views = [], []
         for b in self.buckets:
             flat = torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
@@ -133,37 +142,47 @@ class OverlappedGradReducer:
         return hook
 
     def _launch(self, bi):
-        if self._handles[bi] is not None or self._world <= 1:
+        if self._handles[bi] is not None:
             return
-        # a parameter whose .grad was re-assigned (not accumulated in place) is copied back into its bucket slot first
+        src, dst = [], []
         for p, v in zip(self.buckets[bi], self.views[bi]):
-            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
+            if p.grad is None:
+                v.zero_()                                     # no gradient this step (must be so on every rank)
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)                    # one multi-tensor kernel per bucket
+        for p, v in zip(self.buckets[bi], self.views[bi]):
+            if p.grad is not None:
                 p.grad = v
+        if self._world <= 1:
+            self._handles[bi] = ()
+            return
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
-        self._handles[bi] = dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True)
+        self._handles[bi] = (dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True),)
 
     def prepare(self):
-        """before backward(): zero the buckets (autograd accumulates into the views) and arm the hooks"""
-        for bi, (b, flat, views) in enumerate(zip(self.buckets, self.flat, self.views)):
-            flat.zero_()
-            for p, v in zip(b, views):
-                p.grad = v
+        """before backward(): gradients back to None (autograd hands over its result tensors) and arm the hooks"""
+        for bi, b in enumerate(self.buckets):
+            for p in b:
+                p.grad = None
             self._pending[bi] = len(b)
             self._handles[bi] = None
         self._armed = True
 
     def finish(self):
-        """after backward(): reduce buckets whose hooks did not all fire (unused parameters), wait for every all-reduce"""
+        """after backward(): reduce buckets whose hooks did not all fire (parameters without a gradient this step), wait for
+        every all-reduce"""
         self._armed = False
         for bi in range(len(self.buckets)):
             if self._handles[bi] is None:
                 self._launch(bi)
-        for bi, h in enumerate(self._handles):
-            if h is not None:
+        for bi, hs in enumerate(self._handles):
+            for h in hs or ():
                 h.wait()
-                if not self._avg:
-                    self.flat[bi].mul_(1.0 / self._world)
+            if hs and not self._avg:
+                self.flat[bi].mul_(1.0 / self._world)
 
     def close(self):
         for h in self._hooks:

@@ -144,6 +144,9 @@ def test_sat_module_uses_the_fused_trunk_and_keeps_the_reference_state_dict():
     m.encoder.to(memory_format=torch.channels_last)
     m2.encoder.to(memory_format=torch.channels_last)
     img = torch.rand(8, 3, 64, 64, device="cuda")
+    m.eval()
+    with torch.no_grad():
+        before = m.encode(img.clone())                                           # builds the folded inference weights once
     m.train(); m2.train()
     a, b = m.encode(img.clone()), m2.encode(img.clone())
     assert a.shape == b.shape and relerr(a.float(), b.float()) < 5e-2
@@ -152,6 +155,7 @@ def test_sat_module_uses_the_fused_trunk_and_keeps_the_reference_state_dict():
     with torch.no_grad():
         a, b = m.encode(img.clone()), m2.encode(img.clone())                     # inference: folded batch-norm + fused cuDNN convolutions
     assert relerr(a.float(), b.float()) < 5e-2
+    assert not torch.equal(a, before)                                            # the fold followed the new running statistics
     with torch.enable_grad():                                                    # eval mode WITH autograd: the stock (differentiable) path
         x = img.clone().requires_grad_(True)
         y = m.encoder(x.contiguous(memory_format=torch.channels_last))
