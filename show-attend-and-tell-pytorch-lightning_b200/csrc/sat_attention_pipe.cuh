@@ -1563,13 +1563,10 @@ static int launch_attention_fwd(const T* ann, const T* P, const float* wf, const
   }
   const size_t smem = attention_fwd_pipe_smem(L, D, A, Vec16<T>::N);
   auto kern = attention_step_fwd_pipe_kernel<T, kExact, ATTP_FWD_CW>;
-  static size_t smem_set[64] = {0};           // the attribute is per device
-  int dev_now = 0;
-  SAT_CUDA(cudaGetDevice(&dev_now));
-  if (smem > smem_set[dev_now & 63]) {
-    SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[dev_now & 63] = smem;
-  }
+  // set on every launch (sub-microsecond): a per-translation-unit cache of "largest value set so far" is wrong here, because the
+  // kernel is one function for the whole library while this launcher is compiled into several translation units -- another
+  // unit's launcher may have lowered the attribute in between (seen as "invalid argument" in a long mixed train / decode run)
+  if (smem > 48 * 1024) SAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SAT_CUDA(sat_launch_pdl(kern, dim3(rows), dim3(ATTP_FWD_CW * 32 + 32), smem, st, ann, P, wf, hp, ldhp, lens, t, ncap, L, D, A, scale, alpha,
                           ld_alpha, qsave, z, gz, beta, ld_z, lens_dyn));
   SAT_COUNT_LAUNCH();

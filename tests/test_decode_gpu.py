@@ -187,3 +187,18 @@ def test_early_out_stops_the_launch_loop_and_keeps_results():
     ref = O.caption(W, ann, VOC(V), beamk=3, max_gen_length=60, rescore_method="LN", return_all=True)
     assert out[True][0] == ref[0]
     assert launches[True] < launches[False], launches
+
+
+def test_train_and_decode_alternating_shapes_share_the_attention_kernel():
+    """regression: training with a large annotation map, decoding with a small one, training again -- the shared-memory opt-in
+    of the attention kernel is one attribute for the whole library, whichever driver launched last"""
+    from test_train_backward_gpu import run_cuda_fwd_bwd
+    from test_train_forward_gpu import synth
+    big = dict(Bi=4, ncap=1, hw=(14, 14), D=512, A=128, E=64, H=64, V=128, T=4, ragged=True)
+    small = dict(Bi=4, ncap=1, hw=(12, 12), D=512, A=128, E=64, H=64, V=128, T=4, ragged=True)
+    Wb, annb, capsb, lensb = synth(**big)
+    Ws, anns, _, _ = synth(**small, sharpen=True)
+    l1, _, _ = run_cuda_fwd_bwd(Wb, annb, capsb, lensb, 0.0, 1.0)
+    cuda_caption(Ws, anns, 1, 6)
+    l2, _, _ = run_cuda_fwd_bwd(Wb, annb, capsb, lensb, 0.0, 1.0)
+    assert l1 == l2
