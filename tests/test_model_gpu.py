@@ -296,3 +296,44 @@ def test_training_loop_trajectory_matches_oracle_with_adam(layers):
         optb.step()
         first = float(out["loss"]) if first is None else first
     assert float(out["loss"]) < 0.5 * first, (first, float(out["loss"]))
+
+
+def test_val_batch_and_validation_step_against_the_reference_callers():
+    """§8 f4: val_batch / validation_step (model.py:684-697) = caption() + score_captions().  Ours on the GPU against the unmodified
+    reference on the CPU with the same weights and batch (when the staged reference is present; its nltk imports are pointed at
+    sat_b200.metrics, whose BLEU / GLEU are pinned to nltk's docstring values in tests/test_callers_cpu.py): identical captions,
+    hence identical scores."""
+    import sys
+    m = build(seed=11)
+    with torch.no_grad():
+        m.output.output.weight *= 6
+    g = torch.Generator().manual_seed(12)
+    ann = torch.randn(4, 64, 4, 3, generator=g)
+    caps = torch.randint(1, 124, (4, 3, 9), generator=g)
+    caps[:, :, 0] = 126
+    lens = torch.randint(2, 8, (4, 3), generator=g)
+    for i in range(4):
+        for j in range(3):
+            caps[i, j, int(lens[i, j])] = 127
+            caps[i, j, int(lens[i, j]) + 1:] = 0
+    out = m.val_batch((ann.cuda(), caps.cuda(), lens.cuda()), beamk=3, max_gen_length=8, temperature=1.0, rescore_method="LN")
+    assert {"bleu1", "bleu2", "bleu3", "bleu4", "gleu", "cosine_similarity", "perplexity"} <= set(out.keys())
+    got_caps, _, _, ppl = m.caption(ann.cuda(), beamk=3, max_gen_length=8, temperature=1.0, rescore_method="LN")
+    again = m.score_captions(got_caps, caps, lens, ppl)
+    assert all(abs(out[k] - again[k]) < 1e-9 for k in out)
+    m.hparams["val_beamk"], m.hparams["val_max_len"] = 3, 8
+    vs = m.validation_step((ann.cuda(), caps.cuda(), lens.cuda()), 0)
+    assert all(abs(out[k] - vs[k]) < 1e-9 for k in out)
+    if not rh.available():
+        return
+    model_mod, _ = rh.load_reference()
+    from sat_b200 import metrics
+    model_mod.corpus_bleu, model_mod.corpus_gleu = metrics.corpus_bleu, metrics.corpus_gleu
+    hp = rh.default_hparams(encoder_dim=64, attention_dim=32, embed_dim=32, decoder_dim=64, vocab_size=128, input_size=64)
+    ref = model_mod.SAT(**hp)
+    ref.encoder = nn.Identity()
+    ref.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    want = ref.val_batch([ann.clone(), caps, lens], beamk=3, max_gen_length=8, temperature=1.0, rescore_method="LN")
+    assert set(want.keys()) == set(out.keys())
+    for k in want:
+        assert abs(float(want[k]) - float(out[k])) < 1e-5 * max(1.0, abs(float(want[k]))), k
