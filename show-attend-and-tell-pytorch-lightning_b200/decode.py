@@ -107,53 +107,48 @@ def decode_annotations(dw, ann_bld, k, max_gen_length, temperature=1.0, rescore_
 
 
 def assemble(t, hw, return_all=False, want_alphas=True):
-    """fin_* device arrays -> the reference's four lists."""
+    """fin_* device arrays -> the reference's four lists.  Host side is vectorised (numpy) up to the final Python lists: with many
+    GPUs per host the list assembly, not the device, bounds end-to-end captioning."""
     n_img, k, S, L = t["_dims"]
     cnt = t["fin_count"].cpu().numpy()
     ln = t["fin_len"].cpu().numpy()
-    sc32 = t["fin_score"].cpu()
-    sc = sc32.numpy().astype(np.float64)
+    sc = t["fin_score"].cpu().numpy().astype(np.float64)
     ppl = t["fin_ppl"].cpu().numpy().astype(np.float64)
     toks = t["fin_tokens"].cpu().numpy()
     # which hypotheses are returned, in which order
-    sel = []                                   # per image: list of finished-slot indices
-    for n in range(n_img):
-        c = int(cnt[n])
-        if return_all:                          # sort [score, index] pairs descending (model.py:455-457)
-            order = sorted(range(c), key=lambda i: (sc[n, i], i), reverse=True)
-        else:                                   # first index of the maximum (model.py:463)
-            order = [int(np.argmax(sc[n, :c]))]
-        sel.append(order)
-    alphas_out = None
+    if return_all:                              # sort [score, index] pairs descending (model.py:455-457)
+        sel = [sorted(range(int(cnt[n])), key=lambda i: (sc[n, i], i), reverse=True) for n in range(n_img)]
+    else:                                       # first index of the maximum (model.py:463)
+        masked = np.where(np.arange(sc.shape[1])[None, :] < cnt[:, None], sc, -np.inf)
+        sel = [[int(i)] for i in masked.argmax(1)]
+    img_of = np.fromiter((n for n in range(n_img) for _ in sel[n]), dtype=np.int64)
+    slot_of = np.fromiter((i for n in range(n_img) for i in sel[n]), dtype=np.int64)
+    lens_sel = ln[img_of, slot_of].astype(np.int64) if len(img_of) else np.zeros(0, np.int64)
+    alphas_flat = None
     if want_alphas:
         # gather alpha rows of the selected hypotheses on the device, one D2H copy
-        asrc = t["fin_asrc"].cpu().numpy()
-        steps, rows, offs = [], [], []
-        for n in range(n_img):
-            for i in sel[n]:
-                l = int(ln[n, i])
-                offs.append((len(steps), l))
-                steps.extend(range(l))
-                rows.extend(asrc[n, i, :l].tolist())
-        if steps:
+        if lens_sel.sum() > 0:
+            asrc = t["fin_asrc"].cpu().numpy()
+            width = asrc.shape[2]
+            mask = np.arange(width)[None, :] < lens_sel[:, None]                  # [n_sel, S+1]
+            rows = asrc[img_of, slot_of][mask]
+            steps = np.broadcast_to(np.arange(width)[None, :], mask.shape)[mask]
             dev = t["alpha_all"].device
-            st = torch.tensor(steps, dtype=torch.long, device=dev)
-            rw = torch.tensor(rows, dtype=torch.long, device=dev)
+            st = torch.from_numpy(np.ascontiguousarray(steps)).to(dev, non_blocking=False)
+            rw = torch.from_numpy(np.ascontiguousarray(rows).astype(np.int64)).to(dev, non_blocking=False)
             flat = t["alpha_all"][st, rw].cpu()
         else:
             flat = torch.zeros(0, L)
-        alphas_out, it = [], iter(offs)
-        for n in range(n_img):
-            per = []
-            for _ in sel[n]:
-                o, l = next(it)
-                per.append(flat[o:o + l].reshape(l, *hw).clone())
-            alphas_out.append(per)
-    caps, scores, ppls = [], [], []
+        alphas_flat = [x.reshape(x.shape[0], *hw) for x in torch.split(flat, lens_sel.tolist())] if len(lens_sel) else []
+    caps, scores, ppls, alphas_out, j = [], [], [], ([] if want_alphas else None), 0
     for n in range(n_img):
+        m = len(sel[n])
         caps.append([toks[n, i, :int(ln[n, i])].tolist() for i in sel[n]])
         scores.append([float(sc[n, i]) for i in sel[n]])
         ppls.append([float(ppl[n, i]) for i in sel[n]])
+        if want_alphas:
+            alphas_out.append(alphas_flat[j:j + m])
+        j += m
     if not return_all:
         caps = [c[0] for c in caps]
         scores = [s[0] for s in scores]
