@@ -359,6 +359,22 @@ def _basicblock_forward(self, x):
 _FUSED_CLASSES = {}
 
 
+def _fused_class(base, fwd):
+    """subclass of a torchvision block with the fused forward, registered in this module so that modules holding it can be
+    pickled (torch.save(model)) and deep-copied"""
+    if base not in _FUSED_CLASSES:
+        cls = type("Fused" + base.__name__, (base,), {"forward": fwd, "__module__": __name__})
+        globals()[cls.__name__] = cls
+        _FUSED_CLASSES[base] = cls
+    return _FUSED_CLASSES[base]
+
+
+try:  # created at import when torchvision is present, so that a pickled module can be loaded in a fresh process
+    from torchvision.models.resnet import BasicBlock as _BasicBlock, Bottleneck as _Bottleneck
+except Exception:  # pragma: no cover
+    _BasicBlock = _Bottleneck = None
+
+
 def fuse_residual_blocks(module):
     """After convert_batchnorm: switches every torchvision Bottleneck / BasicBlock under `module` to the fused forward above,
     and a (Conv2d, CudnnBatchNorm2d, ReLU, MaxPool2d) run of an nn.Sequential (the ResNet stem) to bn+relu in one call and
@@ -368,9 +384,7 @@ def fuse_residual_blocks(module):
     for m in module.modules():
         for base, fwd, bns in ((Bottleneck, _bottleneck_forward, ("bn1", "bn2", "bn3")), (BasicBlock, _basicblock_forward, ("bn1", "bn2"))):
             if type(m) is base and type(m.relu) is nn.ReLU and all(type(getattr(m, b)) is CudnnBatchNorm2d for b in bns):
-                if base not in _FUSED_CLASSES:
-                    _FUSED_CLASSES[base] = type("Fused" + base.__name__, (base,), {"forward": fwd})
-                m.__class__ = _FUSED_CLASSES[base]
+                m.__class__ = _fused_class(base, fwd)
                 n += 1
         if isinstance(m, nn.Sequential):
             kids = list(m.named_children())
@@ -402,3 +416,8 @@ def convert_batchnorm(module):
         else:
             n += convert_batchnorm(child)
     return n
+
+
+if _Bottleneck is not None:
+    _fused_class(_Bottleneck, _bottleneck_forward)
+    _fused_class(_BasicBlock, _basicblock_forward)

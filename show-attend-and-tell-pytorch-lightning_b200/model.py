@@ -19,6 +19,8 @@ from torch.nn.utils.rnn import pack_padded_sequence
 from . import _lib, decoder
 from .packing import PackedWeights, layers_of, param_names
 
+_HELPER_STREAMS = {}      # device -> (copy stream, result read-back stream) of SAT.caption_stream
+
 try:  # PyTorch-Lightning is optional (not installed in the build image)
     import pytorch_lightning as pl
     _Base = pl.LightningModule
@@ -704,12 +706,12 @@ class SAT(_Base):
         self.eval()
         dev = self.device
         cur = torch.cuda.current_stream(dev)
-        # the two helper streams live with the module: the caching allocator keeps one pool per stream, so fresh streams per
-        # call would cudaMalloc (and implicitly synchronise) the staging buffers again every time
-        cache = self.__dict__.get("_stream_cache")
-        if cache is None or cache[0] != dev:
-            cache = self.__dict__["_stream_cache"] = (dev, torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-        copy_stream, side = cache[1], cache[2]
+        # the two helper streams are created once per device (module-level, so that the model stays deep-copyable / picklable):
+        # the caching allocator keeps one pool per stream, so fresh streams per call would cudaMalloc (and implicitly
+        # synchronise) the staging buffers again every time
+        if dev not in _HELPER_STREAMS:
+            _HELPER_STREAMS[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        copy_stream, side = _HELPER_STREAMS[dev]
 
         def stage(x):
             with torch.cuda.stream(copy_stream):

@@ -104,3 +104,20 @@ def test_encoder_boundary_swaps_keep_keys_and_cpu_results(arch):
         getattr(b, mode)()
         with torch.no_grad():
             assert torch.equal(a.encoder(x.clone()), b.encoder(x.clone())), mode
+
+
+def test_bf16_module_is_deepcopyable_and_picklable():
+    """the encoder-boundary swaps use subclasses registered in sat_b200.cudnn_bn and module-level helper streams: copy.deepcopy and
+    torch.save(model) (what PL's checkpoint / EMA / SWA utilities do) keep working"""
+    import copy
+    import io
+    from sat_b200.model import SAT
+    m = SAT(**small_hp(encoder_arch="resnet18", precision="bf16"))
+    m2 = copy.deepcopy(m)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m3 = torch.load(buf, weights_only=False)
+    for other in (m2, m3):
+        assert list(other.state_dict().keys()) == list(m.state_dict().keys())
+        assert type(other.encoder[5][0]).__name__ == "FusedBasicBlock"
