@@ -17,11 +17,14 @@ class _ResizeNHWC(torch.autograd.Function):
         _lib.check(_lib.lib().sat_resize_nhwc_fwd(x.data_ptr(), y.data_ptr(), n, h, w, H2, W2, D, _lib.dtype_code(x.dtype), _lib.stream_ptr()),
                    "sat_resize_nhwc_fwd")
         ctx.shape = (n, D, h, w, H2, W2)
+        ctx.dtype = x.dtype
         return y
 
     @staticmethod
     def backward(ctx, dy):
         n, D, h, w, H2, W2 = ctx.shape
+        if dy.dtype != ctx.dtype:
+            dy = dy.to(ctx.dtype)
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = torch.empty((n, D, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
