@@ -93,5 +93,21 @@ int main() {
     }
     printf("LDG.128 read 64 MiB (L2-resident after first pass): %.1f GB/s, %.1f us\n", small / best / 1e6, best * 1e3);
   }
+  // the same small working sets through the TMA bulk-copy ring, repeated: do bulk copies allocate / hit in L2?
+  {
+    constexpr int NST = 6, STG = 16384;
+    auto k = tma_read<NST, STG>;
+    for (size_t mb : {32, 48, 64, 96}) {
+      const int grid = 148 * 2;
+      const size_t per = ((mb << 20) / grid) / STG * STG;
+      float best = 1e9, first = 0;
+      cudaMemset(d + (512ull << 20), 2, 256ull << 20);         // push the set out of L2 first
+      for (int it = 0; it < 10; ++it) {
+        cudaEventRecord(e0); k<<<grid, 128, NST * STG>>>(d, per, o); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (it == 0) first = ms; if (ms < best) best = ms;
+      }
+      printf("TMA bulk read %zu MiB repeated: first pass %.1f us, best %.1f us = %.1f GB/s\n", mb, first * 1e3, best * 1e3, (double)per * grid / best / 1e6);
+    }
+  }
   return 0;
 }
