@@ -71,7 +71,7 @@ typedef struct SatWeights {
   const void* Wfact;   /* [E,D] s      init_lstm.factorize.weight                               */
   const float* bfact;  /* [E]                                                                   */
   const void* Winit;   /* [2H,E] s     init_lstm.init.weight                                    */
-  const float* binit;  /* [2H]                                                                  */
+  const float* binit;  /* [2*layers*H]                                                          */
   /* transposed copies, used by the backward pass only (may be NULL for inference) */
   const void* WoT;     /* [E,V] s */
   const void* WhozoT;  /* [H+D,E] s */
@@ -79,7 +79,7 @@ typedef struct SatWeights {
   const void* WiheT;   /* [E,4H] s */
   const void* WhcatT;  /* [H,A+D+4H] s  (first three row blocks of Whcat, transposed) */
   const void* WaT;     /* [D,A] s */
-  const void* WinitT;  /* [E,2H] s */
+  const void* WinitT;  /* [E,2*layers*H] s */
   const void* WfactT;  /* [D,E] s */
   /* stacked layers l = 1 .. layers-1 (index l-1): the layer's input is the new hidden state of the layer below */
   const void* Wl[SAT_MAX_LAYERS - 1];    /* [4H,2H] s   lstm.weight_ih_l{l} | lstm.weight_hh_l{l}, gate-interleaved rows   */
@@ -93,7 +93,7 @@ typedef struct SatMasterWeights {
   const float* fact_w;       /* init_lstm.factorize.weight [E,D]             */
   const float* fact_b;       /* init_lstm.factorize.bias [E]                 */
   const float* init_w;       /* init_lstm.init.weight [2H,E]                 */
-  const float* init_b;       /* init_lstm.init.bias [2H]                     */
+  const float* init_b;       /* init_lstm.init.bias [2*layers*H]            */
   const float* w_ih;         /* lstm.weight_ih_l0 [4H,E+D]                   */
   const float* w_hh;         /* lstm.weight_hh_l0 [4H,H]                     */
   const float* b_ih;         /* lstm.bias_ih_l0 [4H]                         */
@@ -180,9 +180,9 @@ typedef struct SatTrainBuffers {
   float* de;             /* [T,B,L]      scaled softmax-backward term of each step; dP is rebuilt from it, Q and P
                                           after the time loop (NULL: the slower step-by-step accumulation is used)  */
   float* dXe;            /* [T,B,E]      grad wrt embedded words                                   */
-  float* d_init_out;     /* [Bi,2H]                                                               */
+  float* d_init_out;     /* [Bi,2*layers*H]                                                       */
   float* df1;            /* [Bi,E]                                                                */
-  void* d_init_out16;    /* [Bi,2H] s    operand-dtype copies feeding the tensor-core init-path GEMMs (may be NULL: SIMT) */
+  void* d_init_out16;    /* [Bi,2*layers*H] s  operand-dtype copies feeding the tensor-core init-path GEMMs (may be NULL: SIMT) */
   void* df116;           /* [Bi,E] s                                                              */
   float* dmean;          /* [Bi,D]                                                                */
   void* d_ann;           /* [B,L,D] s    grad wrt annotations, one slab per caption row (host sums the ncap rows of an image) */
@@ -204,7 +204,7 @@ typedef struct SatDecodeBuffers {
   void* P;               /* [n_img,L,A] s                                                        */
   void* meanv;           /* [n_img,D] s                                                          */
   void* f1;              /* [n_img,E] s                                                          */
-  float* init_out;       /* [n_img,2H]                                                           */
+  float* init_out;       /* [n_img,2*layers*H]                                                   */
   const float* GxV;      /* [V,4H]  Emb * Wihe^T + bg per vocabulary entry (sat_decode_prepare_weights) */
   void* h;               /* [layers,R,H] s   state entering the step                              */
   float* c;              /* [layers,R,H]                                                          */
@@ -287,7 +287,7 @@ int sat_linear_nt(const void* A, int64_t lda, const void* B, int64_t ldb, float*
                   int32_t dtype, int32_t use_tc, int32_t splitk, void* stream);
 
 /* Once per image: P = ann * Wa^T (model.py:100), mean over L (model.py:78), factorize/init Linear
- * layers (model.py:79) and the [B,2H] -> [2,B,H] state reinterpretation (model.py:79-80) into
+ * layers (model.py:79) and the [B,2*layers*H] -> [2*layers,B,H] state reinterpretation (model.py:79-80) into
  * h0 [B,H] (s) / c0 [B,H] (fp32). */
 int sat_prepare_images(const SatDims* d, const SatWeights* w, const void* ann, void* P, void* meanv, void* f1,
                        float* init_out, void* h0, float* c0, void* stream);
