@@ -70,7 +70,7 @@ typedef struct SatWeights {
   const void* Emb;     /* [V,E] s      embedding.weight                                         */
   const void* Wfact;   /* [E,D] s      init_lstm.factorize.weight                               */
   const float* bfact;  /* [E]                                                                   */
-  const void* Winit;   /* [2H,E] s     init_lstm.init.weight                                    */
+  const void* Winit;   /* [2*layers*H,E] s  init_lstm.init.weight                               */
   const float* binit;  /* [2*layers*H]                                                          */
   /* transposed copies, used by the backward pass only (may be NULL for inference) */
   const void* WoT;     /* [E,V] s */
@@ -92,7 +92,7 @@ typedef struct SatMasterWeights {
   const float* embedding;    /* embedding.weight [V,E]                       */
   const float* fact_w;       /* init_lstm.factorize.weight [E,D]             */
   const float* fact_b;       /* init_lstm.factorize.bias [E]                 */
-  const float* init_w;       /* init_lstm.init.weight [2H,E]                 */
+  const float* init_w;       /* init_lstm.init.weight [2*layers*H,E]        */
   const float* init_b;       /* init_lstm.init.bias [2*layers*H]            */
   const float* w_ih;         /* lstm.weight_ih_l0 [4H,E+D]                   */
   const float* w_hh;         /* lstm.weight_hh_l0 [4H,H]                     */
@@ -333,7 +333,7 @@ typedef struct SatParamGrads {
   float* embedding;    /* embedding.weight [V0,E0]  (row pad_idx is zero: nn.Embedding(padding_idx), model.py:162)     */
   float* fact_w;       /* init_lstm.factorize.weight [E0,D0]   */
   float* fact_b;       /* init_lstm.factorize.bias [E0]        */
-  float* init_w;       /* init_lstm.init.weight [2H0,E0]       */
+  float* init_w;       /* init_lstm.init.weight [2*layers*H0,E0] */
   float* init_b;       /* init_lstm.init.bias [2H0]            */
   float* w_ih;         /* lstm.weight_ih_l0 [4H0,E0+D0]        */
   float* w_hh;         /* lstm.weight_hh_l0 [4H0,H0]           */
