@@ -334,7 +334,7 @@ typedef struct SatParamGrads {
   float* fact_w;       /* init_lstm.factorize.weight [E0,D0]   */
   float* fact_b;       /* init_lstm.factorize.bias [E0]        */
   float* init_w;       /* init_lstm.init.weight [2*layers*H0,E0] */
-  float* init_b;       /* init_lstm.init.bias [2H0]            */
+  float* init_b;       /* init_lstm.init.bias [2*layers*H0]   */
   float* w_ih;         /* lstm.weight_ih_l0 [4H0,E0+D0]        */
   float* w_hh;         /* lstm.weight_hh_l0 [4H0,H0]           */
   float* b_ih;         /* lstm.bias_ih_l0 [4H0]                */
